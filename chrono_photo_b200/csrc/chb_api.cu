@@ -1,0 +1,800 @@
+// chb_api.cu -- C ABI of libchrono_b200.so (see include/chrono_b200.h). Host side: contexts, the HBM-resident stack,
+// the asynchronous ingest pipeline and kernel dispatch. No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/chrono_b200.h"
+#include "chb_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace chb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static thread_local uint64_t g_last_slow = 0;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t e__ = (call);                                                                                 \
+        if (e__ != cudaSuccess) return fail(CHB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* chb_last_error(void) { return g_err.c_str(); }
+extern "C" int chb_version(void) { return CHB_VERSION; }
+extern "C" uint64_t chb_launch_count(void) { return g_launches.load(); }
+extern "C" void chb_launch_count_reset(void) { g_launches.store(0); }
+extern "C" uint64_t chb_last_slow_pixels(void) { return g_last_slow; }
+
+// ------------------------------------------------------------------------------------------------ objects
+struct Dev {
+    int id = 0;
+    int sm_count = 148;
+    cudaStream_t compute = nullptr, own_compute = nullptr, copy = nullptr, pack = nullptr;
+};
+struct chb_ctx {
+    std::vector<Dev> devs;
+};
+
+struct Band {
+    int dev_slot = 0;
+    int row0 = 0, rows = 0;
+    long long n_pixels = 0, n_tiles = 0;
+    size_t stack_bytes = 0, frame_bytes = 0;
+    uint8_t* d_stack = nullptr;
+    uint8_t* d_out = nullptr;
+    uint8_t* d_mask = nullptr;
+    // ingest: two device staging frames + two pinned host staging frames
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr};  // H2D into d_stage[s] done
+    cudaEvent_t packed[2] = {nullptr, nullptr};  // pack kernel reading d_stage[s] done
+    bool h_busy[2] = {false, false};
+    int next_slot = 0;
+    // per-call scratch
+    uint32_t* d_wmask = nullptr;
+    uint32_t* d_smask = nullptr;
+    int32_t* d_win = nullptr;
+    int32_t* d_posg = nullptr;
+    float* d_fade = nullptr;
+    unsigned long long* d_counters = nullptr;
+    float *d_dbg_median = nullptr, *d_dbg_q1 = nullptr, *d_dbg_q3 = nullptr;
+    int* d_dbg_nout = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct chb_stack {
+    chb_ctx* ctx = nullptr;
+    int W = 0, H = 0, C = 0, N = 0, NG = 0;
+    std::vector<Band> bands;
+    std::vector<uint8_t> uploaded;  // per frame
+    std::mutex upload_mu, call_mu;
+    // pinned host scratch for per-call tables
+    uint32_t* h_wmask = nullptr;
+    uint32_t* h_smask = nullptr;
+    int32_t* h_win = nullptr;
+    int32_t* h_posg = nullptr;
+    float* h_fade = nullptr;
+    unsigned long long* h_counters = nullptr;  // [n_bands * 2]
+    bool last_has_mask = false;
+    uint64_t last_warnings = 0;
+};
+
+static constexpr int kMaxWindowFrames = 4096;  // largest window span the register-resident kernels hold
+static constexpr int kMaxGroupsTable = kMaxWindowFrames / 16;
+
+// ------------------------------------------------------------------------------------------------ context
+extern "C" int chb_ctx_create(const int* device_ids, int n_dev, chb_ctx** out) {
+    if (!out) return fail(CHB_ERR_INVALID, "chb_ctx_create: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(CHB_ERR_CUDA, "chb_ctx_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    std::vector<int> ids;
+    if (!device_ids || n_dev <= 0) ids.push_back(0);
+    else ids.assign(device_ids, device_ids + n_dev);
+    chb_ctx* ctx = new chb_ctx();
+    for (int id : ids) {
+        if (id < 0 || id >= count) {
+            delete ctx;
+            return fail(CHB_ERR_INVALID, "chb_ctx_create: device %d out of range (have %d)", id, count);
+        }
+        Dev d;
+        d.id = id;
+        CU(cudaSetDevice(id));
+        cudaDeviceProp pr;
+        CU(cudaGetDeviceProperties(&pr, id));
+        if (pr.major < 10) {
+            delete ctx;
+            return fail(CHB_ERR_UNSUPPORTED, "chb_ctx_create: device %d is sm_%d%d; this build carries sm_100a code only", id, pr.major, pr.minor);
+        }
+        d.sm_count = pr.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&d.own_compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&d.pack, cudaStreamNonBlocking));
+        d.compute = d.own_compute;
+        ctx->devs.push_back(d);
+    }
+    *out = ctx;
+    return CHB_OK;
+}
+
+extern "C" int chb_ctx_destroy(chb_ctx* ctx) {
+    if (!ctx) return CHB_OK;
+    for (Dev& d : ctx->devs) {
+        cudaSetDevice(d.id);
+        cudaStreamDestroy(d.own_compute);
+        cudaStreamDestroy(d.copy);
+        cudaStreamDestroy(d.pack);
+    }
+    delete ctx;
+    return CHB_OK;
+}
+
+extern "C" int chb_ctx_device_count(const chb_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+extern "C" int chb_ctx_set_stream(chb_ctx* ctx, int dev_slot, void* cuda_stream) {
+    if (!ctx || dev_slot < 0 || dev_slot >= (int)ctx->devs.size()) return fail(CHB_ERR_INVALID, "chb_ctx_set_stream: bad device slot");
+    Dev& d = ctx->devs[dev_slot];
+    d.compute = cuda_stream ? (cudaStream_t)cuda_stream : d.own_compute;
+    return CHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stack
+static void free_band(Band& b) {
+    cudaFree(b.d_stack); cudaFree(b.d_out); cudaFree(b.d_mask);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(b.d_stage[s]);
+        if (b.h_stage[s]) cudaFreeHost(b.h_stage[s]);
+        if (b.copied[s]) cudaEventDestroy(b.copied[s]);
+        if (b.packed[s]) cudaEventDestroy(b.packed[s]);
+    }
+    cudaFree(b.d_wmask); cudaFree(b.d_smask); cudaFree(b.d_win); cudaFree(b.d_posg); cudaFree(b.d_fade); cudaFree(b.d_counters);
+    cudaFree(b.d_dbg_median); cudaFree(b.d_dbg_q1); cudaFree(b.d_dbg_q3); cudaFree(b.d_dbg_nout);
+    if (b.ev0) cudaEventDestroy(b.ev0);
+    if (b.ev1) cudaEventDestroy(b.ev1);
+}
+
+extern "C" int chb_stack_destroy(chb_stack* st) {
+    if (!st) return CHB_OK;
+    for (Band& b : st->bands) {
+        cudaSetDevice(st->ctx->devs[b.dev_slot].id);
+        cudaDeviceSynchronize();
+        free_band(b);
+    }
+    if (st->h_wmask) cudaFreeHost(st->h_wmask);
+    if (st->h_smask) cudaFreeHost(st->h_smask);
+    if (st->h_win) cudaFreeHost(st->h_win);
+    if (st->h_posg) cudaFreeHost(st->h_posg);
+    if (st->h_fade) cudaFreeHost(st->h_fade);
+    if (st->h_counters) cudaFreeHost(st->h_counters);
+    delete st;
+    return CHB_OK;
+}
+
+extern "C" int chb_stack_create(chb_ctx* ctx, int width, int height, int channels, int n_frames, chb_stack** out) {
+    if (!ctx || !out) return fail(CHB_ERR_INVALID, "chb_stack_create: null argument");
+    if (width < 1 || height < 1 || n_frames < 1) return fail(CHB_ERR_INVALID, "chb_stack_create: width, height and n_frames must be positive");
+    if (channels != 3 && channels != 4)
+        return fail(CHB_ERR_UNSUPPORTED, "chb_stack_create: %d channels; the reference only writes Rgb8/Rgba8 (src/main.rs:550-567)", channels);
+    chb_stack* st = new chb_stack();
+    st->ctx = ctx;
+    st->W = width; st->H = height; st->C = channels; st->N = n_frames;
+    st->NG = (n_frames + kGroupFrames - 1) / kGroupFrames;
+    st->uploaded.assign(n_frames, 0);
+    const int nd = std::min<int>((int)ctx->devs.size(), height);
+    auto bail = [&](int code) { chb_stack_destroy(st); return code; };
+#define CUB(call)                                                                                                   \
+    do {                                                                                                            \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess) return bail(fail(CHB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    } while (0)
+    CUB(cudaMallocHost(&st->h_wmask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+    CUB(cudaMallocHost(&st->h_smask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+    CUB(cudaMallocHost(&st->h_win, sizeof(int32_t) * (size_t)std::max(n_frames, 1)));
+    CUB(cudaMallocHost(&st->h_posg, sizeof(int32_t) * (size_t)st->NG));
+    CUB(cudaMallocHost(&st->h_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
+    CUB(cudaMallocHost(&st->h_counters, sizeof(unsigned long long) * 2 * nd));
+    st->bands.resize(nd);
+    for (int k = 0; k < nd; k++) {
+        Band& b = st->bands[k];
+        b.dev_slot = k;
+        b.row0 = (int)((long long)height * k / nd);  // row shard: GPU k owns rows [H*k/G, H*(k+1)/G)
+        b.rows = (int)((long long)height * (k + 1) / nd) - b.row0;
+        b.n_pixels = (long long)b.rows * width;
+        b.n_tiles = (b.n_pixels + kTilePixels - 1) / kTilePixels;
+        b.stack_bytes = (size_t)(b.n_tiles * tile_bytes(channels, st->NG));
+        b.frame_bytes = (size_t)b.n_pixels * channels;
+        CUB(cudaSetDevice(ctx->devs[k].id));
+        CUB(cudaMalloc(&b.d_stack, b.stack_bytes));
+        CUB(cudaMemset(b.d_stack, 0, b.stack_bytes));  // frames beyond n_frames in the last group must read as zero
+        CUB(cudaMalloc(&b.d_out, b.frame_bytes));
+        CUB(cudaMalloc(&b.d_mask, b.frame_bytes));
+        for (int s = 0; s < 2; s++) {
+            CUB(cudaMalloc(&b.d_stage[s], b.frame_bytes));
+            CUB(cudaEventCreateWithFlags(&b.copied[s], cudaEventDisableTiming));
+            CUB(cudaEventCreateWithFlags(&b.packed[s], cudaEventDisableTiming));
+        }
+        CUB(cudaMalloc(&b.d_wmask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+        CUB(cudaMalloc(&b.d_smask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+        CUB(cudaMalloc(&b.d_win, sizeof(int32_t) * (size_t)n_frames));
+        CUB(cudaMalloc(&b.d_posg, sizeof(int32_t) * (size_t)st->NG));
+        CUB(cudaMalloc(&b.d_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
+        CUB(cudaMalloc(&b.d_counters, sizeof(unsigned long long) * 2));
+        CUB(cudaEventCreate(&b.ev0));
+        CUB(cudaEventCreate(&b.ev1));
+        CUB(cudaDeviceSynchronize());
+    }
+#undef CUB
+    *out = st;
+    return CHB_OK;
+}
+
+extern "C" size_t chb_stack_device_bytes(const chb_stack* st, int dev_slot) {
+    if (!st || dev_slot < 0 || dev_slot >= (int)st->bands.size()) return 0;
+    return st->bands[dev_slot].stack_bytes;
+}
+
+static int grid_for(long long work_items, int threads, int sm_count, int waves) {
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)sm_count * waves;
+    return (int)std::max<long long>(1, std::min(blocks, cap));
+}
+
+// Ingest of one frame into every band. `pinned`: the source can be DMA'd directly.
+static int upload_impl(chb_stack* st, int frame_idx, const uint8_t* host, size_t pitch, int crop_x, int crop_y, bool pinned) {
+    if (!st || !host) return fail(CHB_ERR_INVALID, "chb_stack_upload: null argument");
+    if (frame_idx < 0 || frame_idx >= st->N) return fail(CHB_ERR_INVALID, "chb_stack_upload: frame %d outside [0, %d)", frame_idx, st->N);
+    if (crop_x < 0 || crop_y < 0) return fail(CHB_ERR_INVALID, "chb_stack_upload: negative crop origin");
+    const size_t row_bytes = (size_t)st->W * st->C;
+    if (pitch < row_bytes + (size_t)crop_x * st->C) return fail(CHB_ERR_INVALID, "chb_stack_upload: row pitch %zu too small", pitch);
+    std::lock_guard<std::mutex> lk(st->upload_mu);
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        const int s = b.next_slot;
+        b.next_slot ^= 1;
+        const uint8_t* src = host + (size_t)(crop_y + b.row0) * pitch + (size_t)crop_x * st->C;
+        // the pack kernel that last read d_stage[s] must be done before the copy overwrites it
+        CU(cudaStreamWaitEvent(d.copy, b.packed[s], 0));
+        if (pinned) {
+            if (pitch == row_bytes) CU(cudaMemcpyAsync(b.d_stage[s], src, b.frame_bytes, cudaMemcpyHostToDevice, d.copy));
+            else CU(cudaMemcpy2DAsync(b.d_stage[s], row_bytes, src, pitch, row_bytes, (size_t)b.rows, cudaMemcpyHostToDevice, d.copy));
+        } else {
+            if (!b.h_stage[s]) CU(cudaMallocHost(&b.h_stage[s], b.frame_bytes));
+            if (b.h_busy[s]) CU(cudaEventSynchronize(b.copied[s]));  // previous DMA out of this pinned slot
+            if (pitch == row_bytes) memcpy(b.h_stage[s], src, b.frame_bytes);
+            else
+                for (int r = 0; r < b.rows; r++) memcpy(b.h_stage[s] + (size_t)r * row_bytes, src + (size_t)r * pitch, row_bytes);
+            CU(cudaMemcpyAsync(b.d_stage[s], b.h_stage[s], b.frame_bytes, cudaMemcpyHostToDevice, d.copy));
+            b.h_busy[s] = true;
+        }
+        CU(cudaEventRecord(b.copied[s], d.copy));
+        CU(cudaStreamWaitEvent(d.pack, b.copied[s], 0));
+        pack_frame_kernel<<<grid_for(b.n_pixels, 256, d.sm_count, 8), 256, 0, d.pack>>>(b.d_stage[s], b.d_stack, b.n_pixels, st->C, st->NG, frame_idx);
+        g_launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(b.packed[s], d.pack));
+    }
+    st->uploaded[frame_idx] = 1;
+    return CHB_OK;
+}
+
+extern "C" int chb_stack_upload(chb_stack* st, int frame_idx, const uint8_t* host_pixels, size_t row_pitch, int crop_x, int crop_y) {
+    return upload_impl(st, frame_idx, host_pixels, row_pitch, crop_x, crop_y, false);
+}
+extern "C" int chb_stack_upload_pinned(chb_stack* st, int frame_idx, const uint8_t* pinned_pixels, size_t row_pitch, int crop_x, int crop_y) {
+    return upload_impl(st, frame_idx, pinned_pixels, row_pitch, crop_x, crop_y, true);
+}
+
+extern "C" int chb_stack_sync(chb_stack* st) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_stack_sync: null stack");
+    std::lock_guard<std::mutex> lk(st->upload_mu);
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.copy));
+        CU(cudaStreamSynchronize(d.pack));
+    }
+    return CHB_OK;
+}
+
+extern "C" int chb_stack_fill_synthetic(chb_stack* st, int kind, uint64_t seed, int row0_global, int full_height) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_stack_fill_synthetic: null stack");
+    if (kind < 1 || kind > 4) return fail(CHB_ERR_INVALID, "chb_stack_fill_synthetic: unknown kind %d", kind);
+    std::lock_guard<std::mutex> lk(st->upload_mu);
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        const long long units = b.n_tiles * st->C * st->NG * kTilePixels;
+        synth_fill_kernel<<<grid_for(units, 256, d.sm_count, 16), 256, 0, d.pack>>>(b.d_stack, b.n_pixels, b.n_tiles, st->C, st->NG, st->N, kind,
+                                                                                   (unsigned long long)seed, st->W, row0_global + b.row0, full_height);
+        g_launches++;
+        CU(cudaGetLastError());
+    }
+    for (Band& b : st->bands) {
+        CU(cudaSetDevice(st->ctx->devs[b.dev_slot].id));
+        CU(cudaStreamSynchronize(st->ctx->devs[b.dev_slot].pack));
+    }
+    std::fill(st->uploaded.begin(), st->uploaded.end(), 1);
+    return CHB_OK;
+}
+
+extern "C" int chb_synth_frame_host(int kind, uint64_t seed, int frame_idx, int n_frames, int width, int full_height, int channels,
+                                    int row0, int rows, uint8_t* out) {
+    if (!out || kind < 1 || kind > 4 || width < 1 || rows < 0 || channels < 1 || channels > 4) return fail(CHB_ERR_INVALID, "chb_synth_frame_host: bad argument");
+    for (int r = 0; r < rows; r++)
+        for (int x = 0; x < width; x++)
+            for (int c = 0; c < channels; c++)
+                out[((size_t)r * width + x) * channels + c] = synth_byte(kind, seed, frame_idx, n_frames, row0 + r, x, c, width, full_height);
+    return CHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ window tables
+struct Window {
+    std::vector<int32_t> frames;  // position -> frame
+    int g0 = 0, n_groups = 0;
+};
+
+static int build_window(chb_stack* st, const int32_t* indices, int n_indices, Window& w, const char* who) {
+    if (indices) {
+        if (n_indices < 1) return fail(CHB_ERR_INVALID, "%s: empty window", who);
+        w.frames.assign(indices, indices + n_indices);
+        for (int i = 0; i < n_indices; i++) {
+            if (indices[i] < 0 || indices[i] >= st->N) return fail(CHB_ERR_INVALID, "%s: frame index %d outside [0, %d)", who, indices[i], st->N);
+            if (i > 0 && indices[i] <= indices[i - 1]) return fail(CHB_ERR_INVALID, "%s: window indices must be strictly ascending (src/chrono.rs:113-139)", who);
+        }
+    } else {
+        w.frames.resize(st->N);
+        for (int i = 0; i < st->N; i++) w.frames[i] = i;
+    }
+    for (int f : w.frames)
+        if (!st->uploaded[f]) return fail(CHB_ERR_STATE, "%s: frame %d of the window has not been uploaded", who, f);
+    w.g0 = w.frames.front() / kGroupFrames;
+    w.n_groups = w.frames.back() / kGroupFrames - w.g0 + 1;
+    return CHB_OK;
+}
+
+static void byte_masks(const std::vector<int32_t>& frames, int g0, int cap_groups, uint32_t* out) {
+    memset(out, 0, sizeof(uint32_t) * (size_t)cap_groups * 4);
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(out);
+    for (int f : frames) bytes[f - g0 * kGroupFrames] = 0xFF;
+}
+
+// deterministic replacement of rand::seq::sample_indices (src/chrono.rs:157): cnt distinct positions of [0, n), ascending
+static void sample_positions(uint64_t seed, int n, int cnt, std::vector<int32_t>& out) {
+    std::vector<int32_t> perm(n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    for (int i = 0; i < cnt; i++) {
+        int jx = i + (int)rng_range(seed ^ 0x5AFEC0DE5EEDULL, (uint64_t)i, 1, (uint32_t)(n - i));
+        std::swap(perm[i], perm[jx]);
+    }
+    out.assign(perm.begin(), perm.begin() + cnt);
+    std::sort(out.begin(), out.end());
+}
+
+extern "C" int chb_sample_positions(uint64_t seed, int n, int cnt, int32_t* out) {
+    if (!out || n < 1 || cnt < 1 || cnt > n) return fail(CHB_ERR_INVALID, "chb_sample_positions: bad argument");
+    std::vector<int32_t> v;
+    sample_positions(seed, n, cnt, v);
+    memcpy(out, v.data(), sizeof(int32_t) * (size_t)cnt);
+    return CHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 dispatch
+typedef void (*OutlierKernel)(const OutlierArgs);
+struct Variant { int wpl, g; };
+// capacity (frames) = 16 * wpl * g
+static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {7, 2}, {8, 2}, {8, 4}, {8, 8}, {8, 16}, {8, 32}};
+static constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+template <int C, bool SUB>
+static OutlierKernel kernel_for(int v) {
+    switch (v) {
+        case 0: return outlier_kernel<C, 1, 1, SUB>;
+        case 1: return outlier_kernel<C, 2, 1, SUB>;
+        case 2: return outlier_kernel<C, 4, 1, SUB>;
+        case 3: return outlier_kernel<C, 4, 2, SUB>;
+        case 4: return outlier_kernel<C, 7, 2, SUB>;
+        case 5: return outlier_kernel<C, 8, 2, SUB>;
+        case 6: return outlier_kernel<C, 8, 4, SUB>;
+        case 7: return outlier_kernel<C, 8, 8, SUB>;
+        case 8: return outlier_kernel<C, 8, 16, SUB>;
+        default: return outlier_kernel<C, 8, 32, SUB>;
+    }
+}
+
+static void quantile_ranks(int len, float q, int& r0, int& r1, float& frac) {  // src/chrono.rs:568-579
+    float pos = (float)(len + 1) * q;
+    int p1 = (int)pos - 1;
+    float fr = pos - truncf(pos);
+    if (fr < 0.001f) { r0 = r1 = p1; frac = 0.0f; }
+    else if (fr > 0.999f) { r0 = r1 = p1 + 1; frac = 0.0f; }
+    else { r0 = p1; r1 = p1 + 1; frac = fr; }
+}
+
+static int fade_to_dev(const chb_fade& f, FadeDev& out, const char* who) {
+    out.is_none = f.is_none ? 1 : 0;
+    out.mode = f.mode;
+    out.absolute = f.absolute ? 1 : 0;
+    out.offset = f.offset;
+    out.n_values = f.n_values;
+    out.values = nullptr;
+    if (!f.is_none) {
+        if (f.n_values < 1 || f.n_values > CHB_MAX_FADE_VALUES || !f.values) return fail(CHB_ERR_INVALID, "%s: fade needs 1..%d values", who, CHB_MAX_FADE_VALUES);
+        if (f.mode != CHB_FADE_CLAMP && f.mode != CHB_FADE_REPEAT) return fail(CHB_ERR_INVALID, "%s: unknown fade mode", who);
+    }
+    return CHB_OK;
+}
+
+static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, bool want_mask,
+                        const chb_debug_planes* dbg, float* kernel_ms) {
+    if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_outlier: null argument");
+    if (prm->background > CHB_BG_MEDIAN || prm->outlier > CHB_OUT_BACKWARD) return fail(CHB_ERR_INVALID, "chb_outlier: unknown background / outlier mode");
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    Window win;
+    int rc = build_window(st, indices, n_indices, win, "chb_outlier");
+    if (rc) return rc;
+    const int n = (int)win.frames.size();
+    // --sample (src/chrono.rs:151-163)
+    std::vector<int32_t> spos;
+    bool sub = false;
+    if (prm->sample_count >= 0) {
+        if (prm->sample_count == 0) return fail(CHB_ERR_INVALID, "chb_outlier: --sample 0 (the reference panics on an empty sample)");
+        if (prm->sample_count < n) {
+            sample_positions(prm->seed, n, prm->sample_count, spos);
+            sub = true;
+        }
+    }
+    const int n_sub = sub ? (int)spos.size() : n;
+    if (!prm->thr_absolute && n_sub < 3)
+        return fail(CHB_ERR_INVALID, "chb_outlier: relative thresholds need at least 3 samples (quantile() underflows, src/chrono.rs:569-570)");
+    int vidx = -1;
+    for (int v = 0; v < kNumVariants; v++)
+        if (kVariants[v].wpl * kVariants[v].g >= win.n_groups) { vidx = v; break; }
+    if (vidx < 0)
+        return fail(CHB_ERR_UNSUPPORTED, "chb_outlier: window spans %d frames; this build holds at most %d per launch", win.n_groups * 16, kMaxWindowFrames);
+    const Variant var = kVariants[vidx];
+    const int cap_groups = var.wpl * var.g;
+
+    OutlierArgs a;
+    memset(&a, 0, sizeof a);
+    a.NG = st->NG; a.C = st->C;
+    a.g0 = win.g0; a.n_groups = win.n_groups;
+    a.n = n; a.n_sub = n_sub;
+    a.inv_n_sub = 1.0f / (float)n_sub;
+    // median ranks (src/chrono.rs:582-591)
+    if ((n_sub + 1) % 2 == 0) a.rk[2] = a.rk[3] = (n_sub + 1) / 2 - 1;
+    else { a.rk[2] = (n_sub + 1) / 2 - 1; a.rk[3] = (n_sub + 1) / 2; }
+    if (!prm->thr_absolute) {
+        quantile_ranks(n_sub, 0.25f, a.rk[0], a.rk[1], a.q1_frac);
+        quantile_ranks(n_sub, 0.75f, a.rk[4], a.rk[5], a.q3_frac);
+    }
+    a.absolute = prm->thr_absolute ? 1 : 0;
+    a.thr_min = prm->thr_min; a.thr_max = prm->thr_max; a.thr_scale = prm->thr_scale;
+    a.thr_sq = prm->thr_min * prm->thr_min;  // src/chrono.rs:220
+    for (int i = 0; i < 4; i++) a.w[i] = prm->weights[i];
+    a.bg = prm->background; a.om = prm->outlier;
+    rc = fade_to_dev(prm->fade, a.fade, "chb_outlier");
+    if (rc) return rc;
+    a.frame_offset = indices ? indices[0] : 0;  // src/chrono.rs:102-103
+    a.seed = prm->seed;
+
+    // host tables
+    byte_masks(win.frames, win.g0, cap_groups, st->h_wmask);
+    unsigned patch = 0;
+    for (int i = 0; i < var.wpl; i++)
+        for (int jx = 0; jx < var.g; jx++) {
+            const uint32_t* m = st->h_wmask + (size_t)(i * var.g + jx) * 4;
+            if ((m[0] & m[1] & m[2] & m[3]) != 0xffffffffu) patch |= 1u << i;
+        }
+    a.patch_slots = patch;
+    if (sub) {
+        std::vector<int32_t> sframes(spos.size());
+        for (size_t i = 0; i < spos.size(); i++) sframes[i] = win.frames[spos[i]];
+        byte_masks(sframes, win.g0, cap_groups, st->h_smask);
+    }
+    memcpy(st->h_win, win.frames.data(), sizeof(int32_t) * (size_t)n);
+    if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
+
+    OutlierKernel kern;
+    if (st->C == 3) kern = sub ? kernel_for<3, true>(vidx) : kernel_for<3, false>(vidx);
+    else kern = sub ? kernel_for<4, true>(vidx) : kernel_for<4, false>(vidx);
+
+    const size_t P = (size_t)st->W * st->H;
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        cudaStream_t s = d.compute;
+        CU(cudaMemcpyAsync(b.d_wmask, st->h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
+        if (sub) CU(cudaMemcpyAsync(b.d_smask, st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b.d_win, st->h_win, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 2, s));
+        OutlierArgs ab = a;
+        ab.stack = b.d_stack;
+        ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
+        ab.wmask = b.d_wmask; ab.smask = b.d_smask; ab.win_frames = b.d_win;
+        ab.fade.values = b.d_fade;
+        ab.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
+        ab.out_image = b.d_out;
+        ab.out_mask = want_mask ? b.d_mask : nullptr;
+        ab.counters = b.d_counters;
+        if (dbg) {
+            if (dbg->median && !b.d_dbg_median) CU(cudaMalloc(&b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (dbg->q1 && !b.d_dbg_q1) CU(cudaMalloc(&b.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (dbg->q3 && !b.d_dbg_q3) CU(cudaMalloc(&b.d_dbg_q3, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (dbg->n_outliers && !b.d_dbg_nout) CU(cudaMalloc(&b.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels));
+            // the median plane drives the other debug stores inside the kernel
+            if (!b.d_dbg_median && (dbg->q1 || dbg->q3)) CU(cudaMalloc(&b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
+            ab.dbg_median = b.d_dbg_median;
+            ab.dbg_q1 = dbg->q1 ? b.d_dbg_q1 : nullptr;
+            ab.dbg_q3 = dbg->q3 ? b.d_dbg_q3 : nullptr;
+            ab.dbg_nout = dbg->n_outliers ? b.d_dbg_nout : nullptr;
+        }
+        const long long n_tasks = b.n_tiles * var.g;
+        const int blocks = grid_for(n_tasks * 32, 256, d.sm_count, 64);
+        CU(cudaEventRecord(b.ev0, s));
+        kern<<<blocks, 256, 0, s>>>(ab);
+        g_launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(b.ev1, s));
+        CU(cudaMemcpyAsync(st->h_counters + 2 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
+    }
+    float ms_max = 0.0f;
+    uint64_t warnings = 0, slow = 0;
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.compute));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
+        ms_max = std::max(ms_max, ms);
+        warnings += st->h_counters[2 * b.dev_slot];
+        slow += st->h_counters[2 * b.dev_slot + 1];
+        if (dbg) {
+            const size_t off = (size_t)b.row0 * st->W;
+            if (dbg->median) CU(cudaMemcpy(dbg->median + off * 4, b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+            if (dbg->q1) CU(cudaMemcpy(dbg->q1 + off * 4, b.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+            if (dbg->q3) CU(cudaMemcpy(dbg->q3 + off * 4, b.d_dbg_q3, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+            if (dbg->n_outliers) CU(cudaMemcpy(dbg->n_outliers + off, b.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+        }
+    }
+    (void)P;
+    if (kernel_ms) *kernel_ms = ms_max;
+    st->last_has_mask = want_mask;
+    st->last_warnings = warnings;
+    g_last_slow = slow;
+    return CHB_OK;
+}
+
+static int fetch_impl(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        const size_t off = (size_t)b.row0 * st->W * st->C;
+        if (out_image) CU(cudaMemcpyAsync(out_image + off, b.d_out, b.frame_bytes, cudaMemcpyDeviceToHost, d.compute));
+        if (out_mask) {
+            if (!st->last_has_mask) return fail(CHB_ERR_STATE, "chb_fetch_last: the last call did not produce a mask");
+            CU(cudaMemcpyAsync(out_mask + off, b.d_mask, b.frame_bytes, cudaMemcpyDeviceToHost, d.compute));
+        }
+    }
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.compute));
+    }
+    if (n_warnings) *n_warnings = st->last_warnings;
+    return CHB_OK;
+}
+
+extern "C" int chb_outlier_debug(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, uint8_t* out_image,
+                                 uint8_t* out_mask, uint64_t* n_warnings, const chb_debug_planes* dbg) {
+    if (!out_image) return fail(CHB_ERR_INVALID, "chb_outlier: out_image is null");
+    int rc = chb_stack_sync(st);
+    if (rc) return rc;
+    rc = outlier_impl(st, prm, indices, n_indices, out_mask != nullptr, dbg, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    return fetch_impl(st, out_image, out_mask, n_warnings);
+}
+extern "C" int chb_outlier(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, uint8_t* out_image,
+                           uint8_t* out_mask, uint64_t* n_warnings) {
+    return chb_outlier_debug(st, prm, indices, n_indices, out_image, out_mask, n_warnings, nullptr);
+}
+extern "C" int chb_outlier_device(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, int want_mask, float* kernel_ms) {
+    return outlier_impl(st, prm, indices, n_indices, want_mask != 0, nullptr, kernel_ms);
+}
+extern "C" int chb_fetch_last(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_fetch_last: null stack");
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    return fetch_impl(st, out_image, out_mask, n_warnings);
+}
+
+// ------------------------------------------------------------------------------------------------ K2 dispatch
+static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, float* kernel_ms) {
+    if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_simple: null argument");
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    Window win;
+    // SimpleProcessor accepts any index order in principle (src/simple.rs:142-146), but every caller passes ascending
+    // windows (src/main.rs:398-404); the time-sliced stack relies on it.
+    int rc = build_window(st, indices, n_indices, win, "chb_simple");
+    if (rc) return rc;
+    const int n = (int)win.frames.size();
+    SimpleArgs a;
+    memset(&a, 0, sizeof a);
+    a.NG = st->NG; a.C = st->C;
+    a.g0 = win.g0; a.n_groups = win.n_groups;
+    a.n = n;
+    a.darker = prm->darker ? 1 : 0;
+    for (int i = 0; i < 4; i++) a.w[i] = prm->weights[i];
+    rc = fade_to_dev(prm->fade, a.fade, "chb_simple");
+    if (rc) return rc;
+    a.frame_offset = indices ? indices[0] : 0;  // src/simple.rs:54-57
+    const bool fade = !prm->fade.is_none;
+    std::vector<uint32_t> masks((size_t)win.n_groups * 4);
+    byte_masks(win.frames, win.g0, win.n_groups, masks.data());
+    bool all_in = true;
+    for (uint32_t m : masks) all_in = all_in && (m == 0xffffffffu);
+    std::vector<int32_t> posg(win.n_groups, 0);
+    {
+        size_t k = 0;
+        for (int gi = 0; gi < win.n_groups; gi++) {
+            while (k < win.frames.size() && win.frames[k] < (win.g0 + gi) * kGroupFrames) k++;
+            posg[gi] = (int32_t)k;
+        }
+    }
+    if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
+    memcpy(st->h_posg, posg.data(), sizeof(int32_t) * posg.size());
+    std::vector<uint32_t*> tmp_masks;
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        cudaStream_t s = d.compute;
+        SimpleArgs ab = a;
+        ab.stack = b.d_stack;
+        ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
+        ab.wmask = nullptr;
+        if (!all_in) {
+            uint32_t* dm = nullptr;
+            if (win.n_groups <= kMaxGroupsTable) dm = b.d_wmask;
+            else { CU(cudaMalloc(&dm, sizeof(uint32_t) * masks.size())); tmp_masks.push_back(dm); }
+            CU(cudaMemcpyAsync(dm, masks.data(), sizeof(uint32_t) * masks.size(), cudaMemcpyHostToDevice, s));
+            ab.wmask = dm;
+        }
+        CU(cudaMemcpyAsync(b.d_posg, st->h_posg, sizeof(int32_t) * posg.size(), cudaMemcpyHostToDevice, s));
+        ab.pos_of_group = b.d_posg;
+        if (fade) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+        ab.fade.values = b.d_fade;
+        ab.out_image = b.d_out;
+        const int blocks = grid_for(b.n_tiles * kTilePixels, 256, d.sm_count, 64);
+        CU(cudaEventRecord(b.ev0, s));
+        if (st->C == 3) {
+            if (fade) simple_kernel<3, true><<<blocks, 256, 0, s>>>(ab);
+            else simple_kernel<3, false><<<blocks, 256, 0, s>>>(ab);
+        } else {
+            if (fade) simple_kernel<4, true><<<blocks, 256, 0, s>>>(ab);
+            else simple_kernel<4, false><<<blocks, 256, 0, s>>>(ab);
+        }
+        g_launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(b.ev1, s));
+    }
+    float ms_max = 0.0f;
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.compute));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
+        ms_max = std::max(ms_max, ms);
+    }
+    for (uint32_t* p : tmp_masks) cudaFree(p);
+    if (kernel_ms) *kernel_ms = ms_max;
+    st->last_has_mask = false;
+    st->last_warnings = 0;
+    return CHB_OK;
+}
+
+extern "C" int chb_simple(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, uint8_t* out_image) {
+    if (!out_image) return fail(CHB_ERR_INVALID, "chb_simple: out_image is null");
+    int rc = chb_stack_sync(st);
+    if (rc) return rc;
+    rc = simple_impl(st, prm, indices, n_indices, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    return fetch_impl(st, out_image, nullptr, nullptr);
+}
+extern "C" int chb_simple_device(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, float* kernel_ms) {
+    return simple_impl(st, prm, indices, n_indices, kernel_ms);
+}
+
+// ------------------------------------------------------------------------------------------------ host arithmetic
+extern "C" void chb_threshold_new(int absolute, float min, float max, float* out_min, float* out_max, float* out_scale) {
+    // Threshold::new, src/options.rs:197-213 (f32 throughout)
+    if (absolute) {
+        *out_min = min * 255.0f;
+        *out_max = max * 255.0f;
+        *out_scale = 1.0f / ((max - min) * 255.0f);
+    } else {
+        *out_min = min;
+        *out_max = max;
+        *out_scale = 1.0f / (max - min);
+    }
+}
+
+extern "C" int chb_fade_build(const int32_t* frames, const float* values, int n_pairs, float* out_values, int out_cap, int32_t* out_offset) {
+    // Fade::new, src/options.rs:69-94
+    if (!frames || !values || !out_values || !out_offset) return -1;
+    if (n_pairs < 2) return -1;  // "Fade requires at least two frames specified."
+    const int32_t offset = frames[0];
+    const int32_t len = frames[n_pairs - 1] - offset;
+    if (len < 0 || len + 1 > out_cap) return -1;
+    int idx = 0;
+    for (int32_t i = 0; i <= len; i++) {
+        if (idx + 1 >= n_pairs) return -1;
+        const int32_t f1 = frames[idx], f2 = frames[idx + 1];
+        const float v1 = values[idx], v2 = values[idx + 1];
+        const int32_t frame = i + offset;
+        out_values[i] = v1 + (v2 - v1) * (float)(frame - f1) / (float)(f2 - f1);
+        if (frame == f2 && idx + 2 < n_pairs) idx++;
+    }
+    *out_offset = offset;
+    return len + 1;
+}
+
+extern "C" int chb_crop_create(const int32_t* off, int n, int width, int height, int32_t* out_xy, int32_t* out_w, int32_t* out_h) {
+    // Crop::create, src/shake.rs:136-176
+    int32_t xmin = 0, ymin = 0, xmax = 0, ymax = 0;
+    for (int i = 0; i < n; i++) {
+        xmin = std::min(xmin, off[2 * i]); xmax = std::max(xmax, off[2 * i]);
+        ymin = std::min(ymin, off[2 * i + 1]); ymax = std::max(ymax, off[2 * i + 1]);
+    }
+    if (xmin == 0 && ymin == 0 && xmax == 0 && ymax == 0) return 0;
+    *out_w = width + xmin - xmax;
+    *out_h = height + ymin - ymax;
+    for (int i = 0; i < n; i++) {
+        out_xy[2 * i] = -xmin + off[2 * i];
+        out_xy[2 * i + 1] = -ymin + off[2 * i + 1];
+    }
+    return 1;
+}
+
+extern "C" int chb_video_windows(int image_count, int in_has_start, int in_start, int in_has_end, int in_end, int in_step, int out_has_start,
+                                 int out_start, int out_has_end, int out_end, int out_step, int32_t* win_start, int32_t* win_end,
+                                 int32_t* out_number, int cap) {
+    // create_video / create_video_simple, src/main.rs:230-286 and :349-404. Rust's % keeps the dividend's sign, like C++.
+    if (in_step < 1 || out_step < 1) return -1;
+    const int v_lower = out_has_start ? out_start : ((in_has_start && in_has_end) ? -(in_end - in_start) + 1 : 0);
+    const int v_upper = out_has_end ? out_end : image_count;
+    const int count = (v_upper - v_lower) / out_step;
+    for (int i = 0; i < count && i < cap; i++) {
+        const int frame = i * out_step + v_lower;
+        int start = 0, end = image_count;
+        if (in_has_start) {
+            int st = frame + in_start;
+            while (st < 0) st += in_step;
+            start = std::max(st % in_step, frame + in_start);
+        }
+        if (in_has_end) end = std::min(image_count + (frame + in_end) % in_step - in_step, frame + in_end);
+        win_start[i] = start;
+        win_end[i] = end;
+        out_number[i] = frame - v_lower;
+    }
+    return count < 0 ? 0 : count;
+}

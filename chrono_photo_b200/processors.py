@@ -1,0 +1,263 @@
+"""Host-side mirror of the reference's processor interface for the compositing path, on top of the C ABI.
+
+    FrameStack         replaces TimeSlicer::write_time_slices + the temp slice files (src/slicer.rs:106, src/main.rs:574)
+    OutlierProcessor   src/chrono.rs:32-206   new(threshold, bg_mode, outlier_mode, weights, fade, compression, sample_count)
+    SimpleProcessor    src/simple.rs:11-168   new(weights, fade, darker)
+    Crop / crop_create src/shake.rs:121-181
+    video_windows      src/main.rs:230-286 / :349-404
+
+`process` takes the HBM-resident FrameStack where the reference takes the list of slice / image files; every other
+argument keeps its meaning. All arithmetic happens in libchrono_b200.so (CUDA); nothing here computes pixels.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .options import BackgroundMode, Fade, OutlierSelectionMode, Threshold
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+class Context:
+    """chb_ctx: the GPUs this process drives (row shards, one band per device)."""
+
+    def __init__(self, device_ids=None):
+        self._h = C.c_void_p()
+        if device_ids is None:
+            _lib.check(_lib.lib().chb_ctx_create(None, 0, C.byref(self._h)))
+        else:
+            arr = (C.c_int * len(device_ids))(*device_ids)
+            _lib.check(_lib.lib().chb_ctx_create(arr, len(device_ids), C.byref(self._h)))
+
+    @property
+    def device_count(self):
+        return _lib.lib().chb_ctx_device_count(self._h)
+
+    def set_stream(self, dev_slot, cuda_stream):
+        _lib.check(_lib.lib().chb_ctx_set_stream(self._h, dev_slot, C.c_void_p(cuda_stream)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().chb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FrameStack:
+    """Device-resident frame stack (`chb_stack`). width/height are the (cropped) output size."""
+
+    def __init__(self, ctx, width, height, channels, n_frames):
+        self.ctx = ctx
+        self.width, self.height, self.channels, self.n_frames = int(width), int(height), int(channels), int(n_frames)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().chb_stack_create(ctx._h, self.width, self.height, self.channels, self.n_frames, C.byref(self._h)))
+
+    def upload(self, frame_idx, pixels, crop_xy=(0, 0), pinned=False):
+        """pixels: (rows, cols, channels) uint8 host image; crop_xy: Crop origin (src/shake.rs:178-180)."""
+        px = pixels
+        if px.dtype != np.uint8 or px.ndim != 3 or px.shape[2] != self.channels or not px.flags["C_CONTIGUOUS"]:
+            raise ValueError("pixels must be a C-contiguous (rows, cols, channels) uint8 array")
+        if px.shape[0] < crop_xy[1] + self.height or px.shape[1] < crop_xy[0] + self.width:
+            raise ValueError("crop window outside the host image")
+        fn = _lib.lib().chb_stack_upload_pinned if pinned else _lib.lib().chb_stack_upload
+        _lib.check(fn(self._h, int(frame_idx), C.c_void_p(px.ctypes.data), px.strides[0], int(crop_xy[0]), int(crop_xy[1])))
+
+    def upload_raw(self, frame_idx, ptr, row_pitch, crop_xy=(0, 0), pinned=True):
+        fn = _lib.lib().chb_stack_upload_pinned if pinned else _lib.lib().chb_stack_upload
+        _lib.check(fn(self._h, int(frame_idx), C.c_void_p(ptr), int(row_pitch), int(crop_xy[0]), int(crop_xy[1])))
+
+    def upload_all(self, frames, crops=None):
+        for i in range(self.n_frames):
+            self.upload(i, frames[i], crops[i] if crops is not None else (0, 0))
+        self.sync()
+
+    def sync(self):
+        _lib.check(_lib.lib().chb_stack_sync(self._h))
+
+    def fill_synthetic(self, kind, seed=42, row0_global=0, full_height=None):
+        _lib.check(_lib.lib().chb_stack_fill_synthetic(self._h, int(kind), int(seed), int(row0_global),
+                                                      int(self.height if full_height is None else full_height)))
+
+    def device_bytes(self, dev_slot=0):
+        return _lib.lib().chb_stack_device_bytes(self._h, dev_slot)
+
+    def close(self):
+        if self._h:
+            _lib.lib().chb_stack_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_frame_host(kind, seed, frame_idx, n_frames, width, full_height, channels, row0=0, rows=None):
+    rows = full_height if rows is None else rows
+    out = np.empty((rows, width, channels), dtype=np.uint8)
+    _lib.check(_lib.lib().chb_synth_frame_host(int(kind), int(seed), int(frame_idx), int(n_frames), int(width), int(full_height),
+                                               int(channels), int(row0), int(rows), C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def _indices(image_indices):
+    if image_indices is None:
+        return None, 0, None
+    arr = np.ascontiguousarray(image_indices, dtype=np.int32)
+    return arr.ctypes.data_as(C.POINTER(C.c_int32)), len(arr), arr
+
+
+class OutlierProcessor:
+    """OutlierProcessor::new (src/chrono.rs:46-54). `compression` is accepted and ignored (there are no temp files)."""
+
+    def __init__(self, threshold, bg_mode, outlier_mode, weights=(1.0, 1.0, 1.0, 1.0), fade=None, compression=None,
+                 sample_count=None, seed=0, pixel_offset=0):
+        if not isinstance(threshold, Threshold):
+            raise TypeError("threshold must be a Threshold")
+        self.threshold = threshold
+        self.background = BackgroundMode(bg_mode)
+        self.outlier = OutlierSelectionMode(outlier_mode)
+        self.weights = [float(w) for w in weights] + [1.0] * (4 - len(weights))
+        self.fade = fade if fade is not None else Fade.none()
+        self.sample_count = sample_count
+        self.seed = int(seed)
+        self.pixel_offset = int(pixel_offset)
+        self.warnings = 0
+        self.kernel_ms = None
+
+    def _params(self):
+        p = _lib.OutlierParams()
+        p.thr_absolute = 1 if self.threshold.absolute else 0
+        p.background = int(self.background)
+        p.outlier = int(self.outlier)
+        p.thr_min, p.thr_max, p.thr_scale = self.threshold.min, self.threshold.max, self.threshold.scale
+        for i in range(4):
+            p.weights[i] = self.weights[i]
+        p.fade = self.fade.to_c()
+        p.sample_count = -1 if self.sample_count is None else int(self.sample_count)
+        p.seed = self.seed
+        p.pixel_offset = self.pixel_offset
+        return p
+
+    def process(self, stack, image_indices=None, want_mask=True, debug=False):
+        """OutlierProcessor::process (src/chrono.rs:73-206) -> (buffer, is_outlier) as (H, W, C) uint8 arrays.
+        debug=True additionally returns a dict of per-pixel sub-results (median, q1, q3, n_outliers)."""
+        shape = (stack.height, stack.width, stack.channels)
+        out = np.empty(shape, dtype=np.uint8)
+        mask = np.empty(shape, dtype=np.uint8) if want_mask else None
+        ip, n, _keep = _indices(image_indices)
+        warn = C.c_uint64(0)
+        p = self._params()
+        if debug:
+            P = stack.height * stack.width
+            d = {"median": np.zeros((P, 4), np.float32), "q1": np.zeros((P, 4), np.float32), "q3": np.zeros((P, 4), np.float32),
+                 "n_outliers": np.zeros(P, np.int32)}
+            planes = _lib.DebugPlanes(d["median"].ctypes.data_as(C.POINTER(C.c_float)), d["q1"].ctypes.data_as(C.POINTER(C.c_float)),
+                                      d["q3"].ctypes.data_as(C.POINTER(C.c_float)), d["n_outliers"].ctypes.data_as(C.POINTER(C.c_int32)))
+            _lib.check(_lib.lib().chb_outlier_debug(stack._h, C.byref(p), ip, n, C.c_void_p(out.ctypes.data),
+                                                    C.c_void_p(mask.ctypes.data) if want_mask else None, C.byref(warn), C.byref(planes)))
+            self.warnings = warn.value
+            return out, mask, d
+        _lib.check(_lib.lib().chb_outlier(stack._h, C.byref(p), ip, n, C.c_void_p(out.ctypes.data),
+                                          C.c_void_p(mask.ctypes.data) if want_mask else None, C.byref(warn)))
+        self.warnings = warn.value
+        return out, mask
+
+    def process_device(self, stack, image_indices=None, want_mask=True):
+        """Kernel-only variant: results stay on the device; returns the launch's device time in ms."""
+        ip, n, _keep = _indices(image_indices)
+        ms = C.c_float(0)
+        p = self._params()
+        _lib.check(_lib.lib().chb_outlier_device(stack._h, C.byref(p), ip, n, 1 if want_mask else 0, C.byref(ms)))
+        self.kernel_ms = ms.value
+        return ms.value
+
+
+class SimpleProcessor:
+    """SimpleProcessor::new(weights, fade, darker) (src/simple.rs:18)."""
+
+    def __init__(self, weights=(1.0, 1.0, 1.0, 1.0), fade=None, darker=True):
+        self.weights = [float(w) for w in weights] + [1.0] * (4 - len(weights))
+        self.fade = fade if fade is not None else Fade.none()
+        self.darker = bool(darker)
+        self.kernel_ms = None
+
+    def _params(self):
+        p = _lib.SimpleParams()
+        p.darker = 1 if self.darker else 0
+        for i in range(4):
+            p.weights[i] = self.weights[i]
+        p.fade = self.fade.to_c()
+        return p
+
+    def process(self, stack, image_indices=None):
+        """SimpleProcessor::process (src/simple.rs:26-168) -> (H, W, C) uint8 buffer."""
+        out = np.empty((stack.height, stack.width, stack.channels), dtype=np.uint8)
+        ip, n, _keep = _indices(image_indices)
+        p = self._params()
+        _lib.check(_lib.lib().chb_simple(stack._h, C.byref(p), ip, n, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def process_device(self, stack, image_indices=None):
+        ip, n, _keep = _indices(image_indices)
+        ms = C.c_float(0)
+        p = self._params()
+        _lib.check(_lib.lib().chb_simple_device(stack._h, C.byref(p), ip, n, C.byref(ms)))
+        self.kernel_ms = ms.value
+        return ms.value
+
+
+def fetch_last(stack, want_mask=False):
+    out = np.empty((stack.height, stack.width, stack.channels), dtype=np.uint8)
+    mask = np.empty_like(out) if want_mask else None
+    warn = C.c_uint64(0)
+    _lib.check(_lib.lib().chb_fetch_last(stack._h, C.c_void_p(out.ctypes.data), C.c_void_p(mask.ctypes.data) if want_mask else None, C.byref(warn)))
+    return out, mask, warn.value
+
+
+def crop_create(offsets, width, height):
+    """Crop::create (src/shake.rs:136-176): per-frame crop origins and the common size, or None if all offsets are zero."""
+    off = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 2)
+    xy = np.zeros_like(off)
+    w, h = C.c_int32(), C.c_int32()
+    r = _lib.lib().chb_crop_create(off.ctypes.data_as(C.POINTER(C.c_int32)), len(off), int(width), int(height),
+                                   xy.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(w), C.byref(h))
+    if r == 0:
+        return None
+    return xy, w.value, h.value
+
+
+def video_windows(image_count, video_in, video_out):
+    """Window index lists of create_video / create_video_simple (src/main.rs:230-286): returns [(number, indices)],
+    skipping the frames the reference skips (empty windows)."""
+    cap = max(1, 4 * image_count + 16)
+    ws, we, num = (np.zeros(cap, np.int32) for _ in range(3))
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    n = _lib.lib().chb_video_windows(int(image_count),
+                                     video_in.start is not None, video_in.start or 0, video_in.end is not None, video_in.end or 0, video_in.step,
+                                     video_out.start is not None, video_out.start or 0, video_out.end is not None, video_out.end or 0, video_out.step,
+                                     p(ws), p(we), p(num), cap)
+    if n < 0:
+        raise ValueError("invalid frame ranges")
+    out = []
+    for i in range(min(n, cap)):
+        idx = list(range(int(ws[i]), int(we[i]), video_in.step))
+        if idx:
+            out.append((int(num[i]), idx))
+    return out
+
+
+def sample_positions(seed, n, cnt):
+    out = np.zeros(cnt, np.int32)
+    _lib.check(_lib.lib().chb_sample_positions(int(seed), int(n), int(cnt), out.ctypes.data_as(C.POINTER(C.c_int32))))
+    return out

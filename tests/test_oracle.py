@@ -1,0 +1,207 @@
+"""CPU tests (no GPU): the oracle against the reference's own known-answer vectors, against an
+independent numpy restatement, and against properties the algorithm must have."""
+import numpy as np
+import pytest
+
+import np_restatement as npr
+import oracle_lib as orc
+
+BG = {"first": 0, "random": 1, "average": 2, "median": 3}
+OM = {"first": 0, "last": 1, "extreme": 2, "average": 3, "forward": 4, "backward": 5}
+
+
+def make_stack(rng, n, h, w, c, noise=5, n_obj=3):
+    base = rng.integers(40, 200, size=(1, h, w, c))
+    st = base + rng.integers(-noise, noise + 1, size=(n, h, w, c))
+    for _ in range(n_obj):
+        f = rng.integers(0, n, size=max(1, n // 6))
+        y, x = rng.integers(0, h), rng.integers(0, w)
+        st[f, y:y + 2, x:x + 3, :] = rng.integers(0, 256, size=(1, 1, 1, c))
+    return np.clip(st, 0, 255).astype(np.uint8)
+
+
+# ---- the reference's own vectors -------------------------------------------------------------------------------
+def test_quartiles_known_answer():
+    # src/chrono.rs:598-604
+    assert orc.quartiles([0, 1, 2, 3, 4, 5, 6]) == (1.0, 3.0, 5.0)
+
+
+def test_blend_known_answers():
+    # src/color.rs:55-63 (commented-out blend_test documents the intent)
+    assert list(orc.blend_into_u8([0] * 4, [255] * 4, 0.0)) == [0] * 4
+    assert list(orc.blend_into_u8([0] * 4, [255] * 4, 0.5)) == [128] * 4
+    assert list(orc.blend_into_u8([0] * 4, [255] * 4, 1.0)) == [255] * 4
+
+
+def test_threshold_defaults():
+    # abs/0.05/0.2 in f32
+    t = orc.threshold(True, 0.05, 0.2)
+    assert t.min == np.float32(0.05) * np.float32(255) and t.max == np.float32(0.2) * np.float32(255)
+    assert abs(t.min - 12.75) < 1e-5 and abs(t.max - 51.0) < 1e-5
+    assert np.float32(t.scale) == np.float32(1.0) / ((np.float32(0.2) - np.float32(0.05)) * np.float32(255))
+    single = orc.threshold(True, 0.1, 0.1)  # single-value form: max == min -> scale = inf, never used
+    assert np.isinf(single.scale)
+
+
+def test_fade_test_vector():
+    # src/options.rs:350-356 "clamp/abs/0,0/10,1"
+    f, keep = orc.fade(0, True, [(0, 0.0), (10, 1.0)])
+    lib = orc.lib()
+    assert f.n_values == 11 and f.offset == 0
+    assert lib.orc_fade_get(f, -5) == 0.0 and lib.orc_fade_get(f, 50) == 1.0
+    assert abs(lib.orc_fade_get(f, 5) - 0.5) < 1e-6
+    f2, keep2 = orc.fade(1, True, [(0, 0.0), (4, 1.0)])  # repeat
+    assert lib.orc_fade_get(f2, 5) == lib.orc_fade_get(f2, 0) and lib.orc_fade_get(f2, -1) == lib.orc_fade_get(f2, 4)
+
+
+# ---- order statistics -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 7, 25, 200, 255, 256, 257, 1000])
+def test_median_and_quartiles_match_numpy_restatement(n):
+    rng = np.random.default_rng(n)
+    for _ in range(20):
+        d = np.sort(rng.integers(0, 256, size=n).astype(np.uint8))
+        q1, m, q3 = orc.quartiles(d)
+        assert m == npr.median_sorted(list(d)) and q1 == npr.quantile_sorted(list(d), 0.25) and q3 == npr.quantile_sorted(list(d), 0.75)
+        # results are exact multiples of .5 / .25
+        assert (m * 2) % 1 == 0 and (q1 * 4) % 1 == 0 and (q3 * 4) % 1 == 0
+
+
+def test_quantile_positions():
+    # N=200 -> Q1 = .75 d[49] + .25 d[50]; N=25 -> .5 (d[5] + d[6])
+    d = np.arange(200, dtype=np.uint8)
+    assert orc.quartiles(d)[0] == 0.75 * 49 + 0.25 * 50 and orc.quartiles(d)[2] == 0.25 * 149 + 0.75 * 150
+    d = np.arange(25, dtype=np.uint8)
+    assert orc.quartiles(d)[0] == 0.5 * (5 + 6) and orc.quartiles(d)[2] == 0.5 * (18 + 19)
+
+
+# ---- full pixel path against the independent restatement ----------------------------------------------------------
+@pytest.mark.parametrize("bg", ["first", "random", "average", "median"])
+@pytest.mark.parametrize("om", ["first", "last", "extreme", "average", "forward", "backward"])
+def test_outlier_abs_matches_numpy_restatement(bg, om):
+    rng = np.random.default_rng(hash((bg, om)) % 2**32)
+    st = make_stack(rng, 12, 5, 6, 3)
+    thr = orc.threshold(True, 0.05, 0.2)
+    img, msk, warn = orc.outlier(st, thr, BG[bg], OM[om], seed=7)
+    img2, msk2, warn2 = npr.outlier(st, True, thr.min, thr.max, thr.scale, BG[bg], OM[om], seed=7)
+    assert np.array_equal(img, img2) and np.array_equal(msk, msk2) and warn == warn2
+
+
+@pytest.mark.parametrize("om", ["extreme", "average", "forward", "backward"])
+@pytest.mark.parametrize("n,c", [(9, 3), (10, 4)])
+def test_outlier_rel_matches_numpy_restatement(om, n, c):
+    rng = np.random.default_rng(n * 10 + c)
+    st = make_stack(rng, n, 4, 5, c)
+    thr = orc.threshold(False, 3.0, 5.0)
+    for bg in ("first", "average"):
+        img, msk, warn = orc.outlier(st, thr, BG[bg], OM[om])
+        img2, msk2, warn2 = npr.outlier(st, False, thr.min, thr.max, thr.scale, BG[bg], OM[om])
+        assert np.array_equal(img, img2) and np.array_equal(msk, msk2) and warn == warn2
+
+
+def test_outlier_window_fade_weights_sample_matches_numpy_restatement():
+    rng = np.random.default_rng(5)
+    st = make_stack(rng, 20, 4, 4, 3)
+    thr = orc.threshold(True, 0.04, 0.15)
+    idx = list(range(3, 17, 2))
+    spos = [0, 2, 3, 5, 6]
+    for absolute in (True, False):
+        fo = orc.fade(1, absolute, [(0, 0.0), (4, 1.0), (6, 0.25)])
+        fn = npr.Fade.build(1, absolute, [(0, 0.0), (4, 1.0), (6, 0.25)])
+        for w in ((1, 1, 1, 0), (0, 0, 1, 0), (1, 0.5, 0.5, 0)):  # docs/options.md:157-158
+            img, msk, warn = orc.outlier(st, thr, BG["first"], OM["forward"], weights=w, fade_=fo, indices=idx, sample_pos=spos)
+            img2, msk2, warn2 = npr.outlier(st, True, thr.min, thr.max, thr.scale, BG["first"], OM["forward"], weights=w, fade=fn,
+                                            indices=idx, sample_pos=spos)
+            assert np.array_equal(img, img2) and np.array_equal(msk, msk2) and warn == warn2
+
+
+def test_all_outlier_warning_path():
+    # threshold 0: every frame is an outlier (dist_sq >= 0), first_excluded returns (0, warning) src/chrono.rs:510-516
+    rng = np.random.default_rng(11)
+    st = make_stack(rng, 6, 3, 3, 3)
+    thr = orc.threshold(True, 0.0, 0.2)
+    img, msk, warn = orc.outlier(st, thr, BG["first"], OM["extreme"])
+    assert warn == 9
+    img2, msk2, warn2 = npr.outlier(st, True, thr.min, thr.max, thr.scale, BG["first"], OM["extreme"])
+    assert np.array_equal(img, img2) and np.array_equal(msk, msk2) and warn2 == 9
+
+
+def test_constant_frames_no_outliers_and_iqr_zero_branch():
+    st = np.full((8, 3, 3, 3), 77, np.uint8)  # IQR == 0 -> iqr_inv = 1 (src/chrono.rs:249-251)
+    for absolute, mn, mx in ((True, 0.05, 0.2), (False, 3.0, 5.0)):
+        img, msk, warn = orc.outlier(st, orc.threshold(absolute, mn, mx), BG["median"], OM["extreme"])
+        assert (img == 77).all() and (msk == 0).all() and warn == 0
+
+
+def test_mask_alpha_band_is_255():
+    rng = np.random.default_rng(3)
+    st = make_stack(rng, 9, 3, 3, 4)
+    _, msk, _ = orc.outlier(st, orc.threshold(True, 0.05, 0.2), BG["first"], OM["extreme"])
+    assert (msk[..., 3] == 255).all()  # src/chrono.rs:186-190
+
+
+def test_sample_excluded_quirk_is_reproduced():
+    # n=10, outliers {3, 9}: after the position swaps the candidate range holds frame 9 and lacks frame 8
+    st = np.full((10, 1, 1, 3), 100, np.uint8)
+    st[3] = 0
+    st[9] = 255
+    thr = orc.threshold(True, 0.05, 0.2)
+    seen = set()
+    for seed in range(400):
+        _, _, _, d = orc.outlier(st, thr, BG["random"], OM["first"], seed=seed, want_debug=True)
+        seen.add(int(d["bg_index"][0]))
+    assert seen == {0, 1, 2, 9, 4, 5, 6, 7}
+
+
+def test_simple_matches_numpy_restatement():
+    rng = np.random.default_rng(2)
+    st = make_stack(rng, 11, 4, 5, 3)
+    for darker in (True, False):
+        assert np.array_equal(orc.simple(st, darker), npr.simple(st, darker))
+        fo = orc.fade(0, False, [(0, 1.0), (5, 0.0)])
+        fn = npr.Fade.build(0, False, [(0, 1.0), (5, 0.0)])
+        assert np.array_equal(orc.simple(st, darker, weights=(1, 0.5, 0.25, 0), fade_=fo, indices=[1, 2, 5, 6, 9]),
+                              npr.simple(st, darker, weights=(1, 0.5, 0.25, 0), fade=fn, indices=[1, 2, 5, 6, 9]))
+
+
+def test_simple_first_frame_wins_ties():
+    st = np.zeros((3, 1, 2, 3), np.uint8)
+    st[0, 0, 0] = (10, 20, 30)
+    st[1, 0, 0] = (30, 20, 10)  # same sum: strict compare keeps frame 0 (src/simple.rs:108-118)
+    st[2, 0, 0] = (20, 20, 20)
+    assert tuple(orc.simple(st, True)[0, 0]) == (10, 20, 30) and tuple(orc.simple(st, False)[0, 0]) == (10, 20, 30)
+
+
+def test_multithreaded_oracle_is_identical():
+    rng = np.random.default_rng(8)
+    st = make_stack(rng, 15, 16, 9, 3)
+    thr = orc.threshold(True, 0.05, 0.2)
+    a = orc.outlier(st, thr, BG["random"], OM["extreme"], seed=3, n_threads=1)
+    b = orc.outlier(st, thr, BG["random"], OM["extreme"], seed=3, n_threads=4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    assert np.array_equal(orc.simple(st, True, n_threads=1), orc.simple(st, True, n_threads=3))
+
+
+# ---- host-side callers --------------------------------------------------------------------------------------------
+def test_crop_create():
+    # src/shake.rs:136-176
+    assert orc.crop_create([(0, 0), (0, 0)], 100, 80) is None
+    xy, w, h = orc.crop_create([(0, 0), (3, -2), (-1, 4)], 100, 80)
+    assert (w, h) == (100 - 1 - 3, 80 - 2 - 4)
+    assert xy.tolist() == [[1, 2], [4, 0], [0, 6]]
+
+
+def test_video_windows_quirks():
+    # --video-in 0/25/1 on 1800 images: v_lower = -24, 1824 output frames, last image never enters
+    n, ws, we, num = orc.video_windows(1800, (0, 25, 1), (None, None, 1))
+    assert n == 1824 and num[0] == 0 and (ws[0], we[0]) == (0, 1) and (ws[24], we[24]) == (0, 25)
+    assert we.max() == 1799  # end capped at image_count - step (src/main.rs:272-276)
+    # open start: growing trail from 0 (src/main.rs:270)
+    n, ws, we, num = orc.video_windows(10, (None, 3, 1), (None, None, 1))
+    assert (ws == 0).all() and we.tolist() == [min(9, f + 3) for f in range(10)]
+    # step 2 windows start on the step grid
+    n, ws, we, num = orc.video_windows(20, (-4, 2, 2), (0, 20, 1))
+    for f in range(20):
+        st = f - 4
+        while st < 0:
+            st += 2
+        assert ws[f] == max(st % 2, f - 4)
