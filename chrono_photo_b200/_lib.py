@@ -48,6 +48,7 @@ SYMBOLS = {
     "chb_stack_device_bytes": (C.c_size_t, [_vp, _i]),
     "chb_stack_upload": (_i, [_vp, _i, _vp, C.c_size_t, _i, _i]),
     "chb_stack_upload_pinned": (_i, [_vp, _i, _vp, C.c_size_t, _i, _i]),
+    "chb_stack_download": (_i, [_vp, _i, _vp, C.c_size_t]),
     "chb_stack_sync": (_i, [_vp]),
     "chb_stack_fill_synthetic": (_i, [_vp, _i, C.c_uint64, _i, _i]),
     "chb_synth_frame_host": (_i, [_i, C.c_uint64, _i, _i, _i, _i, _i, _i, _i, _vp]),

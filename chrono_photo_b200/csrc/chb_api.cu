@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -302,6 +303,27 @@ extern "C" int chb_stack_upload_pinned(chb_stack* st, int frame_idx, const uint8
     return upload_impl(st, frame_idx, pinned_pixels, row_pitch, crop_x, crop_y, true);
 }
 
+extern "C" int chb_stack_download(chb_stack* st, int frame_idx, uint8_t* host_pixels, size_t row_pitch) {
+    if (!st || !host_pixels) return fail(CHB_ERR_INVALID, "chb_stack_download: null argument");
+    if (frame_idx < 0 || frame_idx >= st->N) return fail(CHB_ERR_INVALID, "chb_stack_download: frame %d outside [0, %d)", frame_idx, st->N);
+    const size_t row_bytes = (size_t)st->W * st->C;
+    if (row_pitch < row_bytes) return fail(CHB_ERR_INVALID, "chb_stack_download: row pitch %zu too small", row_pitch);
+    std::lock_guard<std::mutex> lk(st->upload_mu);
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        CU(cudaStreamSynchronize(d.copy));
+        CU(cudaStreamSynchronize(d.pack));
+        unpack_frame_kernel<<<grid_for(b.n_pixels, 256, d.sm_count, 8), 256, 0, d.pack>>>(b.d_stack, b.d_stage[0], b.n_pixels, st->C, st->NG, frame_idx);
+        g_launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpy2DAsync(host_pixels + (size_t)b.row0 * row_pitch, row_pitch, b.d_stage[0], row_bytes, row_bytes, (size_t)b.rows,
+                             cudaMemcpyDeviceToHost, d.pack));
+        CU(cudaStreamSynchronize(d.pack));
+    }
+    return CHB_OK;
+}
+
 extern "C" int chb_stack_sync(chb_stack* st) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_stack_sync: null stack");
     std::lock_guard<std::mutex> lk(st->upload_mu);
@@ -400,7 +422,7 @@ extern "C" int chb_sample_positions(uint64_t seed, int n, int cnt, int32_t* out)
 typedef void (*OutlierKernel)(const OutlierArgs);
 struct Variant { int wpl, g; };
 // capacity (frames) = 16 * wpl * g
-static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {7, 2}, {8, 2}, {8, 4}, {8, 8}, {8, 16}, {8, 32}};
+static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {7, 2}, {4, 4}, {8, 4}, {8, 8}, {8, 16}, {8, 32}};
 static constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 template <int C, bool SUB>
@@ -411,7 +433,7 @@ static OutlierKernel kernel_for(int v) {
         case 2: return outlier_kernel<C, 4, 1, SUB>;
         case 3: return outlier_kernel<C, 4, 2, SUB>;
         case 4: return outlier_kernel<C, 7, 2, SUB>;
-        case 5: return outlier_kernel<C, 8, 2, SUB>;
+        case 5: return outlier_kernel<C, 4, 4, SUB>;
         case 6: return outlier_kernel<C, 8, 4, SUB>;
         case 7: return outlier_kernel<C, 8, 8, SUB>;
         case 8: return outlier_kernel<C, 8, 16, SUB>;
@@ -467,6 +489,10 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     int vidx = -1;
     for (int v = 0; v < kNumVariants; v++)
         if (kVariants[v].wpl * kVariants[v].g >= win.n_groups) { vidx = v; break; }
+    if (const char* force = getenv("CHB_FORCE_VARIANT")) {  // tuning aid: pick a larger-capacity variant by table index
+        int v = atoi(force);
+        if (v >= 0 && v < kNumVariants && kVariants[v].wpl * kVariants[v].g >= win.n_groups) vidx = v;
+    }
     if (vidx < 0)
         return fail(CHB_ERR_UNSUPPORTED, "chb_outlier: window spans %d frames; this build holds at most %d per launch", win.n_groups * 16, kMaxWindowFrames);
     const Variant var = kVariants[vidx];
@@ -477,6 +503,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     a.NG = st->NG; a.C = st->C;
     a.g0 = win.g0; a.n_groups = win.n_groups;
     a.n = n; a.n_sub = n_sub;
+    a.first_frame = win.frames.front() & 15;
     a.inv_n_sub = 1.0f / (float)n_sub;
     // median ranks (src/chrono.rs:582-591)
     if ((n_sub + 1) % 2 == 0) a.rk[2] = a.rk[3] = (n_sub + 1) / 2 - 1;
@@ -504,6 +531,11 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             if ((m[0] & m[1] & m[2] & m[3]) != 0xffffffffu) patch |= 1u << i;
         }
     a.patch_slots = patch;
+    // frames that exist in the stack, lie inside the span, but are not part of the window must be masked after the load
+    {
+        int in_span_existing = std::min(st->N, (win.g0 + win.n_groups) * kGroupFrames) - win.g0 * kGroupFrames;
+        a.window_masked = (in_span_existing != n) ? 1 : 0;
+    }
     if (sub) {
         std::vector<int32_t> sframes(spos.size());
         for (size_t i = 0; i < spos.size(); i++) sframes[i] = win.frames[spos[i]];
@@ -548,7 +580,11 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             ab.dbg_nout = dbg->n_outliers ? b.d_dbg_nout : nullptr;
         }
         const long long n_tasks = b.n_tiles * var.g;
-        const int blocks = grid_for(n_tasks * 32, 256, d.sm_count, 64);
+        int occ = 1;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 50));  // room for the per-warp queues of several CTAs
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+        // persistent grid: every resident warp strides over the tile slices, so its exact-path queue fills up
+        const int blocks = grid_for(n_tasks * 32, 256, d.sm_count, std::max(1, occ));
         CU(cudaEventRecord(b.ev0, s));
         kern<<<blocks, 256, 0, s>>>(ab);
         g_launches++;
@@ -647,6 +683,12 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
     if (rc) return rc;
     a.frame_offset = indices ? indices[0] : 0;  // src/simple.rs:54-57
     const bool fade = !prm->fade.is_none;
+    // integer kernel: no fade and every weight of an existing band is exactly 0 or 1 (the CLI default is all ones)
+    bool int_path = !fade;
+    for (int i = 0; i < st->C; i++) {
+        if (prm->weights[i] == 1.0f) a.use_mask |= 1u << i;
+        else if (prm->weights[i] != 0.0f) int_path = false;
+    }
     std::vector<uint32_t> masks((size_t)win.n_groups * 4);
     byte_masks(win.frames, win.g0, win.n_groups, masks.data());
     bool all_in = true;
@@ -684,7 +726,10 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
         ab.out_image = b.d_out;
         const int blocks = grid_for(b.n_tiles * kTilePixels, 256, d.sm_count, 64);
         CU(cudaEventRecord(b.ev0, s));
-        if (st->C == 3) {
+        if (int_path) {
+            if (st->C == 3) simple_int_kernel<3><<<blocks, 256, 0, s>>>(ab);
+            else simple_int_kernel<4><<<blocks, 256, 0, s>>>(ab);
+        } else if (st->C == 3) {
             if (fade) simple_kernel<3, true><<<blocks, 256, 0, s>>>(ab);
             else simple_kernel<3, false><<<blocks, 256, 0, s>>>(ab);
         } else {

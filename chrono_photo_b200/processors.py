@@ -80,6 +80,16 @@ class FrameStack:
             self.upload(i, frames[i], crops[i] if crops is not None else (0, 0))
         self.sync()
 
+    def download(self, frame_idx, out=None):
+        """Frame frame_idx as a (height, width, channels) uint8 array (inverse of upload)."""
+        if out is None:
+            out = np.empty((self.height, self.width, self.channels), dtype=np.uint8)
+        _lib.check(_lib.lib().chb_stack_download(self._h, int(frame_idx), C.c_void_p(out.ctypes.data), out.strides[0]))
+        return out
+
+    def download_raw(self, frame_idx, ptr, row_pitch):
+        _lib.check(_lib.lib().chb_stack_download(self._h, int(frame_idx), C.c_void_p(ptr), int(row_pitch)))
+
     def sync(self):
         _lib.check(_lib.lib().chb_stack_sync(self._h))
 

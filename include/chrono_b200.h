@@ -119,6 +119,9 @@ size_t chb_stack_device_bytes(const chb_stack *stack, int dev_slot);
 int chb_stack_upload(chb_stack *stack, int frame_idx, const uint8_t *host_pixels, size_t row_pitch, int crop_x, int crop_y);
 /* Same, from a pinned (page-locked) host buffer the caller keeps alive until chb_stack_sync: no staging copy. */
 int chb_stack_upload_pinned(chb_stack *stack, int frame_idx, const uint8_t *pinned_pixels, size_t row_pitch, int crop_x, int crop_y);
+/* Read frame frame_idx back from the stack (interleaved u8, tightly packed rows of width*channels bytes at row_pitch):
+ * the inverse of chb_stack_upload, for checks and for filling host buffers from a device-generated series. */
+int chb_stack_download(chb_stack *stack, int frame_idx, uint8_t *host_pixels, size_t row_pitch);
 /* Wait until every upload issued so far has landed in HBM. */
 int chb_stack_sync(chb_stack *stack);
 

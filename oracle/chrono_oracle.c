@@ -163,7 +163,28 @@ uint32_t orc_rng_range(uint64_t seed, uint64_t pixel, uint32_t draw, uint32_t n)
 
 /* ---------------------------------------------------------------- chrono.rs calc_pixel */
 
-static int cmp_u8(const void *a, const void *b) { return (int)*(const uint8_t *)a - (int)*(const uint8_t *)b; }
+/* Stand-in for slice::sort_unstable (src/chrono.rs:242). Any correct sort gives the same sorted bytes; a counting sort
+ * (insertion sort for short slices) is used so that the CPU baseline is not handicapped by libc qsort's indirect
+ * compare calls -- pdqsort on u8 keys is at best on par with this. */
+static void sort_u8(uint8_t *v, int n) {
+    if (n <= 24) {
+        for (int i = 1; i < n; i++) {
+            uint8_t k = v[i];
+            int j = i - 1;
+            while (j >= 0 && v[j] > k) { v[j + 1] = v[j]; j--; }
+            v[j + 1] = k;
+        }
+        return;
+    }
+    uint32_t hist[256];
+    memset(hist, 0, sizeof hist);
+    for (int i = 0; i < n; i++) hist[v[i]]++;
+    int o = 0;
+    for (int b = 0; b < 256; b++) {
+        uint32_t c = hist[b];
+        if (c) { memset(v + o, b, c); o += (int)c; }
+    }
+}
 
 typedef struct {
     /* ThreadData, src/chrono.rs:23-28 */
@@ -247,7 +268,7 @@ static uint8_t calc_pixel(const job_t *J, scratch_t *S, size_t pix, uint64_t pix
     for (int i = 0; i < channels; i++) {
         if (P->weights[i] != 0.0f) {
             uint8_t *sl = S->values + (size_t)i * sub;
-            qsort(sl, (size_t)sub, 1, cmp_u8);
+            sort_u8(sl, sub);
             if (P->threshold.absolute) {
                 median[i] = orc_median(sl, (size_t)sub);
             } else {

@@ -67,6 +67,8 @@ def test_upload_then_darker_lighter_roundtrip(ctx):
     fs = upload(ctx, st)
     for darker in (True, False):
         assert np.array_equal(cp.SimpleProcessor(darker=darker).process(fs), orc.simple(st, darker))
+    for f in (0, 7, 15, 16, 18):
+        assert np.array_equal(fs.download(f), st[f])
     fs.close()
 
 
