@@ -422,22 +422,23 @@ extern "C" int chb_sample_positions(uint64_t seed, int n, int cnt, int32_t* out)
 typedef void (*OutlierKernel)(const OutlierArgs);
 struct Variant { int wpl, g; };
 // capacity (frames) = 16 * wpl * g
-static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {7, 2}, {4, 4}, {8, 4}, {8, 8}, {8, 16}, {8, 32}};
+static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {8, 1}, {13, 1}, {7, 2}, {8, 2}, {8, 4}, {8, 8}, {8, 16}, {8, 32}};
 static constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-template <int C, bool SUB>
+template <int C, bool GENERIC>
 static OutlierKernel kernel_for(int v) {
     switch (v) {
-        case 0: return outlier_kernel<C, 1, 1, SUB>;
-        case 1: return outlier_kernel<C, 2, 1, SUB>;
-        case 2: return outlier_kernel<C, 4, 1, SUB>;
-        case 3: return outlier_kernel<C, 4, 2, SUB>;
-        case 4: return outlier_kernel<C, 7, 2, SUB>;
-        case 5: return outlier_kernel<C, 4, 4, SUB>;
-        case 6: return outlier_kernel<C, 8, 4, SUB>;
-        case 7: return outlier_kernel<C, 8, 8, SUB>;
-        case 8: return outlier_kernel<C, 8, 16, SUB>;
-        default: return outlier_kernel<C, 8, 32, SUB>;
+        case 0: return outlier_kernel<C, 1, 1, GENERIC>;
+        case 1: return outlier_kernel<C, 2, 1, GENERIC>;
+        case 2: return outlier_kernel<C, 4, 1, GENERIC>;
+        case 3: return outlier_kernel<C, 8, 1, GENERIC>;
+        case 4: return outlier_kernel<C, 13, 1, GENERIC>;
+        case 5: return outlier_kernel<C, 7, 2, GENERIC>;
+        case 6: return outlier_kernel<C, 8, 2, GENERIC>;
+        case 7: return outlier_kernel<C, 8, 4, GENERIC>;
+        case 8: return outlier_kernel<C, 8, 8, GENERIC>;
+        case 9: return outlier_kernel<C, 8, 16, GENERIC>;
+        default: return outlier_kernel<C, 8, 32, GENERIC>;
     }
 }
 
@@ -528,9 +529,10 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     for (int i = 0; i < var.wpl; i++)
         for (int jx = 0; jx < var.g; jx++) {
             const uint32_t* m = st->h_wmask + (size_t)(i * var.g + jx) * 4;
-            if ((m[0] & m[1] & m[2] & m[3]) != 0xffffffffu) patch |= 1u << i;
+            if ((m[0] & m[1] & m[2] & m[3]) != 0xffffffffu && i < var.wpl - 1) patch |= 1u << i;
         }
     a.patch_slots = patch;
+    a.lead_slots_full = (win.n_groups >= (var.wpl - 1) * var.g) ? 1 : 0;
     // frames that exist in the stack, lie inside the span, but are not part of the window must be masked after the load
     {
         int in_span_existing = std::min(st->N, (win.g0 + win.n_groups) * kGroupFrames) - win.g0 * kGroupFrames;
@@ -544,9 +546,11 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     memcpy(st->h_win, win.frames.data(), sizeof(int32_t) * (size_t)n);
     if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
 
+    // the lean kernel covers whole-stack launches whose leading register slots are all real frame groups
+    const bool generic = sub || a.window_masked || a.patch_slots || !a.lead_slots_full;
     OutlierKernel kern;
-    if (st->C == 3) kern = sub ? kernel_for<3, true>(vidx) : kernel_for<3, false>(vidx);
-    else kern = sub ? kernel_for<4, true>(vidx) : kernel_for<4, false>(vidx);
+    if (st->C == 3) kern = generic ? kernel_for<3, true>(vidx) : kernel_for<3, false>(vidx);
+    else kern = generic ? kernel_for<4, true>(vidx) : kernel_for<4, false>(vidx);
 
     const size_t P = (size_t)st->W * st->H;
     for (Band& b : st->bands) {
@@ -561,7 +565,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         OutlierArgs ab = a;
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
-        ab.wmask = b.d_wmask; ab.smask = b.d_smask; ab.win_frames = b.d_win;
+        ab.wmask = b.d_wmask; ab.smask = sub ? b.d_smask : nullptr; ab.win_frames = b.d_win;
         ab.fade.values = b.d_fade;
         ab.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
         ab.out_image = b.d_out;

@@ -49,10 +49,11 @@ struct OutlierArgs {
     long long n_pixels, n_tiles;
     int NG, C;
     int g0, n_groups;        // frame groups spanned by the window: [g0, g0 + n_groups)
-    unsigned patch_slots;    // bit i: register slot i may hold bytes that are not window frames (patched for the certificate)
+    unsigned patch_slots;    // != 0: a register slot other than the last holds bytes that are not window frames
+    int lead_slots_full;     // 1: slots 0..WPL-2 are real frame groups for every lane (plain loads)
     int window_masked;       // 1: the span holds frames outside the window; they are masked to zero after the load
     const uint32_t* wmask;   // [capacity_groups * 4] byte masks of window frames (0xFF = in window)
-    const uint32_t* smask;   // [capacity_groups * 4] byte masks of the --sample subset (SUB kernels only)
+    const uint32_t* smask;   // [capacity_groups * 4] byte masks of the --sample subset, or null (GENERIC kernels only)
     const int32_t* win_frames;  // [n] window position -> frame index
     int n, n_sub;            // window length ("samples"), subsample size
     int first_frame;         // (frame of window position 0) & 15: its byte inside the first group
@@ -78,37 +79,17 @@ struct OutlierArgs {
 // and the k-th smallest value is min{c : #{x <= c} >= k+1}. Bytes that are not part of the sample are zero, which
 // shifts every rank by the (known) number of such bytes.
 //
-// The search keeps a bracket [lo, hi] per pixel-band plus the last pair of adjacent F values (kc, F(kc), F(kc+1)):
-// a probe next to that pair needs ONE new F evaluation, so walking outward from a good first guess costs one
-// evaluation per step; far targets gallop, then bisect (two evaluations per probe).
+// One probe evaluates F at p0, p0+1, p0+2 (three independent accumulator chains over the same registers) and yields the
+// two exact counts #{x <= p0} and #{x <= p0+1}; both differences are biased, packed into one word and reduced over the
+// G lanes with a single shuffle sequence. A bracket [lo, hi] per pixel-band is narrowed by the same rule for every
+// probe; p0 starts at (guess - 1), then walks / gallops in the direction of the answer, then bisects. All ranks a band
+// needs (median pair; quartile pairs for relative thresholds) run through ONE warp-synchronous loop as a per-lane state
+// machine, so lanes that finish a rank early move on to their next rank instead of idling.
 template <int W4, int G>
 struct Sel {
-    const int cap;  // bytes held by the G lanes of one pixel-band (real + zero padding)
-    // cache of adjacent F values
-    int kc;
-    uint32_t fk0, fk1;
-    bool k0, k1;
-    __device__ __forceinline__ explicit Sel(int cap_) : cap(cap_), kc(-4), fk0(0), fk1(0), k0(false), k1(false) {}
-
-    __device__ __forceinline__ uint32_t F(const uint32_t (&x)[W4], int c) const {
-        const uint32_t cc = rep4(c);
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-        for (int q = 0; q < W4; q += 4) {
-            a0 = sad4_acc(x[q], cc, a0);
-            a1 = sad4_acc(x[q + 1], cc, a1);
-            a2 = sad4_acc(x[q + 2], cc, a2);
-            a3 = sad4_acc(x[q + 3], cc, a3);
-        }
-        return group_sum<G>((a0 + a1) + (a2 + a3));
-    }
-
-    // Evaluates F at g-1, g, g+1 (g clamped to [1, 254]) and narrows the bracket [lo, hi] of padded rank kp.
-    // mode: 0 bisect, 1 walk/gallop up, 2 walk/gallop down.
-    __device__ __forceinline__ void window3(const uint32_t (&x)[W4], int kp, int& g, int& lo, int& hi, int& cnt_hi, int& mode,
-                                            uint32_t& f_at_g) {
-        g = g < 1 ? 1 : (g > 254 ? 254 : g);
-        const uint32_t c0 = rep4(g - 1), c1 = rep4(g), c2 = rep4(g + 1);
+    // counts n0 = #{x <= p0}, n1 = #{x <= p0+1} over the G lanes of the pixel-band; p0 in [0, 253]
+    static __device__ __forceinline__ void probe(const uint32_t (&x)[W4], int p0, int& n0, int& n1, uint32_t& f_mid, bool want_f) {
+        const uint32_t c1 = rep4(p0 + 1), c0 = c1 - 0x01010101u, c2 = c1 + 0x01010101u;
         uint32_t f0 = 0, f1 = 0, f2 = 0, h0 = 0, h1 = 0, h2 = 0;
 #pragma unroll
         for (int q = 0; q < W4; q += 2) {
@@ -119,76 +100,107 @@ struct Sel {
             h1 = sad4_acc(x[q + 1], c1, h1);
             h2 = sad4_acc(x[q + 1], c2, h2);
         }
-        f0 = group_sum<G>(f0 + h0);
-        f1 = group_sum<G>(f1 + h1);
-        f2 = group_sum<G>(f2 + h2);
-        f_at_g = f1;
-        const int A = ((int)f1 - (int)f0 + cap) >> 1;  // #{x <= g-1}
-        const int B = ((int)f2 - (int)f1 + cap) >> 1;  // #{x <= g}
-        mode = 0;
-        if (kp < A) {
-            if (g - 1 < hi) { hi = g - 1; cnt_hi = A; }
-            mode = 2;
-            kc = g - 1; fk0 = f0; fk1 = f1; k0 = k1 = true;
-        } else if (kp < B) {
-            if (g >= lo && g <= hi) { lo = hi = g; cnt_hi = B; }
-            kc = g; fk0 = f1; fk1 = f2; k0 = k1 = true;
-        } else {
-            if (g + 1 > lo) lo = g + 1;
-            mode = 1;
-            kc = g; fk0 = f1; fk1 = f2; k0 = k1 = true;
-        }
+        f0 += h0; f1 += h1; f2 += h2;
+        // per lane |F(c+1) - F(c)| <= bytes per lane (= 16 * W4 / 4 * ... = 4 * W4): bias by that, pack, reduce once
+        constexpr uint32_t kBias = 4 * W4;
+        uint32_t packed = (f1 - f0 + kBias) | ((f2 - f1 + kBias) << 16);
+        packed = group_sum<G>(packed);
+        n0 = (int)((packed & 0xffffu) >> 1);  // sum(d + bias) = 2 * count because G * bias = cap
+        n1 = (int)(packed >> 17);
+        f_mid = 0;
+        if (want_f) f_mid = group_sum<G>(f1);  // F(p0 + 1), only for the spread estimate of relative thresholds
     }
+};
 
-    // Narrows [lo, hi] to one value. Requires #{x <= hi} >= kp+1 (cnt_hi = that count; cap for hi = 255) and
-    // #{x <= lo-1} <= kp. Warp-synchronous: every lane takes part in every evaluation (shuffles inside F).
-    __device__ __forceinline__ void narrow(const uint32_t (&x)[W4], int kp, int& lo, int& hi, int& cnt_hi, int mode) {
-        int steps = 0;
-        while (__any_sync(0xffffffffu, lo < hi)) {
-            const bool act = lo < hi;
-            int c;
-            const int gal = steps < 2 ? 1 : (1 << (steps - 1));
-            if (mode == 1) { c = lo + gal - 1; c = c < hi - 1 ? c : hi - 1; }
-            else if (mode == 2) { c = hi - gal; c = c > lo ? c : lo; }
-            else c = (lo + hi) >> 1;
-            if (!act) c = kc;  // idle lanes re-evaluate a cached point (result unused)
-            // re-anchor the cached pair at c
-            if (c == kc) {
-            } else if (c == kc + 1 && k1) { kc = c; fk0 = fk1; k0 = true; k1 = false; }
-            else if (c == kc - 1 && k0) { kc = c; fk1 = fk0; k1 = true; k0 = false; }
-            else { kc = c; k0 = k1 = false; }
-            const bool second = k0;  // F(c) known -> evaluate c+1, else evaluate c
-            const uint32_t val = F(x, second ? kc + 1 : kc);
-            if (second) { fk1 = val; k1 = true; } else { fk0 = val; k0 = true; }
-            if (act && k0 && k1) {
-                const int cnt = ((int)fk1 - (int)fk0 + cap) >> 1;  // #{x <= c}
-                if (cnt >= kp + 1) {
-                    hi = c; cnt_hi = cnt;
-                    if (mode == 1) mode = 0; else steps++;
+struct BandRanks {  // results of one pixel-band
+    int mlo, mhi, q1a, q1b, q3a, q3b;
+};
+
+// Solves the median pair (and the two quartile pairs when rel) of one pixel-band. rk: padded ranks are a.rk[] + pad.
+template <int W4, int G>
+__device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssum, const OutlierArgs& a, int pad, int cap, BandRanks& r) {
+    const bool rel = !a.absolute;
+    const int nt = rel ? 6 : 2;  // targets in processing order: m1, m2, q1a, q1b, q3a, q3b
+    int t = 0, lo = 0, hi = 255, cnt_hi = cap, dir = 0, gal = 1, first = 1;
+    int kp = a.rk[2] + pad;
+    int p_guess = __float2int_rn((float)ssum * a.inv_n_sub) - 1;  // mean as the first guess for the median
+    int cv_mlo = cap, dq = 0;
+    r.mlo = r.mhi = r.q1a = r.q1b = r.q3a = r.q3b = 0;
+    while (__any_sync(0xffffffffu, t < nt)) {
+        const bool act = t < nt;
+        // ---- choose the probe
+        int p0;
+        if (first) p0 = p_guess;
+        else if (hi - lo <= 2) p0 = lo;
+        else if (dir > 0) { p0 = lo + gal - 1; p0 = p0 < hi - 2 ? p0 : hi - 2; }
+        else if (dir < 0) { p0 = hi - 1 - gal; p0 = p0 > lo ? p0 : lo; }
+        else p0 = ((lo + hi) >> 1) - 1;
+        p0 = p0 < 0 ? 0 : (p0 > 253 ? 253 : p0);
+        if (!act) p0 = 0;
+        int n0, n1;
+        uint32_t f_mid;
+        Sel<W4, G>::probe(x, p0, n0, n1, f_mid, rel && t == 0 && first);
+        if (act) {
+            if (rel && t == 0 && first) {
+                // spread estimate for the quartile guesses: mean absolute deviation around the guess
+                const float mad = ((float)f_mid - (float)pad * (float)(p0 + 1)) * a.inv_n_sub;
+                dq = __float2int_rn(0.95f * mad);
+            }
+            // ---- universal bracket update from #{x <= p0} and #{x <= p0+1}
+            const int lo_before = lo, hi_before = hi;
+            if (n0 >= kp + 1) {
+                if (p0 < hi) { hi = p0; cnt_hi = n0; }
+            } else {
+                lo = lo > p0 + 1 ? lo : p0 + 1;
+                if (n1 >= kp + 1) {
+                    if (p0 + 1 < hi) { hi = p0 + 1; cnt_hi = n1; }
                 } else {
-                    lo = c + 1;
-                    if (mode == 2) mode = 0; else steps++;
+                    lo = lo > p0 + 2 ? lo : p0 + 2;
+                }
+            }
+            // direction bookkeeping: keep walking / galloping while the same end moves, bisect after a flip
+            const int moved = (lo != lo_before ? 1 : 0) - (hi != hi_before ? 1 : 0);
+            if (first) { dir = moved; gal = 1; }
+            else if (moved == dir && dir != 0) gal <<= 1;
+            else dir = 0;
+            first = 0;
+            // ---- resolved: store and set up the next rank(s)
+            if (lo >= hi) {
+                int v = hi, cv = cnt_hi;
+#pragma unroll 1
+                for (;;) {
+                    if (t == 0) { r.mlo = v; cv_mlo = cv; }
+                    else if (t == 1) r.mhi = v;
+                    else if (t == 2) r.q1a = v;
+                    else if (t == 3) r.q1b = v;
+                    else if (t == 4) r.q3a = v;
+                    else r.q3b = v;
+                    t++;
+                    if (t >= nt) break;
+                    const int kprev = kp;
+                    kp = a.rk[t == 1 ? 3 : (t == 2 ? 0 : (t == 3 ? 1 : (t == 4 ? 4 : 5)))] + pad;
+                    if (t & 1) {  // second rank of a pair: the same value unless fewer than kp+1 samples are <= v
+                        if (kp == kprev || cv >= kp + 1) continue;
+                        lo = v + 1;
+                        hi = (t == 3) ? r.mlo : 255;
+                        cnt_hi = (t == 3) ? cv_mlo : cap;
+                        if (lo >= hi) { v = hi; cv = cnt_hi; continue; }
+                        first = 1; p_guess = lo; dir = 0; gal = 1;
+                    } else if (t == 2) {  // lower quartile: in [0, mlo]
+                        lo = 0; hi = r.mlo; cnt_hi = cv_mlo;
+                        if (lo >= hi) { v = hi; cv = cnt_hi; continue; }
+                        first = 1; p_guess = r.mlo - dq - 1; dir = 0; gal = 1;
+                    } else {  // upper quartile: in [mhi, 255]
+                        lo = r.mhi; hi = 255; cnt_hi = cap;
+                        if (lo >= hi) { v = hi; cv = cnt_hi; continue; }
+                        first = 1; p_guess = r.mhi + dq - 1; dir = 0; gal = 1;
+                    }
+                    break;
                 }
             }
         }
     }
-
-    // Two adjacent padded ranks kp1 <= kp2 <= kp1+1 with a first guess.
-    __device__ __forceinline__ void pair(const uint32_t (&x)[W4], int kp1, int kp2, int guess, int& v1, int& v2, uint32_t& f_at_g, int& g_used) {
-        int lo = 0, hi = 255, cnt_hi = cap, mode;
-        g_used = guess;
-        window3(x, kp1, g_used, lo, hi, cnt_hi, mode, f_at_g);
-        narrow(x, kp1, lo, hi, cnt_hi, mode);
-        v1 = lo;
-        v2 = v1;
-        const bool need = (kp2 != kp1) && (cnt_hi < kp2 + 1);  // the next order statistic is a larger value
-        if (__any_sync(0xffffffffu, need)) {
-            int lo2 = need ? v1 + 1 : 0, hi2 = need ? 255 : 0, cnt2 = cap;
-            narrow(x, kp2, lo2, hi2, cnt2, 1);
-            if (need) v2 = lo2;
-        }
-    }
-};
+}
 
 // ------------------------------------------------------------------------------------------------ exact pixel path
 // Line-for-line semantics of calc_pixel once medians / inverse IQRs are known, walking the window's frames from
@@ -451,24 +463,14 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
 template <int W4, int G>
 __device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], uint32_t ssum, const OutlierArgs& a,
                                            int pad, float& median, float& q1o, float& q3o, float& iqr_inv, int& center, float& halfw) {
-    Sel<W4, G> sel(cap);
-    int g = __float2int_rn((float)ssum * a.inv_n_sub);  // mean as the first guess
-    int mlo, mhi, gc;
-    uint32_t f_at_g;
-    sel.pair(xs, a.rk[2] + pad, a.rk[3] + pad, g, mlo, mhi, f_at_g, gc);
-    median = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
-    center = (mlo + mhi) >> 1;
+    BandRanks r;
+    band_solve<W4, G>(xs, ssum, a, pad, cap, r);
+    median = (r.mlo == r.mhi) ? (float)r.mlo : 0.5f * ((float)r.mlo + (float)r.mhi);  // src/chrono.rs:582-591
+    center = (r.mlo + r.mhi) >> 1;
     halfw = median - (float)center;
     if (!a.absolute) {  // quartiles (src/chrono.rs:559-579) and inverse IQR (:246-252)
-        // spread estimate for the quartile guesses: mean absolute deviation around the (clamped) guess
-        const float mad = ((float)f_at_g - (float)pad * (float)gc) * a.inv_n_sub;
-        const int dq = __float2int_rn(0.95f * mad);
-        int alo, ahi, blo, bhi, gdummy;
-        uint32_t dummy;
-        sel.pair(xs, a.rk[0] + pad, a.rk[1] + pad, mlo - dq, alo, ahi, dummy, gdummy);
-        sel.pair(xs, a.rk[4] + pad, a.rk[5] + pad, mhi + dq, blo, bhi, dummy, gdummy);
-        const float q1 = (a.rk[0] == a.rk[1]) ? (float)alo : (1.0f - a.q1_frac) * (float)alo + a.q1_frac * (float)ahi;
-        const float q3 = (a.rk[4] == a.rk[5]) ? (float)blo : (1.0f - a.q3_frac) * (float)blo + a.q3_frac * (float)bhi;
+        const float q1 = (a.rk[0] == a.rk[1]) ? (float)r.q1a : (1.0f - a.q1_frac) * (float)r.q1a + a.q1_frac * (float)r.q1b;
+        const float q3 = (a.rk[4] == a.rk[5]) ? (float)r.q3a : (1.0f - a.q3_frac) * (float)r.q3a + a.q3_frac * (float)r.q3b;
         q1o = q1;
         q3o = q3;
         float iq = q3 - q1;
@@ -478,11 +480,14 @@ __device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], ui
 }
 
 // ------------------------------------------------------------------------------------------------ K1
-// One warp = one tile slice: 32/G pixels x G lanes per pixel. Each lane keeps WPL 16-frame units per band in
-// registers (slot i of lane j holds frame group g0 + i*G + j), so the whole time series of the warp's pixels is
-// read from HBM exactly once with 128-bit loads that are contiguous per (band, group) row.
+// One warp = one tile slice: 32/G pixels x G lanes per pixel. A pixel-band's whole time series (WPL 16-frame units per
+// lane; slot i of lane j holds frame group g0 + i*G + j) is held in registers while its order statistics and its
+// certificate term are computed; the next pixel-band (next band of the same pixels, or the first band of the warp's next
+// tile slice) is already in flight into a second register set, so HBM latency overlaps the arithmetic and every byte of
+// the stack is read from HBM exactly once with 128-bit loads that are contiguous per (band, group) row.
 // Pixels whose "no outlier" certificate fails are queued in shared memory (per warp) with their medians and handled
-// by exact_pixel 32 at a time.
+// by exact_pixel 32 at a time. GENERIC = false is the whole-stack launch whose leading slots are all real frame groups;
+// GENERIC = true adds window masks, spare-capacity slots and the --sample subset.
 constexpr int kWarpsPerCta = 8;
 constexpr int kQueueCap = 64;  // per warp
 struct QueueEntry {
@@ -521,10 +526,20 @@ __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry*
     }
 }
 
-template <int C, int WPL, int G, bool SUB>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (C * WPL <= 24) ? 2 : 1) outlier_kernel(const __grid_constant__ OutlierArgs a) {
+__device__ __forceinline__ void set4(float (&v)[4], int c, float x) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
+}
+__device__ __forceinline__ void set4(uint32_t (&v)[4], int c, uint32_t x) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
+}
+
+template <int C, int WPL, int G, bool GENERIC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier_kernel(const __grid_constant__ OutlierArgs a) {
     constexpr int W4 = 4 * WPL;
     constexpr int PPW = 32 / G;
+    constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
     __shared__ QueueEntry s_queue[kWarpsPerCta][kQueueCap];
     const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     const int j = lane % G, pl = lane / G;
@@ -534,109 +549,119 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (C * WPL <= 24) ? 2 : 1) ou
     const int pad = cap - a.n_sub;  // zero bytes that take part in the selection
     const long long tbytes = tile_bytes(C, a.NG);
     const long long band_stride = (long long)a.NG * (kTilePixels * kUnitBytes);
+    const long long lane_off = ((long long)(a.g0 + j) * kTilePixels) * kUnitBytes;
     QueueEntry* queue = s_queue[warp_in_cta];
     int qcount = 0;
 
-    for (long long task = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); task < n_tasks; task += n_warps) {
+    uint32_t A[W4], B[W4];  // current / next pixel-band
+    auto load_band = [&](long long task, int c, uint32_t (&d)[W4]) {
+        const long long tile = task / G;
+        const int p = (int)(task % G) * PPW + pl;
+        const uint8_t* cb = a.stack + tile * tbytes + lane_off + (long long)p * kUnitBytes + c * band_stride;
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            uint4 v;
+            if (!GENERIC && i < WPL - 1) {
+                v = ldg_stream(cb + i * kSlotStride);
+            } else {
+                v = make_uint4(0, 0, 0, 0);
+                if (i * G + j < a.n_groups) v = ldg_stream(cb + i * kSlotStride);
+            }
+            d[4 * i + 0] = v.x; d[4 * i + 1] = v.y; d[4 * i + 2] = v.z; d[4 * i + 3] = v.w;
+        }
+    };
+
+    long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (task < n_tasks) load_band(task, 0, A);
+    while (task < n_tasks) {
         const long long tile = task / G;
         const int p = (int)(task % G) * PPW + pl;
         const long long pix = tile * kTilePixels + p;
         const bool valid = pix < a.n_pixels;
-        const uint8_t* tb = a.stack + tile * tbytes;
-        const uint8_t* lane_base = tb + ((long long)(a.g0 + j) * kTilePixels + p) * kUnitBytes;  // unit (c=0, slot 0) of this lane
-
-        // ---- load the time series (only HBM read of the kernel)
-        uint32_t x[C][W4];
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (i * G + j < a.n_groups) v = ldg_stream(lane_base + c * band_stride + (long long)i * (G * kTilePixels * kUnitBytes));
-                x[c][4 * i + 0] = v.x; x[c][4 * i + 1] = v.y; x[c][4 * i + 2] = v.z; x[c][4 * i + 3] = v.w;
-            }
-        }
-        if (a.window_masked) {  // frames outside the window must read as zero (whole-stack launches skip this)
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {
-                const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
-#pragma unroll
-                for (int c = 0; c < C; c++) { x[c][4 * i] &= m.x; x[c][4 * i + 1] &= m.y; x[c][4 * i + 2] &= m.z; x[c][4 * i + 3] &= m.w; }
-            }
-        }
-
-        // ---- per band: sum, order statistics
         float median[4] = {0, 0, 0, 0}, iqr_inv[4] = {0, 0, 0, 0}, q1v[4] = {0, 0, 0, 0}, q3v[4] = {0, 0, 0, 0};
-        int center[C];
-        float halfw[C];
-        uint32_t sum[C];
-#pragma unroll
+        uint32_t sum[4] = {0, 0, 0, 0};
+        uint32_t first_px = 0;  // bytes of window position 0, band c in byte c
+        float bound = 0.0f;
+#pragma unroll 1
         for (int c = 0; c < C; c++) {
-            center[c] = 0; halfw[c] = 0.0f; sum[c] = 0;
-            if (a.bg == 2 || a.w[c] != 0.0f) {  // window sum (IDP.4A: FMA pipe)
+            {   // ---- next pixel-band goes in flight before this one is processed
+                const bool last = (c == C - 1);
+                const long long nt = last ? task + n_warps : task;
+                if (nt < n_tasks) load_band(nt, last ? 0 : c + 1, B);
+            }
+            const float w = a.w[c];
+            if (GENERIC && a.window_masked) {  // frames outside the window must read as zero
+#pragma unroll
+                for (int i = 0; i < WPL; i++) {
+                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
+                    A[4 * i] &= m.x; A[4 * i + 1] &= m.y; A[4 * i + 2] &= m.z; A[4 * i + 3] &= m.w;
+                }
+            }
+            {   // window position 0 lives in slot 0 of lane j == 0; its byte index is uniform
+                const int wsel = (a.first_frame >> 2) & 3, sh = (a.first_frame & 3) * 8;
+                const uint32_t wv = wsel == 0 ? A[0] : (wsel == 1 ? A[1] : (wsel == 2 ? A[2] : A[3]));
+                first_px |= ((wv >> sh) & 0xffu) << (8 * c);
+            }
+            uint32_t bsum = 0;
+            if (a.bg == 2 || w != 0.0f) {  // window sum (IDP.4A: FMA pipe)
                 uint32_t s0 = 0, s1 = 0;
 #pragma unroll
-                for (int q = 0; q < W4; q += 2) { s0 = __dp4a(x[c][q], 0x01010101u, s0); s1 = __dp4a(x[c][q + 1], 0x01010101u, s1); }
-                sum[c] = group_sum<G>(s0 + s1);
+                for (int q = 0; q < W4; q += 2) { s0 = __dp4a(A[q], 0x01010101u, s0); s1 = __dp4a(A[q + 1], 0x01010101u, s1); }
+                bsum = group_sum<G>(s0 + s1);
+                set4(sum, c, bsum);
             }
-            if (a.w[c] != 0.0f) {
-                if (SUB) {
+            if (w != 0.0f) {
+                float med = 0.0f, q1 = 0.0f, q3 = 0.0f, iqi = 0.0f, halfw = 0.0f;
+                int center = 0;
+                if (GENERIC && a.smask) {  // --sample: order statistics on the subset only
                     uint32_t xs[W4];
                     uint32_t s = 0;
 #pragma unroll
                     for (int i = 0; i < WPL; i++) {
                         const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.smask) + (i * G + j));
-                        xs[4 * i] = x[c][4 * i] & m.x; xs[4 * i + 1] = x[c][4 * i + 1] & m.y;
-                        xs[4 * i + 2] = x[c][4 * i + 2] & m.z; xs[4 * i + 3] = x[c][4 * i + 3] & m.w;
+                        xs[4 * i] = A[4 * i] & m.x; xs[4 * i + 1] = A[4 * i + 1] & m.y;
+                        xs[4 * i + 2] = A[4 * i + 2] & m.z; xs[4 * i + 3] = A[4 * i + 3] & m.w;
                     }
 #pragma unroll
                     for (int q = 0; q < W4; q++) s = __dp4a(xs[q], 0x01010101u, s);
-                    band_stats<W4, G>(cap, xs, group_sum<G>(s), a, pad, median[c], q1v[c], q3v[c], iqr_inv[c], center[c], halfw[c]);
+                    band_stats<W4, G>(cap, xs, group_sum<G>(s), a, pad, med, q1, q3, iqi, center, halfw);
                 } else {
-                    band_stats<W4, G>(cap, x[c], sum[c], a, pad, median[c], q1v[c], q3v[c], iqr_inv[c], center[c], halfw[c]);
+                    band_stats<W4, G>(cap, A, bsum, a, pad, med, q1, q3, iqi, center, halfw);
                 }
-            }
-        }
-
-        uint4 x0[C];  // slot 0 as loaded (window position 0 for lane j == 0), before the certificate patch
-#pragma unroll
-        for (int c = 0; c < C; c++) x0[c] = make_uint4(x[c][0], x[c][1], x[c][2], x[c][3]);
-        // ---- certificate: an upper bound of every frame's distance to the median.
-        // Bytes that are not window frames (zero in the registers) are replaced by the band's centre value so that they
-        // contribute |c - c| = 0. Whole-stack launches only have such bytes in the last slot(s).
-        if (a.patch_slots) {
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {
-                if ((a.patch_slots >> i) & 1u) {
-                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        const uint32_t cc = rep4(center[c]);
-                        x[c][4 * i] |= cc & ~m.x; x[c][4 * i + 1] |= cc & ~m.y; x[c][4 * i + 2] |= cc & ~m.z; x[c][4 * i + 3] |= cc & ~m.w;
+                set4(median, c, med); set4(iqr_inv, c, iqi); set4(q1v, c, q1); set4(q3v, c, q3);
+                if (!(w < 0.0f)) {  // negative weights only lower dist_sq; NaN poisons the bound (-> exact path)
+                    // certificate term: an upper bound of |x - median| over the window's frames. Bytes that are not
+                    // window frames (zero in the registers) are replaced by the centre value, so they contribute 0.
+                    const uint32_t cc = rep4(center);
+                    {
+                        constexpr int i = WPL - 1;  // last slot: always (mask is all ones when nothing needs patching)
+                        const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
+                        A[4 * i] |= cc & ~m.x; A[4 * i + 1] |= cc & ~m.y; A[4 * i + 2] |= cc & ~m.z; A[4 * i + 3] |= cc & ~m.w;
                     }
+                    if (GENERIC && a.patch_slots) {
+#pragma unroll
+                        for (int i = 0; i < WPL - 1; i++) {
+                            const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
+                            A[4 * i] |= cc & ~m.x; A[4 * i + 1] |= cc & ~m.y; A[4 * i + 2] |= cc & ~m.z; A[4 * i + 3] |= cc & ~m.w;
+                        }
+                    }
+                    uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+                    for (int q = 0; q < W4; q += 2) {
+                        o0 |= absdiff4(A[q], cc);
+                        o1 |= absdiff4(A[q + 1], cc);
+                    }
+                    uint32_t o = o0 | o1;
+                    o |= o >> 16;
+                    o |= o >> 8;
+                    o = group_or<G>(o & 0xffu);  // >= max over frames of |x - centre| (OR dominates max)
+                    const float aw = a.absolute ? w : w * iqi;
+                    const float t = aw * ((float)o + halfw);
+                    bound += t * t;
                 }
             }
-        }
-        float bound = 0.0f;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const float w = a.w[c];
-            if (w != 0.0f && !(w < 0.0f)) {  // negative weights only lower dist_sq; NaN poisons the bound (-> exact path)
-                const uint32_t cc = rep4(center[c]);
-                uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-                for (int q = 0; q < W4; q += 2) {
-                    o0 |= absdiff4(x[c][q], cc);
-                    o1 |= absdiff4(x[c][q + 1], cc);
-                }
-                uint32_t o = o0 | o1;
-                o |= o >> 16;
-                o |= o >> 8;
-                o = group_or<G>(o & 0xffu);  // >= max over frames of |x - centre| (OR dominates max)
-                const float aw = a.absolute ? w : w * iqr_inv[c];
-                const float t = aw * ((float)o + halfw[c]);
-                bound += t * t;
-            }
+            for (int q = 0; q < W4; q++) A[q] = B[q];
         }
         const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
 
@@ -651,17 +676,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (C * WPL <= 24) ? 2 : 1) ou
 #pragma unroll
                 for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(median[c]));  // :340-345
             } else if (a.bg == 0) {
-                // frame of window position 0 lives in slot 0 of lane j == 0 (this lane); its byte index is uniform
-                const int wsel = (a.first_frame >> 2) & 3, sh = (a.first_frame & 3) * 8;
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const uint32_t wv = wsel == 0 ? x0[c].x : (wsel == 1 ? x0[c].y : (wsel == 2 ? x0[c].z : x0[c].w));
-                    pixel[c] = (uint8_t)((wv >> sh) & 0xffu);
-                }
+                for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((first_px >> (8 * c)) & 0xffu);  // :348-350
             } else {
                 const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)a.n);  // :357
                 const int f = __ldg(a.win_frames + pos);
-                const PixelSrc src{tb, a.NG, C, p};
+                const PixelSrc src{a.stack + tile * tbytes, a.NG, C, p};
 #pragma unroll
                 for (int c = 0; c < C; c++) pixel[c] = src.at(f, c);
             }
@@ -696,6 +716,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (C * WPL <= 24) ? 2 : 1) ou
             while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
             __syncwarp();
         }
+        task += n_warps;
     }
     __syncwarp();
     if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
@@ -827,9 +848,9 @@ __global__ void __launch_bounds__(256) simple_int_kernel(const __grid_constant__
             uint32_t best_e = darker ? 0xffffffffu : 0u, best_o = best_e;  // even frames (0,2) / odd frames (1,3) of each word
 #pragma unroll
             for (int gg = 0; gg < kChunkGroups; gg++) {
+                if (g_base + gg >= a.n_groups) break;  // uniform: the last chunk may be short
                 uint4 m = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-                if (g_base + gg >= a.n_groups) m = make_uint4(0, 0, 0, 0);
-                else if (a.wmask) m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (g_base + gg));
+                if (a.wmask) m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (g_base + gg));
 #pragma unroll
                 for (int wq = 0; wq < 4; wq++) {
                     const uint32_t mw = wq == 0 ? m.x : (wq == 1 ? m.y : (wq == 2 ? m.z : m.w));
