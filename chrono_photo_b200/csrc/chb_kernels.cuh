@@ -79,36 +79,25 @@ struct OutlierArgs {
 // and the k-th smallest value is min{c : #{x <= c} >= k+1}. Bytes that are not part of the sample are zero, which
 // shifts every rank by the (known) number of such bytes.
 //
-// One probe evaluates F at p0, p0+1, p0+2 (three independent accumulator chains over the same registers) and yields the
-// two exact counts #{x <= p0} and #{x <= p0+1}; both differences are biased, packed into one word and reduced over the
-// G lanes with a single shuffle sequence. A bracket [lo, hi] per pixel-band is narrowed by the same rule for every
-// probe; p0 starts at (guess - 1), then walks / gallops in the direction of the answer, then bisects. All ranks a band
-// needs (median pair; quartile pairs for relative thresholds) run through ONE warp-synchronous loop as a per-lane state
-// machine, so lanes that finish a rank early move on to their next rank instead of idling.
+// Every iteration evaluates F at two points per lane (four accumulator chains over the same registers). A rank starts
+// with a "jump" at a guess g (F(g), F(g+1) -> #{x <= g}), then walks away from g two values per iteration, re-using the
+// F value at the edge of the known range so that two new evaluations give two new counts; after three walking steps it
+// bisects. All ranks a band needs (median pair; quartile pairs for relative thresholds) run through ONE warp-synchronous
+// loop as a per-lane state machine, so lanes that finish a rank early move on to their next rank instead of idling.
 template <int W4, int G>
 struct Sel {
-    // counts n0 = #{x <= p0}, n1 = #{x <= p0+1} over the G lanes of the pixel-band; p0 in [0, 253]
-    static __device__ __forceinline__ void probe(const uint32_t (&x)[W4], int p0, int& n0, int& n1, uint32_t& f_mid, bool want_f) {
-        const uint32_t c1 = rep4(p0 + 1), c0 = c1 - 0x01010101u, c2 = c1 + 0x01010101u;
-        uint32_t f0 = 0, f1 = 0, f2 = 0, h0 = 0, h1 = 0, h2 = 0;
+    static __device__ __forceinline__ void eval2(const uint32_t (&x)[W4], int e1, int e2, uint32_t& f1, uint32_t& f2) {
+        const uint32_t c1 = rep4(e1), c2 = rep4(e2);
+        uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
 #pragma unroll
         for (int q = 0; q < W4; q += 2) {
-            f0 = sad4_acc(x[q], c0, f0);
-            f1 = sad4_acc(x[q], c1, f1);
-            f2 = sad4_acc(x[q], c2, f2);
-            h0 = sad4_acc(x[q + 1], c0, h0);
-            h1 = sad4_acc(x[q + 1], c1, h1);
-            h2 = sad4_acc(x[q + 1], c2, h2);
+            a1 = sad4_acc(x[q], c1, a1);
+            a2 = sad4_acc(x[q], c2, a2);
+            b1 = sad4_acc(x[q + 1], c1, b1);
+            b2 = sad4_acc(x[q + 1], c2, b2);
         }
-        f0 += h0; f1 += h1; f2 += h2;
-        // per lane |F(c+1) - F(c)| <= bytes per lane (= 16 * W4 / 4 * ... = 4 * W4): bias by that, pack, reduce once
-        constexpr uint32_t kBias = 4 * W4;
-        uint32_t packed = (f1 - f0 + kBias) | ((f2 - f1 + kBias) << 16);
-        packed = group_sum<G>(packed);
-        n0 = (int)((packed & 0xffffu) >> 1);  // sum(d + bias) = 2 * count because G * bias = cap
-        n1 = (int)(packed >> 17);
-        f_mid = 0;
-        if (want_f) f_mid = group_sum<G>(f1);  // F(p0 + 1), only for the spread estimate of relative thresholds
+        f1 = group_sum<G>(a1 + b1);
+        f2 = group_sum<G>(a2 + b2);
     }
 };
 
@@ -116,57 +105,80 @@ struct BandRanks {  // results of one pixel-band
     int mlo, mhi, q1a, q1b, q3a, q3b;
 };
 
-// Solves the median pair (and the two quartile pairs when rel) of one pixel-band. rk: padded ranks are a.rk[] + pad.
+// Solves the median pair (and the two quartile pairs when rel) of one pixel-band; padded ranks are a.rk[] + pad.
 template <int W4, int G>
-__device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssum, const OutlierArgs& a, int pad, int cap, BandRanks& r) {
+__device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssum, float inv_cnt, const OutlierArgs& a, int pad, int cap, BandRanks& r) {
     const bool rel = !a.absolute;
     const int nt = rel ? 6 : 2;  // targets in processing order: m1, m2, q1a, q1b, q3a, q3b
-    int t = 0, lo = 0, hi = 255, cnt_hi = cap, dir = 0, gal = 1, first = 1;
-    int kp = a.rk[2] + pad;
-    int p_guess = __float2int_rn((float)ssum * a.inv_n_sub) - 1;  // mean as the first guess for the median
+    // per-lane state: target t, its padded rank kp; phase 0 = jump at g, 1 = walking from edge (pe, fe = F(pe)), 2 = bisecting [lo, hi]
+    int t = 0, kp = a.rk[2] + pad, phase = 0, steps = 0;
+    int g = __float2int_rn((float)ssum * inv_cnt);  // mean as the first guess for the median
+    g = g < 0 ? 0 : (g > 254 ? 254 : g);
+    bool up = false;
+    int pe = 0, hi_cnt = cap, lo = 0, hi = 255;
+    uint32_t fe = 0;
     int cv_mlo = cap, dq = 0;
     r.mlo = r.mhi = r.q1a = r.q1b = r.q3a = r.q3b = 0;
     while (__any_sync(0xffffffffu, t < nt)) {
         const bool act = t < nt;
-        // ---- choose the probe
-        int p0;
-        if (first) p0 = p_guess;
-        else if (hi - lo <= 2) p0 = lo;
-        else if (dir > 0) { p0 = lo + gal - 1; p0 = p0 < hi - 2 ? p0 : hi - 2; }
-        else if (dir < 0) { p0 = hi - 1 - gal; p0 = p0 > lo ? p0 : lo; }
-        else p0 = ((lo + hi) >> 1) - 1;
-        p0 = p0 < 0 ? 0 : (p0 > 253 ? 253 : p0);
-        if (!act) p0 = 0;
-        int n0, n1;
-        uint32_t f_mid;
-        Sel<W4, G>::probe(x, p0, n0, n1, f_mid, rel && t == 0 && first);
+        // ---- the two evaluation points of this lane
+        int e1, e2;
+        if (phase == 0) { e1 = g; e2 = g + 1; }
+        else if (phase == 1) {
+            const int d = up ? 1 : -1;
+            e1 = pe + d; e2 = pe + 2 * d;
+            e2 = e2 < 0 ? 0 : (e2 > 255 ? 255 : e2);
+        } else { e1 = (lo + hi) >> 1; e2 = e1 + 1; }
+        if (!act) { e1 = 0; e2 = 0; }
+        uint32_t f1, f2;
+        Sel<W4, G>::eval2(x, e1, e2, f1, f2);
         if (act) {
-            if (rel && t == 0 && first) {
-                // spread estimate for the quartile guesses: mean absolute deviation around the guess
-                const float mad = ((float)f_mid - (float)pad * (float)(p0 + 1)) * a.inv_n_sub;
-                dq = __float2int_rn(0.95f * mad);
-            }
-            // ---- universal bracket update from #{x <= p0} and #{x <= p0+1}
-            const int lo_before = lo, hi_before = hi;
-            if (n0 >= kp + 1) {
-                if (p0 < hi) { hi = p0; cnt_hi = n0; }
-            } else {
-                lo = lo > p0 + 1 ? lo : p0 + 1;
-                if (n1 >= kp + 1) {
-                    if (p0 + 1 < hi) { hi = p0 + 1; cnt_hi = n1; }
-                } else {
-                    lo = lo > p0 + 2 ? lo : p0 + 2;
+            bool res = false, has_next = false;
+            int v = 0, cv = cap;
+            uint32_t fnext = 0;  // F(v + 1) when has_next
+            if (phase == 0) {
+                const int n = ((int)f2 - (int)f1 + cap) >> 1;  // #{x <= g}
+                if (rel && t == 0) {  // spread estimate for the quartile guesses: mean absolute deviation around g
+                    const float mad = ((float)f1 - (float)pad * (float)g) * a.inv_n_sub;
+                    dq = __float2int_rn(0.95f * mad);
                 }
+                up = kp >= n;
+                phase = 1; steps = 0;
+                if (up) {
+                    pe = g + 1; fe = f2;
+                    if (pe == 255) { res = true; v = 255; cv = cap; }
+                } else {
+                    pe = g; fe = f1; hi_cnt = n;
+                    if (pe == 0) { res = true; v = 0; cv = n; }
+                }
+            } else if (phase == 1) {
+                if (up) {  // invariant: #{x <= pe-1} <= kp
+                    const int n1 = ((int)f1 - (int)fe + cap) >> 1;                            // #{x <= pe}
+                    const int n2 = (pe + 1 >= 255) ? cap : (((int)f2 - (int)f1 + cap) >> 1);  // #{x <= pe+1}
+                    if (n1 >= kp + 1) { res = true; v = pe; cv = n1; fnext = f1; has_next = true; }
+                    else if (n2 >= kp + 1) { res = true; v = pe + 1; cv = n2; fnext = f2; has_next = (pe + 2 <= 255); }
+                    else { pe += 2; fe = f2; steps++; }
+                } else {  // invariant: #{x <= pe} = hi_cnt >= kp+1
+                    const int n1 = ((int)fe - (int)f1 + cap) >> 1;                       // #{x <= pe-1}
+                    const int n2 = (pe - 2 < 0) ? 0 : (((int)f1 - (int)f2 + cap) >> 1);  // #{x <= pe-2}
+                    if (kp >= n1) { res = true; v = pe; cv = hi_cnt; }
+                    else if (kp >= n2) { res = true; v = pe - 1; cv = n1; fnext = fe; has_next = true; }
+                    else { pe -= 2; fe = f2; hi_cnt = n2; steps++; }
+                }
+                if (!res && steps >= 3) {  // far from the guess: bisect what is left
+                    phase = 2;
+                    lo = up ? pe : 0;
+                    hi = up ? 255 : pe;
+                    if (up) hi_cnt = cap;
+                    if (lo >= hi) { res = true; v = hi; cv = hi_cnt; }
+                }
+            } else {
+                const int n = ((int)f2 - (int)f1 + cap) >> 1;  // #{x <= e1}
+                if (n >= kp + 1) { hi = e1; hi_cnt = n; } else lo = e1 + 1;
+                if (lo >= hi) { res = true; v = hi; cv = hi_cnt; }
             }
-            // direction bookkeeping: keep walking / galloping while the same end moves, bisect after a flip
-            const int moved = (lo != lo_before ? 1 : 0) - (hi != hi_before ? 1 : 0);
-            if (first) { dir = moved; gal = 1; }
-            else if (moved == dir && dir != 0) gal <<= 1;
-            else dir = 0;
-            first = 0;
-            // ---- resolved: store and set up the next rank(s)
-            if (lo >= hi) {
-                int v = hi, cv = cnt_hi;
+            // ---- resolved: store, then set up the next rank(s) of this lane
+            if (res) {
 #pragma unroll 1
                 for (;;) {
                     if (t == 0) { r.mlo = v; cv_mlo = cv; }
@@ -181,19 +193,17 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
                     kp = a.rk[t == 1 ? 3 : (t == 2 ? 0 : (t == 3 ? 1 : (t == 4 ? 4 : 5)))] + pad;
                     if (t & 1) {  // second rank of a pair: the same value unless fewer than kp+1 samples are <= v
                         if (kp == kprev || cv >= kp + 1) continue;
-                        lo = v + 1;
-                        hi = (t == 3) ? r.mlo : 255;
-                        cnt_hi = (t == 3) ? cv_mlo : cap;
-                        if (lo >= hi) { v = hi; cv = cnt_hi; continue; }
-                        first = 1; p_guess = lo; dir = 0; gal = 1;
-                    } else if (t == 2) {  // lower quartile: in [0, mlo]
-                        lo = 0; hi = r.mlo; cnt_hi = cv_mlo;
-                        if (lo >= hi) { v = hi; cv = cnt_hi; continue; }
-                        first = 1; p_guess = r.mlo - dq - 1; dir = 0; gal = 1;
-                    } else {  // upper quartile: in [mhi, 255]
-                        lo = r.mhi; hi = 255; cnt_hi = cap;
-                        if (lo >= hi) { v = hi; cv = cnt_hi; continue; }
-                        first = 1; p_guess = r.mhi + dq - 1; dir = 0; gal = 1;
+                        // answer >= v+1: walk up from there (v < 255 because cv < cap)
+                        if (has_next) {
+                            phase = 1; up = true; pe = v + 1; fe = fnext; steps = 0;
+                            if (pe == 255) { v = 255; cv = cap; has_next = false; continue; }
+                        } else {
+                            phase = 0; g = v + 1 > 254 ? 254 : v + 1;
+                        }
+                    } else {  // first rank of a quartile pair: jump at median -/+ spread
+                        g = (t == 2) ? r.mlo - dq : r.mhi + dq;
+                        g = g < 0 ? 0 : (g > 254 ? 254 : g);
+                        phase = 0;
                     }
                     break;
                 }
@@ -461,10 +471,10 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
 
 // Median (and, for relative thresholds, quartiles and the inverse IQR) of one pixel-band (src/chrono.rs:238-255).
 template <int W4, int G>
-__device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], uint32_t ssum, const OutlierArgs& a,
+__device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], uint32_t ssum, float inv_cnt, const OutlierArgs& a,
                                            int pad, float& median, float& q1o, float& q3o, float& iqr_inv, int& center, float& halfw) {
     BandRanks r;
-    band_solve<W4, G>(xs, ssum, a, pad, cap, r);
+    band_solve<W4, G>(xs, ssum, inv_cnt, a, pad, cap, r);
     median = (r.mlo == r.mhi) ? (float)r.mlo : 0.5f * ((float)r.mlo + (float)r.mhi);  // src/chrono.rs:582-591
     center = (r.mlo + r.mhi) >> 1;
     halfw = median - (float)center;
@@ -624,9 +634,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
                     }
 #pragma unroll
                     for (int q = 0; q < W4; q++) s = __dp4a(xs[q], 0x01010101u, s);
-                    band_stats<W4, G>(cap, xs, group_sum<G>(s), a, pad, med, q1, q3, iqi, center, halfw);
+                    band_stats<W4, G>(cap, xs, group_sum<G>(s), a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
                 } else {
-                    band_stats<W4, G>(cap, A, bsum, a, pad, med, q1, q3, iqi, center, halfw);
+                    band_stats<W4, G>(cap, A, bsum, a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
                 }
                 set4(median, c, med); set4(iqr_inv, c, iqi); set4(q1v, c, q1); set4(q3v, c, q3);
                 if (!(w < 0.0f)) {  // negative weights only lower dist_sq; NaN poisons the bound (-> exact path)
