@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the compositing hot path (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one pass of the hot path over one frame stack. Default workload = BASELINE.json configs[2]:
+`--mode outlier -t abs/0.05/0.2 -l extreme -b first`, 200 frames x 6000x4000 RGB8 (synthetic series S2, seed 42),
+row-sharded over the ranks (strong scaling: the image is fixed, every rank owns H/N rows; no data-path collective).
+value  = pixel-frames/s, stack resident in HBM, CUDA events around K steps, max over ranks.
+e2e    = same metric through the C ABI with pinned HOST frames: H2D upload of all frames + kernel + D2H of composite and
+         mask inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (mode, frames, height, width, synthetic kind, description)
+    "c3-outlier-abs-extreme": ("outlier", 200, 4000, 6000, 2, "--mode outlier -t abs/0.05/0.2 -l extreme -b first, 200 x 6000x4000 RGB8"),
+    "c2-darker": ("darker", 200, 4000, 6000, 2, "--mode darker, 200 x 6000x4000 RGB8"),
+    "c2-lighter": ("lighter", 200, 4000, 6000, 2, "--mode lighter, 200 x 6000x4000 RGB8"),
+    "c4-outlier-rel-forward": ("outlier-rel", 1000, 2160, 3840, 2, "--mode outlier -t rel/3.0/5.0 -l forward -b first, 1000 x 3840x2160 RGB8"),
+    "c1-minimal": ("outlier-c1", 25, 768, 1024, 1, "cmd_examples/minimal: defaults abs/0.05/0.2, extreme, 25 x 1024x768 RGB8 (background first)"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def traffic_from_profiles(kernel_key):
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        t = json.load(open(path))[kernel_key]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def make_processor(cp, mode, seed=42, pixel_offset=0):
+    if mode in ("outlier", "outlier-c1"):
+        return cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), cp.BackgroundMode.FIRST, cp.OutlierSelectionMode.EXTREME, seed=seed, pixel_offset=pixel_offset)
+    if mode == "outlier-rel":
+        return cp.OutlierProcessor(cp.Threshold.rel(3.0, 5.0), cp.BackgroundMode.FIRST, cp.OutlierSelectionMode.ALL_FORWARD, seed=seed, pixel_offset=pixel_offset)
+    return cp.SimpleProcessor(darker=(mode == "darker"))
+
+
+def oracle_call(orc, mode, st, n_threads):
+    if mode in ("outlier", "outlier-c1"):
+        return orc.outlier(st, orc.threshold(True, 0.05, 0.2), 0, 2, n_threads=n_threads)
+    if mode == "outlier-rel":
+        return orc.outlier(st, orc.threshold(False, 3.0, 5.0), 0, 4, n_threads=n_threads)
+    return orc.simple(st, mode == "darker", n_threads=n_threads)
+
+
+def cpu_sample(cp, kind, n, H, W, rows, row0):
+    import numpy as np
+    return np.stack([cp.synth_frame_host(kind, 42, f, n, W, H, 3, row0=row0, rows=rows) for f in range(n)])
+
+
+def time_cpu(orc, cp, mode, kind, n, H, W, n_threads, target_s=12.0):
+    """Times the oracle (CPU port of the reference algorithm) on a bounded row band of the same workload."""
+    rows = 2
+    st = cpu_sample(cp, kind, n, H, W, rows, H // 2)
+    t0 = time.perf_counter(); oracle_call(orc, mode, st, n_threads); dt = time.perf_counter() - t0
+    rate = n * rows * W / max(dt, 1e-6)
+    rows = int(max(n_threads, min(H, rate * target_s / (n * W))))
+    rows = max(rows - rows % max(1, n_threads), n_threads) if rows >= n_threads else rows
+    rows = min(rows, 256)  # generating the sample is itself CPU work
+    st = cpu_sample(cp, kind, n, H, W, rows, min(H // 2, H - rows))
+    t0 = time.perf_counter(); oracle_call(orc, mode, st, n_threads); dt = time.perf_counter() - t0
+    return n * rows * W / dt, rows, dt, st
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the Rust crate cannot be built here: no cargo)
+    with all host threads on a bounded sample of the workload. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    import chrono_photo_b200 as cp
+    mode, n, H, W, kind, desc = WORKLOADS[wl]
+    cores = os.cpu_count() or 1
+    rate, rows, dt, st = time_cpu(orc, cp, mode, kind, n, H, W, cores, target_s=3.0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter(); oracle_call(orc, mode, st, cores); t = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(t)
+    ms = 1e3 * sum(times) / len(times)
+    value = n * rows * W / (ms / 1e3)
+    sample = f"rows [{min(H // 2, H - rows)}, +{rows}) x {W} px x {n} frames of the workload per step, in-memory stack (no JPEG decode / temp files)"
+    print(json.dumps({
+        "impl": "reference", "metric": "pixel-frames/s", "value": value, "unit": "pixel-frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": wl, "description": desc, "frames": n, "height": H, "width": W, "channels": 3},
+        "cpu_baseline": {"value": value, "unit": "pixel-frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pixel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU port of chrono-photo's algorithm (oracle/chrono_oracle.c), row-parallel over all host threads; the reference itself runs "
+                "outlier photos single-threaded (src/chrono.rs:96,169)"}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3-outlier-abs-extreme", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = args.workload
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import numpy as np
+    import torch
+    import chrono_photo_b200 as cp
+    from chrono_photo_b200 import _lib
+    from chrono_photo_b200.sharding import shard_rows
+
+    mode, n, H, W, kind, desc = WORKLOADS[wl]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the compositing path has no CPU fallback")
+    multi_proc = world > 1
+    if multi_proc:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        devices, shard_rank, shard_world = [local_rank], rank, world
+    else:
+        devices, shard_rank, shard_world = list(range(args.gpus)), 0, 1  # one process drives all GPUs through one context
+        torch.cuda.set_device(0)
+    n_gpus = world if multi_proc else args.gpus
+
+    row0, rows = shard_rows(H, shard_rank, shard_world)
+    ctx = cp.Context(devices)
+    if len(devices) == 1:
+        ctx.set_stream(0, torch.cuda.current_stream().cuda_stream)  # torch events then bracket the launches
+    stack = cp.FrameStack(ctx, W, rows, 3, n)
+    stack.fill_synthetic(kind, seed=42, row0_global=row0, full_height=H)
+    proc = make_processor(cp, mode, pixel_offset=row0 * W)
+    is_outlier = mode.startswith("outlier")
+
+    def barrier():
+        if multi_proc:
+            dist.barrier()
+        for d in devices:
+            torch.cuda.synchronize(d)
+
+    def max_over_ranks(x):
+        if not multi_proc:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- kernel-only: stack resident in HBM
+    for _ in range(args.warmup):
+        proc.process_device(stack)
+    sampler = ClockSampler(devices[0])
+    barrier()
+    _lib.lib().chb_launch_count_reset()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    launch_ms = []
+    for _ in range(args.steps):
+        launch_ms.append(proc.process_device(stack))
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = int(_lib.lib().chb_launch_count())
+    ms_total = ev0.elapsed_time(ev1) if len(devices) == 1 else t_wall * 1e3
+    ms_step = max_over_ranks(ms_total / args.steps)
+    kernel_ms = max_over_ranks(sum(launch_ms) / len(launch_ms))
+    total_pf = float(n) * H * W
+    value = total_pf / (ms_step / 1e3)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes of this rank's shard / its average launch duration)
+    P_shard = rows * W
+    alg_bytes = P_shard * 3 * (n + (2 if is_outlier else 1))  # read the stack once + composite (+ mask) write
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    kernel_name = "outlier_kernel" if is_outlier else "simple_int_kernel"
+    traffic = traffic_from_profiles(kernel_name + ":" + wl) if n_gpus == 1 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "peak_source": peak_src,
+                "slow_path_pixels_per_launch": int(_lib.lib().chb_last_slow_pixels()) if is_outlier else 0}
+
+    # ---- end to end through the C ABI with pinned host frames
+    e2e = None
+    host = None
+    if not args.no_e2e:
+        frame_bytes = rows * W * 3
+        host = torch.empty((n, rows, W, 3), dtype=torch.uint8, pin_memory=True)
+        base, pitch = host.data_ptr(), W * 3
+        for f in range(n):
+            stack.download_raw(f, base + f * frame_bytes, pitch)  # host copy of the synthetic series
+        out_t = torch.empty((rows, W, 3), dtype=torch.uint8, pin_memory=True)
+        msk_t = torch.empty((rows, W, 3), dtype=torch.uint8, pin_memory=True)
+        out_np, msk_np = out_t.numpy(), msk_t.numpy()
+        stack2 = cp.FrameStack(ctx, W, rows, 3, n)
+
+        def e2e_step():
+            for f in range(n):
+                stack2.upload_raw(f, base + f * frame_bytes, pitch, pinned=True)
+            if is_outlier:
+                proc.process(stack2, out=out_np, mask_out=msk_np)
+            else:
+                _lib.check(_lib.lib().chb_simple(stack2._h, proc._params(), None, 0, out_np.ctypes.data))
+
+        e2e_step()  # warm-up (allocations, first-touch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        d2h = frame_bytes * (2 if is_outlier else 1)
+        e2e = {"value": total_pf / e2e_s, "unit": "pixel-frames/s", "h2d_bytes_per_step": n * frame_bytes * (shard_world if multi_proc else 1),
+               "d2h_bytes_per_step": d2h * (shard_world if multi_proc else 1), "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps}
+        stack2.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
+    cpu_baseline = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as orc
+        cores = os.cpu_count() or 1
+
+        def sample_rows(r):  # rows from the middle of the image, every frame
+            a0 = (rows - r) // 2
+            if e2e is not None:
+                return np.ascontiguousarray(host.numpy()[:, a0:a0 + r]), a0
+            return cpu_sample(cp, kind, n, H, W, r, row0 + a0), a0
+
+        def timed(r, threads):
+            st, a0 = sample_rows(r)
+            t0 = time.perf_counter(); oracle_call(orc, mode, st, threads); dt = time.perf_counter() - t0
+            return n * r * W / dt, dt
+
+        probe_rate, _ = timed(4 * cores if 4 * cores <= rows else rows, cores)
+        r_all = int(min(rows, max(cores, probe_rate * 12.0 / (n * W))))  # ~12 s of all-core work, at most the whole image
+        rate, dt = timed(r_all, cores)
+        cpu_baseline = {"value": rate, "unit": "pixel-frames/s", "cores": cores, "kind": "port",
+                        "sample": f"{r_all} of {H} rows x {W} px x {n} frames of the workload ({dt:.1f} s, row-parallel over all host threads), in-memory stack: "
+                                  "excludes the reference's JPEG decode, deflate/inflate and temp-file I/O (flatters the reference)"}
+        if is_outlier:  # reference-faithful threading: outlier photo compute is single-threaded (src/chrono.rs:96,169)
+            probe1, _ = timed(4, 1)
+            r1 = int(min(rows, max(1, probe1 * 8.0 / (n * W))))
+            rate1, dt1 = timed(r1, 1)
+            cpu_baseline["value_reference_threading"] = rate1
+            cpu_baseline["cores_reference_threading"] = 1
+            cpu_baseline["sample_reference_threading"] = f"{r1} rows ({dt1:.1f} s, one thread like src/chrono.rs:96,169)"
+    host = None
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "pixel-frames/s", "value": value, "unit": "pixel-frames/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl, "description": desc, "frames": n, "height": H, "width": W, "channels": 3, "series": f"S{kind} seed 42",
+                       "sharding": f"rows/{n_gpus}", "l2": "inputs (%.1f GB per GPU) larger than L2, no flush needed" % (stack.device_bytes(0) / 1e9),
+                       "launcher": "torchrun" if multi_proc else "single-process"},
+            "hbm_gbs": achieved * n_gpus if n_gpus > 1 else achieved,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
+    stack.close()
+    ctx.close()
+    if multi_proc:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

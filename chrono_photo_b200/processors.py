@@ -159,12 +159,13 @@ class OutlierProcessor:
         p.pixel_offset = self.pixel_offset
         return p
 
-    def process(self, stack, image_indices=None, want_mask=True, debug=False):
+    def process(self, stack, image_indices=None, want_mask=True, debug=False, out=None, mask_out=None):
         """OutlierProcessor::process (src/chrono.rs:73-206) -> (buffer, is_outlier) as (H, W, C) uint8 arrays.
-        debug=True additionally returns a dict of per-pixel sub-results (median, q1, q3, n_outliers)."""
+        debug=True additionally returns a dict of per-pixel sub-results (median, q1, q3, n_outliers).
+        out / mask_out: optional preallocated (e.g. pinned) C-contiguous uint8 arrays to receive the results."""
         shape = (stack.height, stack.width, stack.channels)
-        out = np.empty(shape, dtype=np.uint8)
-        mask = np.empty(shape, dtype=np.uint8) if want_mask else None
+        out = np.empty(shape, dtype=np.uint8) if out is None else out
+        mask = (np.empty(shape, dtype=np.uint8) if mask_out is None else mask_out) if want_mask else None
         ip, n, _keep = _indices(image_indices)
         warn = C.c_uint64(0)
         p = self._params()
