@@ -551,6 +551,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     OutlierKernel kern;
     if (st->C == 3) kern = generic ? kernel_for<3, true>(vidx) : kernel_for<3, false>(vidx);
     else kern = generic ? kernel_for<4, true>(vidx) : kernel_for<4, false>(vidx);
+    if (getenv("CHB_NO_PREFETCH") && st->C == 3 && !generic && vidx == 4) kern = outlier_kernel<3, 13, 1, false, false>;  // tuning aid
 
     const size_t P = (size_t)st->W * st->H;
     for (Band& b : st->bands) {

@@ -545,7 +545,7 @@ __device__ __forceinline__ void set4(uint32_t (&v)[4], int c, uint32_t x) {
     for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
 }
 
-template <int C, int WPL, int G, bool GENERIC>
+template <int C, int WPL, int G, bool GENERIC, bool PREFETCH = true>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier_kernel(const __grid_constant__ OutlierArgs a) {
     constexpr int W4 = 4 * WPL;
     constexpr int PPW = 32 / G;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
     };
 
     long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (task < n_tasks) load_band(task, 0, A);
+    if (PREFETCH && task < n_tasks) load_band(task, 0, A);
     while (task < n_tasks) {
         const long long tile = task / G;
         const int p = (int)(task % G) * PPW + pl;
@@ -594,10 +594,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
         float bound = 0.0f;
 #pragma unroll 1
         for (int c = 0; c < C; c++) {
-            {   // ---- next pixel-band goes in flight before this one is processed
+            if (PREFETCH) {  // ---- next pixel-band goes in flight before this one is processed
                 const bool last = (c == C - 1);
                 const long long nt = last ? task + n_warps : task;
                 if (nt < n_tasks) load_band(nt, last ? 0 : c + 1, B);
+            } else {
+                load_band(task, c, A);
             }
             const float w = a.w[c];
             if (GENERIC && a.window_masked) {  // frames outside the window must read as zero
@@ -670,8 +672,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
                     bound += t * t;
                 }
             }
+            if (PREFETCH) {
 #pragma unroll
-            for (int q = 0; q < W4; q++) A[q] = B[q];
+                for (int q = 0; q < W4; q++) A[q] = B[q];
+            }
         }
         const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
 
