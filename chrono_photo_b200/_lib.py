@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libchrono_b200.so")
+LIB_PATH = os.environ.get("CHB_LIB", os.path.join(HERE, "libchrono_b200.so"))  # CHB_LIB: tuning builds
 
 
 class ChbError(RuntimeError):

@@ -551,7 +551,6 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     OutlierKernel kern;
     if (st->C == 3) kern = generic ? kernel_for<3, true>(vidx) : kernel_for<3, false>(vidx);
     else kern = generic ? kernel_for<4, true>(vidx) : kernel_for<4, false>(vidx);
-    if (getenv("CHB_NO_PREFETCH") && st->C == 3 && !generic && vidx == 4) kern = outlier_kernel<3, 13, 1, false, false>;  // tuning aid
 
     const size_t P = (size_t)st->W * st->H;
     for (Band& b : st->bands) {
@@ -586,12 +585,14 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         }
         const long long n_tasks = b.n_tiles * var.g;
         int occ = 1;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 50));  // room for the per-warp queues of several CTAs
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+        const int smem = outlier_smem_bytes(var.wpl, var.g);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem));
         // persistent grid: every resident warp strides over the tile slices, so its exact-path queue fills up
-        const int blocks = grid_for(n_tasks * 32, 256, d.sm_count, std::max(1, occ));
+        const int blocks = grid_for(n_tasks * 32, kWarpsPerCta * 32, d.sm_count, std::max(1, occ));
         CU(cudaEventRecord(b.ev0, s));
-        kern<<<blocks, 256, 0, s>>>(ab);
+        kern<<<blocks, kWarpsPerCta * 32, smem, s>>>(ab);
         g_launches++;
         CU(cudaGetLastError());
         CU(cudaEventRecord(b.ev1, s));

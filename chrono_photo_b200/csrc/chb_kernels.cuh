@@ -43,6 +43,33 @@ __device__ __forceinline__ uint32_t group_or(uint32_t v) {
     return v;
 }
 
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier, used to stage the next pixel-band in shared memory
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (int spin = 0; !ok; spin++) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1 << 22)) asm volatile("trap;");  // a lost copy must abort the launch, never hang the GPU
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel arguments
 struct OutlierArgs {
     const uint8_t* stack;
@@ -498,7 +525,13 @@ __device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], ui
 // Pixels whose "no outlier" certificate fails are queued in shared memory (per warp) with their medians and handled
 // by exact_pixel 32 at a time. GENERIC = false is the whole-stack launch whose leading slots are all real frame groups;
 // GENERIC = true adds window masks, spare-capacity slots and the --sample subset.
-constexpr int kWarpsPerCta = 8;
+#ifndef CHB_WARPS
+#define CHB_WARPS 8
+#endif
+#ifndef CHB_MINB
+#define CHB_MINB 2
+#endif
+constexpr int kWarpsPerCta = CHB_WARPS;
 constexpr int kQueueCap = 64;  // per warp
 struct QueueEntry {
     long long pix;
@@ -545,12 +578,19 @@ __device__ __forceinline__ void set4(uint32_t (&v)[4], int c, uint32_t x) {
     for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
 }
 
-template <int C, int WPL, int G, bool GENERIC, bool PREFETCH = true>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier_kernel(const __grid_constant__ OutlierArgs a) {
+constexpr int kQueueBytes = kWarpsPerCta * kQueueCap * (int)sizeof(QueueEntry);
+constexpr int kBarBytes = 128;
+// dynamic shared memory of one CTA: exact-path queues, one mbarrier per warp, one staged pixel-band per warp (G == 1)
+__host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) { return kQueueBytes + kBarBytes + (g == 1 ? kWarpsPerCta * wpl * 512 : 0); }
+
+template <int C, int WPL, int G, bool GENERIC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 : CHB_MINB) outlier_kernel(const __grid_constant__ OutlierArgs a) {
     constexpr int W4 = 4 * WPL;
     constexpr int PPW = 32 / G;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
-    __shared__ QueueEntry s_queue[kWarpsPerCta][kQueueCap];
+    constexpr bool kStage = (G == 1);  // a tile's band is one contiguous slab: stage it with one TMA bulk copy per pixel-band
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    QueueEntry* const s_queue = reinterpret_cast<QueueEntry*>(smem_raw);
     const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     const int j = lane % G, pl = lane / G;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -560,10 +600,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
     const long long tbytes = tile_bytes(C, a.NG);
     const long long band_stride = (long long)a.NG * (kTilePixels * kUnitBytes);
     const long long lane_off = ((long long)(a.g0 + j) * kTilePixels) * kUnitBytes;
-    QueueEntry* queue = s_queue[warp_in_cta];
+    QueueEntry* queue = s_queue + warp_in_cta * kQueueCap;
     int qcount = 0;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + kQueueBytes) + warp_in_cta;
+    uint8_t* const stage = smem_raw + kQueueBytes + kBarBytes + warp_in_cta * (WPL * 512);
+    const int staged_groups = a.n_groups < WPL ? a.n_groups : WPL;
+    uint32_t parity = 0;
+    if (kStage) {
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+    }
+    auto stage_band = [&](long long task, int c) {  // one lane starts the copy of a whole pixel-band slab
+        if (lane == 0) {
+            const uint8_t* src = a.stack + task * tbytes + ((long long)c * a.NG + a.g0) * (kTilePixels * kUnitBytes);
+            mbar_expect_tx(bar, (uint32_t)staged_groups * 512u);
+            bulk_g2s(stage, src, (uint32_t)staged_groups * 512u, bar);
+        }
+    };
 
-    uint32_t A[W4], B[W4];  // current / next pixel-band
+    uint32_t A[W4];  // the current pixel-band
     auto load_band = [&](long long task, int c, uint32_t (&d)[W4]) {
         const long long tile = task / G;
         const int p = (int)(task % G) * PPW + pl;
@@ -582,7 +637,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
     };
 
     long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (PREFETCH && task < n_tasks) load_band(task, 0, A);
+    if (kStage && task < n_tasks) stage_band(task, 0);
     while (task < n_tasks) {
         const long long tile = task / G;
         const int p = (int)(task % G) * PPW + pl;
@@ -594,10 +649,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
         float bound = 0.0f;
 #pragma unroll 1
         for (int c = 0; c < C; c++) {
-            if (PREFETCH) {  // ---- next pixel-band goes in flight before this one is processed
+            if (kStage) {
+                // ---- the band was staged by a bulk copy issued one pixel-band ago: smem -> registers, then start the next copy
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+#pragma unroll
+                for (int i = 0; i < WPL; i++) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if ((!GENERIC && i < WPL - 1) || i < staged_groups) v = *reinterpret_cast<const uint4*>(stage + i * 512 + lane * 16);
+                    A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
+                }
+                __syncwarp();  // every lane has read the slab before the next copy may overwrite it
                 const bool last = (c == C - 1);
                 const long long nt = last ? task + n_warps : task;
-                if (nt < n_tasks) load_band(nt, last ? 0 : c + 1, B);
+                if (nt < n_tasks) stage_band(nt, last ? 0 : c + 1);
             } else {
                 load_band(task, c, A);
             }
@@ -671,10 +736,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? 3 : 2) outlier
                     const float t = aw * ((float)o + halfw);
                     bound += t * t;
                 }
-            }
-            if (PREFETCH) {
-#pragma unroll
-                for (int q = 0; q < W4; q++) A[q] = B[q];
             }
         }
         const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
