@@ -578,6 +578,9 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             if (dbg->n_outliers && !b.d_dbg_nout) CU(cudaMalloc(&b.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels));
             // the median plane drives the other debug stores inside the kernel
             if (!b.d_dbg_median && (dbg->q1 || dbg->q3)) CU(cudaMalloc(&b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (b.d_dbg_median) CU(cudaMemsetAsync(b.d_dbg_median, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
+            if (b.d_dbg_q1) CU(cudaMemsetAsync(b.d_dbg_q1, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
+            if (b.d_dbg_q3) CU(cudaMemsetAsync(b.d_dbg_q3, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
             ab.dbg_median = b.d_dbg_median;
             ab.dbg_q1 = dbg->q1 ? b.d_dbg_q1 : nullptr;
             ab.dbg_q3 = dbg->q3 ? b.d_dbg_q3 : nullptr;

@@ -133,77 +133,94 @@ struct BandRanks {  // results of one pixel-band
 };
 
 // Solves the median pair (and the two quartile pairs when rel) of one pixel-band; padded ranks are a.rk[] + pad.
+// The per-iteration bookkeeping is written with selects instead of branches: every lane runs the same short
+// instruction sequence whatever phase it is in; only "a rank has been resolved" takes a (divergent) branch.
 template <int W4, int G>
 __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssum, float inv_cnt, const OutlierArgs& a, int pad, int cap, BandRanks& r) {
     const bool rel = !a.absolute;
     const int nt = rel ? 6 : 2;  // targets in processing order: m1, m2, q1a, q1b, q3a, q3b
-    // per-lane state: target t, its padded rank kp; phase 0 = jump at g, 1 = walking from edge (pe, fe = F(pe)), 2 = bisecting [lo, hi]
-    int t = 0, kp = a.rk[2] + pad, phase = 0, steps = 0;
+    // per-lane state. mode 0: jump at g; 1: walking in direction d from edge b with fc = F(b); 2: bisecting [b, hi].
+    int t = 0, kp = a.rk[2] + pad, mode = 0, steps = 0, d = 1, b = 0, hi = 255, cnth = cap;
+    uint32_t fc = 0;
     int g = __float2int_rn((float)ssum * inv_cnt);  // mean as the first guess for the median
     g = g < 0 ? 0 : (g > 254 ? 254 : g);
-    bool up = false;
-    int pe = 0, hi_cnt = cap, lo = 0, hi = 255;
-    uint32_t fe = 0;
     int cv_mlo = cap, dq = 0;
     r.mlo = r.mhi = r.q1a = r.q1b = r.q3a = r.q3b = 0;
     while (__any_sync(0xffffffffu, t < nt)) {
         const bool act = t < nt;
+        const bool m0 = mode == 0, m1 = mode == 1;
+        const bool u = d > 0;
         // ---- the two evaluation points of this lane
-        int e1, e2;
-        if (phase == 0) { e1 = g; e2 = g + 1; }
-        else if (phase == 1) {
-            const int d = up ? 1 : -1;
-            e1 = pe + d; e2 = pe + 2 * d;
-            e2 = e2 < 0 ? 0 : (e2 > 255 ? 255 : e2);
-        } else { e1 = (lo + hi) >> 1; e2 = e1 + 1; }
-        if (!act) { e1 = 0; e2 = 0; }
+        int e2w = b + 2 * d;
+        const bool e2_out = (e2w < 0) | (e2w > 255);
+        e2w = e2w < 0 ? 0 : (e2w > 255 ? 255 : e2w);
+        const int mid = (b + hi) >> 1;
+        int e1 = m0 ? g : (m1 ? b + d : mid);
+        int e2 = m0 ? g + 1 : (m1 ? e2w : mid + 1);
+        e1 = act ? e1 : 0;
+        e2 = act ? e2 : 0;
         uint32_t f1, f2;
         Sel<W4, G>::eval2(x, e1, e2, f1, f2);
-        if (act) {
-            bool res = false, has_next = false;
-            int v = 0, cv = cap;
-            uint32_t fnext = 0;  // F(v + 1) when has_next
-            if (phase == 0) {
-                const int n = ((int)f2 - (int)f1 + cap) >> 1;  // #{x <= g}
-                if (rel && t == 0) {  // spread estimate for the quartile guesses: mean absolute deviation around g
-                    const float mad = ((float)f1 - (float)pad * (float)g) * a.inv_n_sub;
-                    dq = __float2int_rn(0.95f * mad);
+        // ---- counts
+        const int nj = ((int)f2 - (int)f1 + cap) >> 1;                         // jump / bisect: #{x <= e1}
+        const int n1 = ((u ? (int)f1 - (int)fc : (int)fc - (int)f1) + cap) >> 1;  // walk: #{x <= b} (up) / #{x <= b-1} (down)
+        int n2 = ((u ? (int)f2 - (int)f1 : (int)f1 - (int)f2) + cap) >> 1;       // walk: #{x <= b+1} (up) / #{x <= b-2} (down)
+        n2 = e2_out ? (u ? cap : 0) : n2;
+        if (rel && act && m0 && t == 0) {  // spread estimate for the quartile guesses: mean absolute deviation around g
+            const float mad = ((float)f1 - (float)pad * (float)g) * a.inv_n_sub;
+            dq = __float2int_rn(0.95f * mad);
+        }
+        // ---- mode 0: jump.  up0: the answer is above g
+        const bool up0 = kp >= nj;
+        // ---- mode 1: walk.  rb: resolved at b, rb1: resolved at b + d
+        const bool s1 = n1 >= kp + 1, s2 = n2 >= kp + 1;
+        const bool rb = (s1 == u), rb1 = !rb && (s2 == u);
+        // ---- mode 2: bisect
+        const bool ge = nj >= kp + 1;
+        // ---- new state
+        int nb, nhi = hi, ncnth = cnth, nmode = mode, nsteps = steps, nd = d;
+        uint32_t nfc = fc;
+        bool res;
+        int v, cv;
+        uint32_t fnext = 0;
+        bool has_next = false;
+        if (m0) {
+            nd = up0 ? 1 : -1;
+            nb = up0 ? g + 1 : g;
+            nfc = up0 ? f2 : f1;
+            ncnth = up0 ? cap : nj;
+            nmode = 1; nsteps = 0;
+            res = up0 ? (nb == 255) : (nb == 0);
+            v = nb; cv = ncnth;
+        } else if (m1) {
+            res = rb | rb1;
+            v = rb ? b : b + d;
+            cv = rb ? (u ? n1 : cnth) : (u ? n2 : n1);
+            fnext = rb ? f1 : (u ? f2 : fc);
+            has_next = rb ? u : (u ? (b + 2 <= 255) : true);
+            nb = b + 2 * d;
+            nfc = f2;
+            ncnth = u ? cnth : n2;
+            nsteps = steps + 1;
+            if (!res) {
+                if (u ? (nb >= 255) : (nb <= 0)) {  // walked into the end of the byte range
+                    res = true; v = u ? 255 : 0; cv = ncnth; has_next = false;
+                } else if (nsteps >= 3) {  // far from the guess: bisect what is left
+                    nmode = 2;
+                    nhi = u ? 255 : nb;
+                    nb = u ? nb : 0;
+                    ncnth = u ? cap : ncnth;
                 }
-                up = kp >= n;
-                phase = 1; steps = 0;
-                if (up) {
-                    pe = g + 1; fe = f2;
-                    if (pe == 255) { res = true; v = 255; cv = cap; }
-                } else {
-                    pe = g; fe = f1; hi_cnt = n;
-                    if (pe == 0) { res = true; v = 0; cv = n; }
-                }
-            } else if (phase == 1) {
-                if (up) {  // invariant: #{x <= pe-1} <= kp
-                    const int n1 = ((int)f1 - (int)fe + cap) >> 1;                            // #{x <= pe}
-                    const int n2 = (pe + 1 >= 255) ? cap : (((int)f2 - (int)f1 + cap) >> 1);  // #{x <= pe+1}
-                    if (n1 >= kp + 1) { res = true; v = pe; cv = n1; fnext = f1; has_next = true; }
-                    else if (n2 >= kp + 1) { res = true; v = pe + 1; cv = n2; fnext = f2; has_next = (pe + 2 <= 255); }
-                    else { pe += 2; fe = f2; steps++; }
-                } else {  // invariant: #{x <= pe} = hi_cnt >= kp+1
-                    const int n1 = ((int)fe - (int)f1 + cap) >> 1;                       // #{x <= pe-1}
-                    const int n2 = (pe - 2 < 0) ? 0 : (((int)f1 - (int)f2 + cap) >> 1);  // #{x <= pe-2}
-                    if (kp >= n1) { res = true; v = pe; cv = hi_cnt; }
-                    else if (kp >= n2) { res = true; v = pe - 1; cv = n1; fnext = fe; has_next = true; }
-                    else { pe -= 2; fe = f2; hi_cnt = n2; steps++; }
-                }
-                if (!res && steps >= 3) {  // far from the guess: bisect what is left
-                    phase = 2;
-                    lo = up ? pe : 0;
-                    hi = up ? 255 : pe;
-                    if (up) hi_cnt = cap;
-                    if (lo >= hi) { res = true; v = hi; cv = hi_cnt; }
-                }
-            } else {
-                const int n = ((int)f2 - (int)f1 + cap) >> 1;  // #{x <= e1}
-                if (n >= kp + 1) { hi = e1; hi_cnt = n; } else lo = e1 + 1;
-                if (lo >= hi) { res = true; v = hi; cv = hi_cnt; }
             }
+        } else {
+            nhi = ge ? e1 : hi;
+            ncnth = ge ? nj : cnth;
+            nb = ge ? b : e1 + 1;
+            res = nb >= nhi;
+            v = nhi; cv = ncnth;
+        }
+        if (act) {
+            b = nb; hi = nhi; cnth = ncnth; mode = nmode; steps = nsteps; d = nd; fc = nfc;
             // ---- resolved: store, then set up the next rank(s) of this lane
             if (res) {
 #pragma unroll 1
@@ -222,15 +239,15 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
                         if (kp == kprev || cv >= kp + 1) continue;
                         // answer >= v+1: walk up from there (v < 255 because cv < cap)
                         if (has_next) {
-                            phase = 1; up = true; pe = v + 1; fe = fnext; steps = 0;
-                            if (pe == 255) { v = 255; cv = cap; has_next = false; continue; }
+                            if (v + 1 == 255) { v = 255; cv = cap; has_next = false; continue; }
+                            mode = 1; d = 1; b = v + 1; fc = fnext; steps = 0; cnth = cap;
                         } else {
-                            phase = 0; g = v + 1 > 254 ? 254 : v + 1;
+                            mode = 0; g = v + 1 > 254 ? 254 : v + 1;
                         }
                     } else {  // first rank of a quartile pair: jump at median -/+ spread
                         g = (t == 2) ? r.mlo - dq : r.mhi + dq;
                         g = g < 0 ? 0 : (g > 254 ? 254 : g);
-                        phase = 0;
+                        mode = 0;
                     }
                     break;
                 }
@@ -516,15 +533,54 @@ __device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], ui
     }
 }
 
+// Straight-line median pair for the common case: F at five consecutive values p..p+4 around the band mean (ten
+// independent accumulator chains, no loop, no divergence) gives the four exact counts #{x <= p..p+3}; if both ranks fall
+// inside the window the pair is read off directly. Returns false when a rank lies outside (the pixel then takes the
+// iterative solver). The byte-range ends count as known: #{x <= -1} = 0, #{x <= 255} = cap.
+template <int W4, int G>
+__device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], uint32_t ssum, float inv_cnt, int kp1, int kp2, int cap, int& v1, int& v2) {
+    int p = __float2int_rn((float)ssum * inv_cnt) - 2;
+    p = p < 0 ? 0 : (p > 251 ? 251 : p);
+    const uint32_t c0 = rep4(p), c1 = c0 + 0x01010101u, c2 = c1 + 0x01010101u, c3 = c2 + 0x01010101u, c4 = c3 + 0x01010101u;
+    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+#pragma unroll
+    for (int q = 0; q < W4; q += 2) {
+        f0 = sad4_acc(x[q], c0, f0); f1 = sad4_acc(x[q], c1, f1); f2 = sad4_acc(x[q], c2, f2); f3 = sad4_acc(x[q], c3, f3); f4 = sad4_acc(x[q], c4, f4);
+        h0 = sad4_acc(x[q + 1], c0, h0); h1 = sad4_acc(x[q + 1], c1, h1); h2 = sad4_acc(x[q + 1], c2, h2); h3 = sad4_acc(x[q + 1], c3, h3);
+        h4 = sad4_acc(x[q + 1], c4, h4);
+    }
+    f0 += h0; f1 += h1; f2 += h2; f3 += h3; f4 += h4;
+    int n0, n1, n2, n3;
+    if (G == 1) {
+        n0 = ((int)f1 - (int)f0 + cap) >> 1; n1 = ((int)f2 - (int)f1 + cap) >> 1;
+        n2 = ((int)f3 - (int)f2 + cap) >> 1; n3 = ((int)f4 - (int)f3 + cap) >> 1;
+    } else {
+        // per lane |F(c+1) - F(c)| <= bytes per lane = 4*W4: bias, pack two differences per word, one reduction each
+        constexpr uint32_t kBias = 4 * W4;
+        uint32_t pa = (f1 - f0 + kBias) | ((f2 - f1 + kBias) << 16), pb = (f3 - f2 + kBias) | ((f4 - f3 + kBias) << 16);
+        pa = group_sum<G>(pa);
+        pb = group_sum<G>(pb);
+        n0 = (int)((pa & 0xffffu) >> 1); n1 = (int)(pa >> 17);  // sum(d + bias) = 2 * count because G * bias = cap
+        n2 = (int)((pb & 0xffffu) >> 1); n3 = (int)(pb >> 17);
+    }
+    v1 = p + (n0 <= kp1) + (n1 <= kp1) + (n2 <= kp1) + (n3 <= kp1);
+    v2 = p + (n0 <= kp2) + (n1 <= kp2) + (n2 <= kp2) + (n3 <= kp2);
+    return ((n0 <= kp1) || p == 0) && ((kp2 < n3) || p == 251);
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 // One warp = one tile slice: 32/G pixels x G lanes per pixel. A pixel-band's whole time series (WPL 16-frame units per
 // lane; slot i of lane j holds frame group g0 + i*G + j) is held in registers while its order statistics and its
-// certificate term are computed; the next pixel-band (next band of the same pixels, or the first band of the warp's next
-// tile slice) is already in flight into a second register set, so HBM latency overlaps the arithmetic and every byte of
-// the stack is read from HBM exactly once with 128-bit loads that are contiguous per (band, group) row.
-// Pixels whose "no outlier" certificate fails are queued in shared memory (per warp) with their medians and handled
-// by exact_pixel 32 at a time. GENERIC = false is the whole-stack launch whose leading slots are all real frame groups;
-// GENERIC = true adds window masks, spare-capacity slots and the --sample subset.
+// certificate term are computed. With G == 1 a tile's band is one contiguous slab of the stack, and the NEXT pixel-band
+// is staged into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier) while the current one is processed, so HBM
+// latency overlaps the arithmetic; every byte of the stack is read from HBM exactly once.
+// Three tiers per pixel:
+//   fast    absolute thresholds, every band's median pair inside the 5-value window, certificate holds -> done from registers
+//   hard    a median outside the window (or relative thresholds): iterative solver (band_solve); such pixels are queued per
+//           warp in shared memory and re-processed a warp-full at a time
+//   exact   certificate fails: exact_pixel walks the frames, 32 queued pixels at a time
+// GENERIC = false is the whole-stack launch whose leading slots are all real frame groups; GENERIC = true adds window
+// masks, spare-capacity slots and the --sample subset.
 #ifndef CHB_WARPS
 #define CHB_WARPS 8
 #endif
@@ -538,6 +594,11 @@ struct QueueEntry {
     float median[4];
     float iqr_inv[4];
 };
+constexpr int kQueueBytes = kWarpsPerCta * kQueueCap * (int)sizeof(QueueEntry);
+constexpr int kHardBytes = kWarpsPerCta * kQueueCap * (int)sizeof(long long);
+constexpr int kBarBytes = 128;
+// dynamic shared memory of one CTA: exact-path queues, hard-pixel queues, one mbarrier per warp, one staged pixel-band per warp (G == 1)
+__host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) { return kQueueBytes + kHardBytes + kBarBytes + (g == 1 ? kWarpsPerCta * wpl * 512 : 0); }
 
 template <int C>
 __device__ __forceinline__ void store_pixel(const OutlierArgs& a, long long pix, const uint8_t (&pixel)[4], uint8_t mask) {
@@ -578,10 +639,187 @@ __device__ __forceinline__ void set4(uint32_t (&v)[4], int c, uint32_t x) {
     for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
 }
 
-constexpr int kQueueBytes = kWarpsPerCta * kQueueCap * (int)sizeof(QueueEntry);
-constexpr int kBarBytes = 128;
-// dynamic shared memory of one CTA: exact-path queues, one mbarrier per warp, one staged pixel-band per warp (G == 1)
-__host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) { return kQueueBytes + kBarBytes + (g == 1 ? kWarpsPerCta * wpl * 512 : 0); }
+struct PixelAcc {  // what a pixel accumulates over its bands
+    float median[4], iqr_inv[4];
+    uint32_t sum[4];
+    uint32_t first_px;  // bytes of window position 0, band c in byte c
+    float bound;        // certificate: upper bound of dist_sq over the window's frames
+    bool hard;          // a median pair fell outside the 5-value window
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { median[i] = 0.0f; iqr_inv[i] = 0.0f; sum[i] = 0; }
+        first_px = 0; bound = 0.0f; hard = false;
+    }
+};
+
+// One pixel-band held in A: window mask, sum, order statistics, certificate term. FAST: try the straight-line window first
+// (absolute thresholds only); otherwise run the iterative solver.
+template <int C, int WPL, int G, bool GENERIC, bool FAST>
+__device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)[4 * WPL], int c, int j, long long pix, bool write_dbg,
+                                             int cap, int pad, PixelAcc& acc) {
+    constexpr int W4 = 4 * WPL;
+    const float w = a.w[c];
+    if (GENERIC && a.window_masked) {  // frames outside the window must read as zero
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
+            A[4 * i] &= m.x; A[4 * i + 1] &= m.y; A[4 * i + 2] &= m.z; A[4 * i + 3] &= m.w;
+        }
+    }
+    {   // window position 0 lives in slot 0 of lane j == 0; its byte index is uniform
+        const int wsel = (a.first_frame >> 2) & 3, sh = (a.first_frame & 3) * 8;
+        const uint32_t wv = wsel == 0 ? A[0] : (wsel == 1 ? A[1] : (wsel == 2 ? A[2] : A[3]));
+        acc.first_px |= ((wv >> sh) & 0xffu) << (8 * c);
+    }
+    uint32_t bsum = 0;
+    if (a.bg == 2 || w != 0.0f) {  // window sum (IDP.4A: FMA pipe)
+        uint32_t s0 = 0, s1 = 0;
+#pragma unroll
+        for (int q = 0; q < W4; q += 2) { s0 = __dp4a(A[q], 0x01010101u, s0); s1 = __dp4a(A[q + 1], 0x01010101u, s1); }
+        bsum = group_sum<G>(s0 + s1);
+        set4(acc.sum, c, bsum);
+    }
+    if (w == 0.0f) return;
+    float med = 0.0f, q1 = 0.0f, q3 = 0.0f, iqi = 0.0f, halfw = 0.0f;
+    int center = 0;
+    bool solved = false;
+    if (GENERIC && a.smask) {  // --sample: order statistics on the subset only
+        uint32_t xs[W4];
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.smask) + (i * G + j));
+            xs[4 * i] = A[4 * i] & m.x; xs[4 * i + 1] = A[4 * i + 1] & m.y;
+            xs[4 * i + 2] = A[4 * i + 2] & m.z; xs[4 * i + 3] = A[4 * i + 3] & m.w;
+        }
+#pragma unroll
+        for (int q = 0; q < W4; q++) s = __dp4a(xs[q], 0x01010101u, s);
+        band_stats<W4, G>(cap, xs, group_sum<G>(s), a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
+        solved = true;
+    } else if (FAST && a.absolute) {
+        int mlo, mhi;
+        const bool ok = band_window<W4, G>(A, bsum, a.inv_n_sub, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi);
+        acc.hard = acc.hard || !ok;
+        med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
+        center = (mlo + mhi) >> 1;
+        halfw = med - (float)center;
+        solved = true;
+    }
+    if (!solved) band_stats<W4, G>(cap, A, bsum, a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
+    set4(acc.median, c, med);
+    set4(acc.iqr_inv, c, iqi);
+    if (a.dbg_median && write_dbg) {  // per-band sub-results (planes are zeroed by the host)
+        a.dbg_median[pix * 4 + c] = med;
+        if (a.dbg_q1) a.dbg_q1[pix * 4 + c] = q1;
+        if (a.dbg_q3) a.dbg_q3[pix * 4 + c] = q3;
+    }
+    if (!(w < 0.0f)) {  // negative weights only lower dist_sq; NaN poisons the bound (-> exact path)
+        // certificate term: an upper bound of |x - median| over the window's frames. Bytes that are not window frames
+        // (zero in the registers) are replaced by the centre value, so they contribute 0.
+        const uint32_t cc = rep4(center);
+        {
+            constexpr int i = WPL - 1;  // last slot: always (its mask is all ones when nothing needs patching)
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
+            A[4 * i] |= cc & ~m.x; A[4 * i + 1] |= cc & ~m.y; A[4 * i + 2] |= cc & ~m.z; A[4 * i + 3] |= cc & ~m.w;
+        }
+        if (GENERIC && a.patch_slots) {
+#pragma unroll
+            for (int i = 0; i < WPL - 1; i++) {
+                const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
+                A[4 * i] |= cc & ~m.x; A[4 * i + 1] |= cc & ~m.y; A[4 * i + 2] |= cc & ~m.z; A[4 * i + 3] |= cc & ~m.w;
+            }
+        }
+        uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+        for (int q = 0; q < W4; q += 2) {
+            o0 |= absdiff4(A[q], cc);
+            o1 |= absdiff4(A[q + 1], cc);
+        }
+        uint32_t o = o0 | o1;
+        o |= o >> 16;
+        o |= o >> 8;
+        o = group_or<G>(o & 0xffu);  // >= max over frames of |x - centre| (OR dominates max)
+        const float aw = a.absolute ? w : w * iqi;
+        const float t = aw * ((float)o + halfw);
+        acc.bound += t * t;
+    }
+}
+
+// Certified pixels are written from registers; the others are appended to the warp's exact-path queue.
+template <int C>
+__device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAcc& acc, long long pix, int p_in_tile, bool owner, int lane,
+                                             QueueEntry* queue, int& qcount) {
+    const bool clean = acc.bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
+    if (owner && clean) {
+        uint8_t pixel[4] = {0, 0, 0, 0};
+        if (a.bg == 2) {
+#pragma unroll
+            for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf((float)acc.sum[c] / (float)a.n));  // src/chrono.rs:297-306,335-337
+        } else if (a.bg == 3) {
+#pragma unroll
+            for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(acc.median[c]));  // :340-345
+        } else if (a.bg == 0) {
+#pragma unroll
+            for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((acc.first_px >> (8 * c)) & 0xffu);  // :348-350
+        } else {
+            const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)a.n);  // :357
+            const int f = __ldg(a.win_frames + pos);
+            const PixelSrc src{a.stack + (pix >> 5) * tile_bytes(C, a.NG), a.NG, C, p_in_tile};
+#pragma unroll
+            for (int c = 0; c < C; c++) pixel[c] = src.at(f, c);
+        }
+        store_pixel<C>(a, pix, pixel, 0);
+        if (a.dbg_nout) a.dbg_nout[pix] = 0;
+    }
+    const bool dirty = owner && !clean;
+    const unsigned db = __ballot_sync(0xffffffffu, dirty);
+    if (db) {
+        const int nd = __popc(db);
+        if (qcount + nd > kQueueCap) {  // make room: drain full batches
+            __syncwarp();
+            while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
+            __syncwarp();
+        }
+        if (dirty) {
+            QueueEntry& e = queue[qcount + __popc(db & ((1u << lane) - 1u))];
+            e.pix = pix;
+#pragma unroll
+            for (int c = 0; c < 4; c++) { e.median[c] = acc.median[c]; e.iqr_inv[c] = acc.iqr_inv[c]; }
+        }
+        qcount += nd;
+        __syncwarp();
+        while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
+        __syncwarp();
+    }
+}
+
+// Hard pixels, 32/G at a time: each pixel group reloads its own bands (L2) and runs the iterative solver.
+template <int C, int WPL, int G, bool GENERIC>
+__device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* hq, int count, int lane, int cap, int pad, QueueEntry* queue, int& qcount) {
+    constexpr int W4 = 4 * WPL;
+    constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
+    const int j = lane % G, pl = lane / G;
+    const bool active = pl < count;
+    const long long pix = hq[active ? pl : 0];
+    const long long tile = pix >> 5;
+    const int p = (int)(pix & 31);
+    const long long band_stride = (long long)a.NG * (kTilePixels * kUnitBytes);
+    const uint8_t* base = a.stack + tile * tile_bytes(C, a.NG) + ((long long)(a.g0 + j) * kTilePixels + p) * kUnitBytes;
+    PixelAcc acc;
+    acc.reset();
+    uint32_t A[W4];
+#pragma unroll 1
+    for (int c = 0; c < C; c++) {
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (i * G + j < a.n_groups) v = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + i * kSlotStride));
+            A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
+        }
+        process_band<C, WPL, G, GENERIC, false>(a, A, c, j, pix, active && j == 0, cap, pad, acc);
+    }
+    finish_pixel<C>(a, acc, pix, p, active && j == 0, lane, queue, qcount);
+}
 
 template <int C, int WPL, int G, bool GENERIC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 : CHB_MINB) outlier_kernel(const __grid_constant__ OutlierArgs a) {
@@ -590,7 +828,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
     constexpr bool kStage = (G == 1);  // a tile's band is one contiguous slab: stage it with one TMA bulk copy per pixel-band
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    QueueEntry* const s_queue = reinterpret_cast<QueueEntry*>(smem_raw);
     const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     const int j = lane % G, pl = lane / G;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -600,10 +837,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
     const long long tbytes = tile_bytes(C, a.NG);
     const long long band_stride = (long long)a.NG * (kTilePixels * kUnitBytes);
     const long long lane_off = ((long long)(a.g0 + j) * kTilePixels) * kUnitBytes;
-    QueueEntry* queue = s_queue + warp_in_cta * kQueueCap;
-    int qcount = 0;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + kQueueBytes) + warp_in_cta;
-    uint8_t* const stage = smem_raw + kQueueBytes + kBarBytes + warp_in_cta * (WPL * 512);
+    QueueEntry* const queue = reinterpret_cast<QueueEntry*>(smem_raw) + warp_in_cta * kQueueCap;
+    long long* const hq = reinterpret_cast<long long*>(smem_raw + kQueueBytes) + warp_in_cta * kQueueCap;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + kQueueBytes + kHardBytes) + warp_in_cta;
+    uint8_t* const stage = smem_raw + kQueueBytes + kHardBytes + kBarBytes + warp_in_cta * (WPL * 512);
+    int qcount = 0, hcount = 0;
     const int staged_groups = a.n_groups < WPL ? a.n_groups : WPL;
     uint32_t parity = 0;
     if (kStage) {
@@ -619,34 +857,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
     };
 
     uint32_t A[W4];  // the current pixel-band
-    auto load_band = [&](long long task, int c, uint32_t (&d)[W4]) {
-        const long long tile = task / G;
-        const int p = (int)(task % G) * PPW + pl;
-        const uint8_t* cb = a.stack + tile * tbytes + lane_off + (long long)p * kUnitBytes + c * band_stride;
-#pragma unroll
-        for (int i = 0; i < WPL; i++) {
-            uint4 v;
-            if (!GENERIC && i < WPL - 1) {
-                v = ldg_stream(cb + i * kSlotStride);
-            } else {
-                v = make_uint4(0, 0, 0, 0);
-                if (i * G + j < a.n_groups) v = ldg_stream(cb + i * kSlotStride);
-            }
-            d[4 * i + 0] = v.x; d[4 * i + 1] = v.y; d[4 * i + 2] = v.z; d[4 * i + 3] = v.w;
-        }
-    };
-
     long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (kStage && task < n_tasks) stage_band(task, 0);
     while (task < n_tasks) {
         const long long tile = task / G;
         const int p = (int)(task % G) * PPW + pl;
         const long long pix = tile * kTilePixels + p;
-        const bool valid = pix < a.n_pixels;
-        float median[4] = {0, 0, 0, 0}, iqr_inv[4] = {0, 0, 0, 0}, q1v[4] = {0, 0, 0, 0}, q3v[4] = {0, 0, 0, 0};
-        uint32_t sum[4] = {0, 0, 0, 0};
-        uint32_t first_px = 0;  // bytes of window position 0, band c in byte c
-        float bound = 0.0f;
+        const bool owner = pix < a.n_pixels && j == 0;
+        PixelAcc acc;
+        acc.reset();
 #pragma unroll 1
         for (int c = 0; c < C; c++) {
             if (kStage) {
@@ -664,135 +883,39 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
                 const long long nt = last ? task + n_warps : task;
                 if (nt < n_tasks) stage_band(nt, last ? 0 : c + 1);
             } else {
-                load_band(task, c, A);
-            }
-            const float w = a.w[c];
-            if (GENERIC && a.window_masked) {  // frames outside the window must read as zero
+                const uint8_t* cb = a.stack + tile * tbytes + lane_off + (long long)p * kUnitBytes + c * band_stride;
 #pragma unroll
                 for (int i = 0; i < WPL; i++) {
-                    const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
-                    A[4 * i] &= m.x; A[4 * i + 1] &= m.y; A[4 * i + 2] &= m.z; A[4 * i + 3] &= m.w;
+                    uint4 v;
+                    if (!GENERIC && i < WPL - 1) {
+                        v = ldg_stream(cb + i * kSlotStride);
+                    } else {
+                        v = make_uint4(0, 0, 0, 0);
+                        if (i * G + j < a.n_groups) v = ldg_stream(cb + i * kSlotStride);
+                    }
+                    A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
                 }
             }
-            {   // window position 0 lives in slot 0 of lane j == 0; its byte index is uniform
-                const int wsel = (a.first_frame >> 2) & 3, sh = (a.first_frame & 3) * 8;
-                const uint32_t wv = wsel == 0 ? A[0] : (wsel == 1 ? A[1] : (wsel == 2 ? A[2] : A[3]));
-                first_px |= ((wv >> sh) & 0xffu) << (8 * c);
-            }
-            uint32_t bsum = 0;
-            if (a.bg == 2 || w != 0.0f) {  // window sum (IDP.4A: FMA pipe)
-                uint32_t s0 = 0, s1 = 0;
-#pragma unroll
-                for (int q = 0; q < W4; q += 2) { s0 = __dp4a(A[q], 0x01010101u, s0); s1 = __dp4a(A[q + 1], 0x01010101u, s1); }
-                bsum = group_sum<G>(s0 + s1);
-                set4(sum, c, bsum);
-            }
-            if (w != 0.0f) {
-                float med = 0.0f, q1 = 0.0f, q3 = 0.0f, iqi = 0.0f, halfw = 0.0f;
-                int center = 0;
-                if (GENERIC && a.smask) {  // --sample: order statistics on the subset only
-                    uint32_t xs[W4];
-                    uint32_t s = 0;
-#pragma unroll
-                    for (int i = 0; i < WPL; i++) {
-                        const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.smask) + (i * G + j));
-                        xs[4 * i] = A[4 * i] & m.x; xs[4 * i + 1] = A[4 * i + 1] & m.y;
-                        xs[4 * i + 2] = A[4 * i + 2] & m.z; xs[4 * i + 3] = A[4 * i + 3] & m.w;
-                    }
-#pragma unroll
-                    for (int q = 0; q < W4; q++) s = __dp4a(xs[q], 0x01010101u, s);
-                    band_stats<W4, G>(cap, xs, group_sum<G>(s), a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
-                } else {
-                    band_stats<W4, G>(cap, A, bsum, a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
-                }
-                set4(median, c, med); set4(iqr_inv, c, iqi); set4(q1v, c, q1); set4(q3v, c, q3);
-                if (!(w < 0.0f)) {  // negative weights only lower dist_sq; NaN poisons the bound (-> exact path)
-                    // certificate term: an upper bound of |x - median| over the window's frames. Bytes that are not
-                    // window frames (zero in the registers) are replaced by the centre value, so they contribute 0.
-                    const uint32_t cc = rep4(center);
-                    {
-                        constexpr int i = WPL - 1;  // last slot: always (mask is all ones when nothing needs patching)
-                        const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
-                        A[4 * i] |= cc & ~m.x; A[4 * i + 1] |= cc & ~m.y; A[4 * i + 2] |= cc & ~m.z; A[4 * i + 3] |= cc & ~m.w;
-                    }
-                    if (GENERIC && a.patch_slots) {
-#pragma unroll
-                        for (int i = 0; i < WPL - 1; i++) {
-                            const uint4 m = __ldg(reinterpret_cast<const uint4*>(a.wmask) + (i * G + j));
-                            A[4 * i] |= cc & ~m.x; A[4 * i + 1] |= cc & ~m.y; A[4 * i + 2] |= cc & ~m.z; A[4 * i + 3] |= cc & ~m.w;
-                        }
-                    }
-                    uint32_t o0 = 0, o1 = 0;
-#pragma unroll
-                    for (int q = 0; q < W4; q += 2) {
-                        o0 |= absdiff4(A[q], cc);
-                        o1 |= absdiff4(A[q + 1], cc);
-                    }
-                    uint32_t o = o0 | o1;
-                    o |= o >> 16;
-                    o |= o >> 8;
-                    o = group_or<G>(o & 0xffu);  // >= max over frames of |x - centre| (OR dominates max)
-                    const float aw = a.absolute ? w : w * iqi;
-                    const float t = aw * ((float)o + halfw);
-                    bound += t * t;
-                }
-            }
+            process_band<C, WPL, G, GENERIC, true>(a, A, c, j, pix, owner, cap, pad, acc);
         }
-        const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
-
-        // ---- output of certified pixels; the others are queued
-        const bool owner = valid && j == 0;
-        if (owner && clean) {
-            uint8_t pixel[4] = {0, 0, 0, 0};
-            if (a.bg == 2) {
-#pragma unroll
-                for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf((float)sum[c] / (float)a.n));  // src/chrono.rs:297-306,335-337
-            } else if (a.bg == 3) {
-#pragma unroll
-                for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(median[c]));  // :340-345
-            } else if (a.bg == 0) {
-#pragma unroll
-                for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((first_px >> (8 * c)) & 0xffu);  // :348-350
-            } else {
-                const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)a.n);  // :357
-                const int f = __ldg(a.win_frames + pos);
-                const PixelSrc src{a.stack + tile * tbytes, a.NG, C, p};
-#pragma unroll
-                for (int c = 0; c < C; c++) pixel[c] = src.at(f, c);
-            }
-            store_pixel<C>(a, pix, pixel, 0);
-            if (a.dbg_nout) a.dbg_nout[pix] = 0;
-        }
-        if (owner && a.dbg_median) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                a.dbg_median[pix * 4 + c] = median[c];
-                if (a.dbg_q1) a.dbg_q1[pix * 4 + c] = q1v[c];
-                if (a.dbg_q3) a.dbg_q3[pix * 4 + c] = q3v[c];
-            }
-        }
-        const bool dirty = owner && !clean;
-        const unsigned db = __ballot_sync(0xffffffffu, dirty);
-        if (db) {
-            const int nd = __popc(db);
-            if (qcount + nd > kQueueCap) {  // make room: drain full batches
-                __syncwarp();
-                while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
-                __syncwarp();
-            }
-            if (dirty) {
-                QueueEntry& e = queue[qcount + __popc(db & ((1u << lane) - 1u))];
-                e.pix = pix;
-#pragma unroll
-                for (int c = 0; c < 4; c++) { e.median[c] = median[c]; e.iqr_inv[c] = iqr_inv[c]; }
-            }
-            qcount += nd;
+        // ---- hard pixels wait in the warp's queue until a warp-full can run the iterative solver together
+        const bool hard = owner && acc.hard;
+        const unsigned hb = __ballot_sync(0xffffffffu, hard);
+        if (hb) {
+            if (hard) hq[hcount + __popc(hb & ((1u << lane) - 1u))] = pix;
+            hcount += __popc(hb);
             __syncwarp();
-            while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
+            while (hcount >= PPW) {
+                drain_hard<C, WPL, G, GENERIC>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount);
+                hcount -= PPW;
+            }
             __syncwarp();
         }
+        finish_pixel<C>(a, acc, pix, p, owner && !acc.hard, lane, queue, qcount);
         task += n_warps;
     }
+    __syncwarp();
+    if (hcount > 0) drain_hard<C, WPL, G, GENERIC>(a, hq, hcount, lane, cap, pad, queue, qcount);
     __syncwarp();
     if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
 }
