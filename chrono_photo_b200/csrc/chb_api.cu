@@ -18,7 +18,7 @@ using namespace chb;
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
-static thread_local uint64_t g_last_slow = 0;
+static thread_local uint64_t g_last_slow = 0, g_last_hard = 0;
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
@@ -41,6 +41,7 @@ extern "C" int chb_version(void) { return CHB_VERSION; }
 extern "C" uint64_t chb_launch_count(void) { return g_launches.load(); }
 extern "C" void chb_launch_count_reset(void) { g_launches.store(0); }
 extern "C" uint64_t chb_last_slow_pixels(void) { return g_last_slow; }
+extern "C" uint64_t chb_last_hard_pixels(void) { return g_last_hard; }
 
 // ------------------------------------------------------------------------------------------------ objects
 struct Dev {
@@ -210,7 +211,7 @@ extern "C" int chb_stack_create(chb_ctx* ctx, int width, int height, int channel
     CUB(cudaMallocHost(&st->h_win, sizeof(int32_t) * (size_t)std::max(n_frames, 1)));
     CUB(cudaMallocHost(&st->h_posg, sizeof(int32_t) * (size_t)st->NG));
     CUB(cudaMallocHost(&st->h_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
-    CUB(cudaMallocHost(&st->h_counters, sizeof(unsigned long long) * 2 * nd));
+    CUB(cudaMallocHost(&st->h_counters, sizeof(unsigned long long) * 4 * nd));
     st->bands.resize(nd);
     for (int k = 0; k < nd; k++) {
         Band& b = st->bands[k];
@@ -236,7 +237,7 @@ extern "C" int chb_stack_create(chb_ctx* ctx, int width, int height, int channel
         CUB(cudaMalloc(&b.d_win, sizeof(int32_t) * (size_t)n_frames));
         CUB(cudaMalloc(&b.d_posg, sizeof(int32_t) * (size_t)st->NG));
         CUB(cudaMalloc(&b.d_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
-        CUB(cudaMalloc(&b.d_counters, sizeof(unsigned long long) * 2));
+        CUB(cudaMalloc(&b.d_counters, sizeof(unsigned long long) * 4));
         CUB(cudaEventCreate(&b.ev0));
         CUB(cudaEventCreate(&b.ev1));
         CUB(cudaDeviceSynchronize());
@@ -561,7 +562,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         if (sub) CU(cudaMemcpyAsync(b.d_smask, st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(b.d_win, st->h_win, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
         if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 2, s));
+        CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
         OutlierArgs ab = a;
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
@@ -599,10 +600,10 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         g_launches++;
         CU(cudaGetLastError());
         CU(cudaEventRecord(b.ev1, s));
-        CU(cudaMemcpyAsync(st->h_counters + 2 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
     }
     float ms_max = 0.0f;
-    uint64_t warnings = 0, slow = 0;
+    uint64_t warnings = 0, slow = 0, hard = 0;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
@@ -610,8 +611,9 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
         ms_max = std::max(ms_max, ms);
-        warnings += st->h_counters[2 * b.dev_slot];
-        slow += st->h_counters[2 * b.dev_slot + 1];
+        warnings += st->h_counters[4 * b.dev_slot];
+        slow += st->h_counters[4 * b.dev_slot + 1];
+        hard += st->h_counters[4 * b.dev_slot + 2];
         if (dbg) {
             const size_t off = (size_t)b.row0 * st->W;
             if (dbg->median) CU(cudaMemcpy(dbg->median + off * 4, b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
@@ -625,6 +627,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     st->last_has_mask = want_mask;
     st->last_warnings = warnings;
     g_last_slow = slow;
+    g_last_hard = hard;
     return CHB_OK;
 }
 

@@ -96,7 +96,7 @@ struct OutlierArgs {
     unsigned long long seed, pixel_offset;
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
-    unsigned long long* counters;  // [0] warnings (all-outlier pixels), [1] pixels that left the certified fast path
+    unsigned long long* counters;  // [0] warnings (all-outlier pixels), [1] pixels on the exact path, [2] pixels on the iterative (hard) path
     float* dbg_median; float* dbg_q1; float* dbg_q3; int* dbg_nout;
 };
 
@@ -597,8 +597,12 @@ struct QueueEntry {
 constexpr int kQueueBytes = kWarpsPerCta * kQueueCap * (int)sizeof(QueueEntry);
 constexpr int kHardBytes = kWarpsPerCta * kQueueCap * (int)sizeof(long long);
 constexpr int kBarBytes = 128;
-// dynamic shared memory of one CTA: exact-path queues, hard-pixel queues, one mbarrier per warp, one staged pixel-band per warp (G == 1)
-__host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) { return kQueueBytes + kHardBytes + kBarBytes + (g == 1 ? kWarpsPerCta * wpl * 512 : 0); }
+constexpr int kAccBytes = kWarpsPerCta * 32 * 12 * 4;
+// dynamic shared memory of one CTA: exact-path queues, hard-pixel queues, one mbarrier per warp, per-thread result slots,
+// one staged pixel-band per warp (G == 1)
+__host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) {
+    return kQueueBytes + kHardBytes + kBarBytes + kAccBytes + (g == 1 ? kWarpsPerCta * wpl * 512 : 0);
+}
 
 template <int C>
 __device__ __forceinline__ void store_pixel(const OutlierArgs& a, long long pix, const uint8_t (&pixel)[4], uint8_t mask) {
@@ -639,17 +643,26 @@ __device__ __forceinline__ void set4(uint32_t (&v)[4], int c, uint32_t x) {
     for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
 }
 
-struct PixelAcc {  // what a pixel accumulates over its bands
-    float median[4], iqr_inv[4];
-    uint32_t sum[4];
+// What a pixel accumulates over its bands. The per-band results (median, 1/IQR, sum) are only needed when the pixel
+// is finished, so they live in per-thread shared-memory slots ([field][thread], conflict-free) instead of registers.
+constexpr int kAccWords = 12;
+struct PixelAcc {
+    uint32_t* slot;     // this thread's slots: slot[k * stride]
+    int stride;
     uint32_t first_px;  // bytes of window position 0, band c in byte c
     float bound;        // certificate: upper bound of dist_sq over the window's frames
     bool hard;          // a median pair fell outside the 5-value window
     __device__ __forceinline__ void reset() {
 #pragma unroll
-        for (int i = 0; i < 4; i++) { median[i] = 0.0f; iqr_inv[i] = 0.0f; sum[i] = 0; }
+        for (int i = 0; i < kAccWords; i++) slot[i * stride] = 0u;
         first_px = 0; bound = 0.0f; hard = false;
     }
+    __device__ __forceinline__ void set_median(int c, float v) { slot[c * stride] = __float_as_uint(v); }
+    __device__ __forceinline__ void set_iqr_inv(int c, float v) { slot[(4 + c) * stride] = __float_as_uint(v); }
+    __device__ __forceinline__ void set_sum(int c, uint32_t v) { slot[(8 + c) * stride] = v; }
+    __device__ __forceinline__ float median(int c) const { return __uint_as_float(slot[c * stride]); }
+    __device__ __forceinline__ float iqr_inv(int c) const { return __uint_as_float(slot[(4 + c) * stride]); }
+    __device__ __forceinline__ uint32_t sum(int c) const { return slot[(8 + c) * stride]; }
 };
 
 // One pixel-band held in A: window mask, sum, order statistics, certificate term. FAST: try the straight-line window first
@@ -677,7 +690,7 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
 #pragma unroll
         for (int q = 0; q < W4; q += 2) { s0 = __dp4a(A[q], 0x01010101u, s0); s1 = __dp4a(A[q + 1], 0x01010101u, s1); }
         bsum = group_sum<G>(s0 + s1);
-        set4(acc.sum, c, bsum);
+        acc.set_sum(c, bsum);
     }
     if (w == 0.0f) return;
     float med = 0.0f, q1 = 0.0f, q3 = 0.0f, iqi = 0.0f, halfw = 0.0f;
@@ -706,8 +719,8 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         solved = true;
     }
     if (!solved) band_stats<W4, G>(cap, A, bsum, a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
-    set4(acc.median, c, med);
-    set4(acc.iqr_inv, c, iqi);
+    acc.set_median(c, med);
+    acc.set_iqr_inv(c, iqi);
     if (a.dbg_median && write_dbg) {  // per-band sub-results (planes are zeroed by the host)
         a.dbg_median[pix * 4 + c] = med;
         if (a.dbg_q1) a.dbg_q1[pix * 4 + c] = q1;
@@ -754,10 +767,10 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
         uint8_t pixel[4] = {0, 0, 0, 0};
         if (a.bg == 2) {
 #pragma unroll
-            for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf((float)acc.sum[c] / (float)a.n));  // src/chrono.rs:297-306,335-337
+            for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf((float)acc.sum(c) / (float)a.n));  // src/chrono.rs:297-306,335-337
         } else if (a.bg == 3) {
 #pragma unroll
-            for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(acc.median[c]));  // :340-345
+            for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(acc.median(c)));  // :340-345
         } else if (a.bg == 0) {
 #pragma unroll
             for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((acc.first_px >> (8 * c)) & 0xffu);  // :348-350
@@ -784,7 +797,7 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
             QueueEntry& e = queue[qcount + __popc(db & ((1u << lane) - 1u))];
             e.pix = pix;
 #pragma unroll
-            for (int c = 0; c < 4; c++) { e.median[c] = acc.median[c]; e.iqr_inv[c] = acc.iqr_inv[c]; }
+            for (int c = 0; c < 4; c++) { e.median[c] = acc.median(c); e.iqr_inv[c] = acc.iqr_inv(c); }
         }
         qcount += nd;
         __syncwarp();
@@ -795,7 +808,8 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
 
 // Hard pixels, 32/G at a time: each pixel group reloads its own bands (L2) and runs the iterative solver.
 template <int C, int WPL, int G, bool GENERIC>
-__device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* hq, int count, int lane, int cap, int pad, QueueEntry* queue, int& qcount) {
+__device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* hq, int count, int lane, int cap, int pad, QueueEntry* queue, int& qcount,
+                                         uint32_t* acc_slot) {
     constexpr int W4 = 4 * WPL;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
     const int j = lane % G, pl = lane / G;
@@ -806,6 +820,7 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* h
     const long long band_stride = (long long)a.NG * (kTilePixels * kUnitBytes);
     const uint8_t* base = a.stack + tile * tile_bytes(C, a.NG) + ((long long)(a.g0 + j) * kTilePixels + p) * kUnitBytes;
     PixelAcc acc;
+    acc.slot = acc_slot; acc.stride = kWarpsPerCta * 32;
     acc.reset();
     uint32_t A[W4];
 #pragma unroll 1
@@ -840,7 +855,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
     QueueEntry* const queue = reinterpret_cast<QueueEntry*>(smem_raw) + warp_in_cta * kQueueCap;
     long long* const hq = reinterpret_cast<long long*>(smem_raw + kQueueBytes) + warp_in_cta * kQueueCap;
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + kQueueBytes + kHardBytes) + warp_in_cta;
-    uint8_t* const stage = smem_raw + kQueueBytes + kHardBytes + kBarBytes + warp_in_cta * (WPL * 512);
+    uint32_t* const acc_slot = reinterpret_cast<uint32_t*>(smem_raw + kQueueBytes + kHardBytes + kBarBytes) + threadIdx.x;
+    uint8_t* const stage = smem_raw + kQueueBytes + kHardBytes + kBarBytes + kAccBytes + warp_in_cta * (WPL * 512);
     int qcount = 0, hcount = 0;
     const int staged_groups = a.n_groups < WPL ? a.n_groups : WPL;
     uint32_t parity = 0;
@@ -865,6 +881,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
         const long long pix = tile * kTilePixels + p;
         const bool owner = pix < a.n_pixels && j == 0;
         PixelAcc acc;
+        acc.slot = acc_slot; acc.stride = kWarpsPerCta * 32;
         acc.reset();
 #pragma unroll 1
         for (int c = 0; c < C; c++) {
@@ -904,9 +921,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
         if (hb) {
             if (hard) hq[hcount + __popc(hb & ((1u << lane) - 1u))] = pix;
             hcount += __popc(hb);
+            if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(hb));
             __syncwarp();
             while (hcount >= PPW) {
-                drain_hard<C, WPL, G, GENERIC>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount);
+                drain_hard<C, WPL, G, GENERIC>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount, acc_slot);
                 hcount -= PPW;
             }
             __syncwarp();
@@ -915,7 +933,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 :
         task += n_warps;
     }
     __syncwarp();
-    if (hcount > 0) drain_hard<C, WPL, G, GENERIC>(a, hq, hcount, lane, cap, pad, queue, qcount);
+    if (hcount > 0) drain_hard<C, WPL, G, GENERIC>(a, hq, hcount, lane, cap, pad, queue, qcount, acc_slot);
     __syncwarp();
     if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
 }

@@ -160,6 +160,7 @@ int chb_fetch_last(chb_stack *stack, uint8_t *out_image, uint8_t *out_mask, uint
 uint64_t chb_launch_count(void);
 void chb_launch_count_reset(void);
 uint64_t chb_last_slow_pixels(void);
+uint64_t chb_last_hard_pixels(void); /* pixels whose medians needed the iterative solver */
 
 /* The --sample subset the library draws for (seed, window length n, cnt): cnt ascending positions in [0, n).
  * Deterministic replacement of rand::seq::sample_indices (src/chrono.rs:157), exported so a checker can use the same set. */

@@ -27,5 +27,6 @@ for kind in kinds:
         ms = [proc.process_device(fs) for _ in range(4)]
         best = min(ms[1:])
         slow = _lib.lib().chb_last_slow_pixels() if "outlier" in name else 0
-        print(f"  {name:28s} ms {['%.3f' % m for m in ms]}  {alg/best/1e6:8.0f} GB/s  {N*H*W/best/1e6:9.1f} Gpf/s  slow px {slow} ({100*slow/(H*W):.3f}%)")
+        hard = _lib.lib().chb_last_hard_pixels() if "outlier" in name else 0
+        print(f"  {name:28s} ms {['%.3f' % m for m in ms]}  {alg/best/1e6:8.0f} GB/s  {N*H*W/best/1e6:9.1f} Gpf/s  slow px {slow} ({100*slow/(H*W):.3f}%) hard {100*hard/(H*W):.2f}%")
 fs.close()
