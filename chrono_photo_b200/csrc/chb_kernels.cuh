@@ -1036,7 +1036,7 @@ __global__ void __launch_bounds__(256) simple_kernel(const __grid_constant__ Sim
 // `darker` (min of key); `lighter` stores 63 - index and takes the max. A pixel is streamed in chunks of 4 frame groups
 // (12-16 independent 128-bit loads in flight per thread); the four runs (frame mod 4) of a chunk are merged by
 // (sum, frame) and compared strictly with the best so far, so the first extreme wins exactly like the f32 compare of
-// src/simple.rs:103-118 (all values are exact integers). The winner's bytes are fetched while its chunk is still in L2.
+// src/simple.rs:103-118 (all values are exact integers). The winner's bytes are picked from the chunk's registers.
 constexpr int kChunkGroups = 4;
 template <int C>
 __global__ void __launch_bounds__(256) simple_int_kernel(const __grid_constant__ SimpleArgs a) {
@@ -1106,10 +1106,20 @@ __global__ void __launch_bounds__(256) simple_int_kernel(const __grid_constant__
             }
             if (c_frame >= 0 && (darker ? (c_sum < best_sum) : (c_sum > best_sum))) {  // strict: earlier chunks win ties
                 best_sum = c_sum;
-                const int f = (a.g0 + g_base) * kGroupFrames + c_frame;
-                const PixelSrc src{a.stack + tile * tbytes, a.NG, C, p};
+                // the winner's bytes are still in this chunk's registers: select unit, word, byte (no second trip to memory)
+                const int gsel = c_frame >> 4, wsel = (c_frame >> 2) & 3, sh = (c_frame & 3) * 8;
 #pragma unroll
-                for (int c = 0; c < C; c++) outp[c] = src.at(f, c);
+                for (int c = 0; c < C; c++) {
+                    uint4 uu = u[0][c];
+#pragma unroll
+                    for (int gg = 1; gg < kChunkGroups; gg++) {
+                        if (gsel == gg) uu = u[gg][c];
+                    }
+                    const uint32_t wv = wsel == 0 ? uu.x : (wsel == 1 ? uu.y : (wsel == 2 ? uu.z : uu.w));
+                    // bands with weight 0 are not loaded by this kernel: fetch those from memory (rare configuration)
+                    if ((a.use_mask >> c) & 1u) outp[c] = (uint8_t)((wv >> sh) & 0xffu);
+                    else outp[c] = PixelSrc{a.stack + tile * tbytes, a.NG, C, p}.at((a.g0 + g_base) * kGroupFrames + c_frame, c);
+                }
             }
         }
         if (pix < a.n_pixels) {
