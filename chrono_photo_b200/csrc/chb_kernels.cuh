@@ -538,8 +538,9 @@ __device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], ui
 // inside the window the pair is read off directly. Returns false when a rank lies outside (the pixel then takes the
 // iterative solver). The byte-range ends count as known: #{x <= -1} = 0, #{x <= 255} = cap.
 template <int W4, int G>
-__device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], uint32_t ssum, float inv_cnt, int kp1, int kp2, int cap, int& v1, int& v2) {
-    int p = __float2int_rn((float)ssum * inv_cnt) - 2;
+__device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center, int kp1, int kp2, int cap, int& v1, int& v2, bool want_f,
+                                            uint32_t& f_mid, int& p_mid) {
+    int p = center - 2;
     p = p < 0 ? 0 : (p > 251 ? 251 : p);
     const uint32_t c0 = rep4(p), c1 = c0 + 0x01010101u, c2 = c1 + 0x01010101u, c3 = c2 + 0x01010101u, c4 = c3 + 0x01010101u;
     uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
@@ -563,6 +564,9 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], uint32_t ss
         n0 = (int)((pa & 0xffffu) >> 1); n1 = (int)(pa >> 17);  // sum(d + bias) = 2 * count because G * bias = cap
         n2 = (int)((pb & 0xffffu) >> 1); n3 = (int)(pb >> 17);
     }
+    f_mid = 0;
+    p_mid = p + 2;
+    if (want_f) f_mid = group_sum<G>(f2);  // F(p + 2): spread estimate for the quartile guesses (relative thresholds)
     v1 = p + (n0 <= kp1) + (n1 <= kp1) + (n2 <= kp1) + (n3 <= kp1);
     v2 = p + (n0 <= kp2) + (n1 <= kp2) + (n2 <= kp2) + (n3 <= kp2);
     return ((n0 <= kp1) || p == 0) && ((kp2 < n3) || p == 251);
@@ -575,8 +579,8 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], uint32_t ss
 // is staged into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier) while the current one is processed, so HBM
 // latency overlaps the arithmetic; every byte of the stack is read from HBM exactly once.
 // Three tiers per pixel:
-//   fast    absolute thresholds, every band's median pair inside the 5-value window, certificate holds -> done from registers
-//   hard    a median outside the window (or relative thresholds): iterative solver (band_solve); such pixels are queued per
+//   fast    every band's median pair (and quartile pairs) inside their 5-value windows, certificate holds -> done from registers
+//   hard    an order statistic outside its window: iterative solver (band_solve); such pixels are queued per
 //           warp in shared memory and re-processed a warp-full at a time
 //   exact   certificate fails: exact_pixel walks the frames, 32 queued pixels at a time
 // GENERIC = false is the whole-stack launch whose leading slots are all real frame groups; GENERIC = true adds window
@@ -709,13 +713,28 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         for (int q = 0; q < W4; q++) s = __dp4a(xs[q], 0x01010101u, s);
         band_stats<W4, G>(cap, xs, group_sum<G>(s), a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
         solved = true;
-    } else if (FAST && a.absolute) {
-        int mlo, mhi;
-        const bool ok = band_window<W4, G>(A, bsum, a.inv_n_sub, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi);
-        acc.hard = acc.hard || !ok;
+    } else if (FAST) {
+        int mlo, mhi, pm;
+        uint32_t fm;
+        const bool rel = !a.absolute;
+        bool ok = band_window<W4, G>(A, __float2int_rn((float)bsum * a.inv_n_sub), a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, rel, fm, pm);
         med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
         center = (mlo + mhi) >> 1;
         halfw = med - (float)center;
+        if (rel) {  // quartile pairs in their own windows around median -/+ 0.95 * mean absolute deviation
+            const float mad = ((float)fm - (float)pad * (float)pm) * a.inv_n_sub;
+            const int dq = __float2int_rn(0.95f * mad);
+            int alo, ahi, blo, bhi, pd;
+            uint32_t fd;
+            ok = band_window<W4, G>(A, mlo - dq, a.rk[0] + pad, a.rk[1] + pad, cap, alo, ahi, false, fd, pd) && ok;
+            ok = band_window<W4, G>(A, mhi + dq, a.rk[4] + pad, a.rk[5] + pad, cap, blo, bhi, false, fd, pd) && ok;
+            q1 = (a.rk[0] == a.rk[1]) ? (float)alo : (1.0f - a.q1_frac) * (float)alo + a.q1_frac * (float)ahi;  // src/chrono.rs:568-579
+            q3 = (a.rk[4] == a.rk[5]) ? (float)blo : (1.0f - a.q3_frac) * (float)blo + a.q3_frac * (float)bhi;
+            float iq = q3 - q1;
+            if (iq == 0.0f) iq = 1.0f;
+            iqi = 1.0f / iq;  // :246-252
+        }
+        acc.hard = acc.hard || !ok;
         solved = true;
     }
     if (!solved) band_stats<W4, G>(cap, A, bsum, a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
@@ -837,7 +856,7 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* h
 }
 
 template <int C, int WPL, int G, bool GENERIC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (WPL <= 8) ? CHB_MINB + 1 : CHB_MINB) outlier_kernel(const __grid_constant__ OutlierArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(const __grid_constant__ OutlierArgs a) {
     constexpr int W4 = 4 * WPL;
     constexpr int PPW = 32 / G;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
