@@ -522,6 +522,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     rc = fade_to_dev(prm->fade, a.fade, "chb_outlier");
     if (rc) return rc;
     a.frame_offset = indices ? indices[0] : 0;  // src/chrono.rs:102-103
+    a.contig_f0 = (win.frames.back() - win.frames.front() + 1 == n) ? win.frames.front() : -1;
     a.seed = prm->seed;
 
     // host tables

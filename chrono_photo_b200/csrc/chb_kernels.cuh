@@ -93,6 +93,7 @@ struct OutlierArgs {
     int bg, om;
     FadeDev fade;
     int frame_offset;
+    int contig_f0;           // >= 0: the window is the contiguous frame range starting here (position s = frame contig_f0 + s)
     unsigned long long seed, pixel_offset;
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
@@ -293,7 +294,69 @@ struct ColumnReader {
             }
         }
     }
+    // the 4-frame word (frames frame .. frame+3, frame a multiple of 4) of every band
+    __device__ __forceinline__ void fetch_word(int frame, uint32_t (&xw)[4]) {
+        const int g = frame >> 4;
+        if (g != cur_g) {
+            cur_g = g;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c < C) u[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
+        }
+        const int wsel = (frame >> 2) & 3;
+#pragma unroll
+        for (int c = 0; c < 4; c++) xw[c] = (c < C) ? (wsel == 0 ? u[c].x : (wsel == 1 ? u[c].y : (wsel == 2 ? u[c].z : u[c].w))) : 0u;
+    }
 };
+
+// Conservative per-word pre-test of the exact path: a frame can only be an outlier if some band deviates from the
+// band's centre by more than cap_c, where the caps split thr_min^2 evenly over the positive-weight bands
+// ((fac_c * (cap_c + halfwidth_c))^2 <= thr^2 / bands, with margin). One VABSDIFF4 + three logic ops per band test four
+// frames at once; words without a flagged frame are skipped. Flags: bit 7 of byte k <=> frame k may be an outlier.
+struct WordScan {
+    uint32_t cc[4], kadd[4];
+    bool use[4];
+    bool all;  // caps are useless (tiny threshold, NaN): every frame is evaluated
+};
+__device__ __forceinline__ void make_word_scan(const OutlierArgs& a, const float (&median)[4], const float (&iqr_inv)[4], WordScan& ws) {
+    int nb = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float w = a.w[i];
+        ws.use[i] = (i < a.C) && (w != 0.0f) && !(w < 0.0f);  // negative weights only lower dist_sq
+        nb += ws.use[i] ? 1 : 0;
+    }
+    ws.all = false;
+    const float share = nb > 0 ? sqrtf(a.thr_sq * 0.9999f / (float)nb) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ws.cc[i] = 0; ws.kadd[i] = 0;
+        if (ws.use[i]) {
+            const float fac = fabsf(a.absolute ? a.w[i] : a.w[i] * iqr_inv[i]);
+            const int center = (int)median[i];  // floor: medians are >= 0
+            const float halfw = median[i] - (float)center;
+            const float capf = share / fac - halfw - 1e-3f;
+            int cap = (capf == capf && capf > -1.0f) ? (int)floorf(capf) : -1;  // NaN / negative -> no cap
+            if (cap < 0) ws.all = true;
+            cap = cap < 0 ? 0 : (cap > 127 ? 127 : cap);
+            ws.cc[i] = rep4(center);
+            ws.kadd[i] = rep4(127 - cap);  // (d & 0x7f) + (127 - cap) sets bit 7 iff (d & 0x7f) > cap
+        }
+    }
+    if (!(a.thr_sq > 0.0f)) ws.all = true;  // threshold 0 (or NaN): everything is an outlier
+}
+__device__ __forceinline__ uint32_t may_exceed(const WordScan& ws, const uint32_t (&xw)[4]) {
+    if (ws.all) return 0x80808080u;
+    uint32_t ex = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (ws.use[i]) {
+            const uint32_t d = absdiff4(xw[i], ws.cc[i]);
+            ex |= d | ((d & 0x7f7f7f7fu) + ws.kadd[i]);  // bit 7: d >= 128, or low 7 bits above the cap
+        }
+    }
+    return ex & 0x80808080u;
+}
 
 struct DistCtx {  // per-band constants of the distance (src/chrono.rs:265-278)
     float med[4], fac[4], sgn[4];
@@ -363,26 +426,22 @@ __device__ __forceinline__ void blend_into_f32_u8(float (&pa)[4], const uint8_t 
 // Returns the mask byte; writes the composite pixel; n_out = number of outliers; warn = all-outlier warning.
 // `active` lanes hold a pixel; inactive lanes run along (uniform loops) and their results are discarded.
 __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const PixelSrc& src, unsigned long long pixel_id,
-                                               const float (&median)[4], const float (&iqr_inv)[4], uint8_t (&pixel)[4],
-                                               int& n_out, int& warn) {
+                                               const float (&median)[4], const float (&iqr_inv)[4], const uint32_t (&band_sum)[4],
+                                               uint8_t (&pixel)[4], int& n_out, int& warn) {
     const int n = a.n, C = a.C;
     const float thr_sq = a.thr_sq;
     DistCtx dc;
     make_dist_ctx(a, median, iqr_inv, dc);
+    WordScan ws;
+    make_word_scan(a, median, iqr_inv, ws);
     ColumnReader rd(src);
     // pass 1 (src/chrono.rs:261-288 plus the sums the policies need)
     int k = 0, first_idx = 0, last_idx = 0, max_index = 0, first_non = -1;
     float first_d = 0.0f, last_d = 0.0f, max_dist_sq = 0.0f, mean_dist = 0.0f;
-    float out_sum[4] = {0, 0, 0, 0}, all_sum[4] = {0, 0, 0, 0};
+    float out_sum[4] = {0, 0, 0, 0};
     uint8_t px[4] = {0, 0, 0, 0};
-    const bool need_all = a.bg == 2, need_avg = a.om == 3 || a.bg == 2;
-    for (int s = 0; s < n; s++) {
-        rd.fetch(__ldg(a.win_frames + s), px);
-        const float d = dist_sq_px(dc, px);
-        if (need_all) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) all_sum[i] += (float)px[i];
-        }
+    const bool need_avg = a.om == 3 || a.bg == 2;
+    auto visit = [&](int s, float d) {  // one frame of the window, in order
         if (d >= thr_sq) {
             if (k == 0) { first_idx = s; first_d = d; }
             last_idx = s; last_d = d;
@@ -396,6 +455,41 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         } else if (first_non < 0) {
             first_non = s;
         }
+    };
+    if (a.contig_f0 >= 0) {  // contiguous window: position s is frame contig_f0 + s; aligned words are pre-tested four frames at a time
+        int s = 0;
+        while (s < n) {
+            const int f = a.contig_f0 + s;
+            if ((f & 3) == 0 && s + 4 <= n) {
+                uint32_t xw[4];
+                rd.fetch_word(f, xw);
+                const uint32_t ex = may_exceed(ws, xw);
+                if (ex == 0) {
+                    if (first_non < 0) first_non = s;
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        if ((ex >> (8 * kk + 7)) & 1u) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) px[i] = (uint8_t)((xw[i] >> (8 * kk)) & 0xffu);
+                            visit(s + kk, dist_sq_px(dc, px));
+                        } else if (first_non < 0) {
+                            first_non = s + kk;
+                        }
+                    }
+                }
+                s += 4;
+            } else {
+                rd.fetch(f, px);
+                visit(s, dist_sq_px(dc, px));
+                s++;
+            }
+        }
+    } else {
+        for (int s = 0; s < n; s++) {
+            rd.fetch(__ldg(a.win_frames + s), px);
+            visit(s, dist_sq_px(dc, px));
+        }
     }
     n_out = k;
     warn = 0;
@@ -405,7 +499,7 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
     if (a.bg == 2) {  // Average
         float mean[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) mean[i] = all_sum[i] / (float)n;
+        for (int i = 0; i < 4; i++) mean[i] = (float)band_sum[i] / (float)n;  // the reference's f32 running sum is exact (< 2^24)
         if (has_outliers) {
             const float ratio = (float)n / (float)(n - k);  // k == 1: samples/(samples-1); k > 1: samples/num_non_outliers
 #pragma unroll
@@ -471,10 +565,20 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         float pix_new[4], blend_inv = 1.0f;
 #pragma unroll
         for (int i = 0; i < 4; i++) pix_new[i] = (float)pixel[i];
-        // only the span [first_idx, last_idx] holds outliers
+        // only the span [first_idx, last_idx] holds outliers; in a contiguous window whole words without a candidate are skipped
         for (int ss = first_idx; ss <= last_idx; ss++) {
             const int s = (a.om == 4) ? ss : last_idx - (ss - first_idx);
-            rd.fetch(__ldg(a.win_frames + s), sample);
+            const int f = a.contig_f0 >= 0 ? a.contig_f0 + s : __ldg(a.win_frames + s);
+            if (a.contig_f0 >= 0) {
+                const int wf = f & ~3;  // word of this frame; when entering a word from its far end, test it once
+                const bool entering = (a.om == 4) ? ((f & 3) == 0) : ((f & 3) == 3);
+                if (entering && wf - a.contig_f0 >= first_idx && wf + 3 - a.contig_f0 <= last_idx) {
+                    uint32_t xw[4];
+                    rd.fetch_word(wf, xw);
+                    if (may_exceed(ws, xw) == 0) { ss += 3; continue; }
+                }
+            }
+            rd.fetch(f, sample);
             const float d = dist_sq_px(dc, sample);
             if (d >= thr_sq) {
                 const float fade = fade_for(a.fade, s, n, a.frame_offset);
@@ -597,6 +701,7 @@ struct QueueEntry {
     long long pix;
     float median[4];
     float iqr_inv[4];
+    uint32_t sum[4];
 };
 constexpr int kQueueBytes = kWarpsPerCta * kQueueCap * (int)sizeof(QueueEntry);
 constexpr int kHardBytes = kWarpsPerCta * kQueueCap * (int)sizeof(long long);
@@ -626,7 +731,7 @@ __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry*
     const PixelSrc src{a.stack + tile * tile_bytes(C, a.NG), a.NG, C, (int)(e.pix & 31)};
     uint8_t pixel[4] = {0, 0, 0, 0};
     int n_out = 0, warn = 0;
-    const uint8_t mask = exact_pixel(a, src, a.pixel_offset + (unsigned long long)e.pix, e.median, e.iqr_inv, pixel, n_out, warn);
+    const uint8_t mask = exact_pixel(a, src, a.pixel_offset + (unsigned long long)e.pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn);
     if (active) {
         store_pixel<C>(a, e.pix, pixel, mask);
         if (a.dbg_nout) a.dbg_nout[e.pix] = n_out;
@@ -816,7 +921,7 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
             QueueEntry& e = queue[qcount + __popc(db & ((1u << lane) - 1u))];
             e.pix = pix;
 #pragma unroll
-            for (int c = 0; c < 4; c++) { e.median[c] = acc.median(c); e.iqr_inv[c] = acc.iqr_inv(c); }
+            for (int c = 0; c < 4; c++) { e.median[c] = acc.median(c); e.iqr_inv[c] = acc.iqr_inv(c); e.sum[c] = acc.sum(c); }
         }
         qcount += nd;
         __syncwarp();
