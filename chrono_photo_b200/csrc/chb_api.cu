@@ -95,6 +95,7 @@ struct chb_stack {
     unsigned long long* h_counters = nullptr;  // [n_bands * 2]
     bool last_has_mask = false;
     uint64_t last_warnings = 0;
+    std::vector<uint8_t> last_tables;  // fingerprint of the per-call tables currently on the devices
 };
 
 static constexpr int kMaxWindowFrames = 4096;  // largest window span the register-resident kernels hold
@@ -423,7 +424,7 @@ extern "C" int chb_sample_positions(uint64_t seed, int n, int cnt, int32_t* out)
 typedef void (*OutlierKernel)(const OutlierArgs);
 struct Variant { int wpl, g; };
 // capacity (frames) = 16 * wpl * g
-static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {8, 1}, {13, 1}, {7, 2}, {8, 2}, {8, 4}, {8, 8}, {8, 16}, {8, 32}};
+static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {8, 1}, {13, 1}, {7, 2}, {8, 2}, {8, 4}, {16, 4}, {8, 8}, {8, 16}, {8, 32}};
 static constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 template <int C, bool GENERIC>
@@ -437,8 +438,9 @@ static OutlierKernel kernel_for(int v) {
         case 5: return outlier_kernel<C, 7, 2, GENERIC>;
         case 6: return outlier_kernel<C, 8, 2, GENERIC>;
         case 7: return outlier_kernel<C, 8, 4, GENERIC>;
-        case 8: return outlier_kernel<C, 8, 8, GENERIC>;
-        case 9: return outlier_kernel<C, 8, 16, GENERIC>;
+        case 8: return outlier_kernel<C, 16, 4, GENERIC>;
+        case 9: return outlier_kernel<C, 8, 8, GENERIC>;
+        case 10: return outlier_kernel<C, 8, 16, GENERIC>;
         default: return outlier_kernel<C, 8, 32, GENERIC>;
     }
 }
@@ -554,15 +556,30 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     if (st->C == 3) kern = generic ? kernel_for<3, true>(vidx) : kernel_for<3, false>(vidx);
     else kern = generic ? kernel_for<4, true>(vidx) : kernel_for<4, false>(vidx);
 
+    // fingerprint of the device-side tables of this call
+    std::vector<uint8_t> blob;
+    {
+        auto put = [&](const void* p, size_t nbytes) { const uint8_t* q = (const uint8_t*)p; blob.insert(blob.end(), q, q + nbytes); };
+        const int hdr[4] = {1 /* outlier */, cap_groups, n, sub ? 1 : 0};
+        put(hdr, sizeof hdr);
+        put(st->h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4);
+        if (sub) put(st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4);
+        put(st->h_win, sizeof(int32_t) * (size_t)n);
+        if (!prm->fade.is_none) put(st->h_fade, sizeof(float) * (size_t)prm->fade.n_values);
+    }
+    const bool tables_cached = (blob == st->last_tables);
+    if (!tables_cached) st->last_tables = blob;
     const size_t P = (size_t)st->W * st->H;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
         cudaStream_t s = d.compute;
-        CU(cudaMemcpyAsync(b.d_wmask, st->h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
-        if (sub) CU(cudaMemcpyAsync(b.d_smask, st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b.d_win, st->h_win, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
-        if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+        if (!tables_cached) {  // window / sample / fade tables: uploaded only when they differ from the previous call's
+            CU(cudaMemcpyAsync(b.d_wmask, st->h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
+            if (sub) CU(cudaMemcpyAsync(b.d_smask, st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(b.d_win, st->h_win, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+            if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+        }
         CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
         OutlierArgs ab = a;
         ab.stack = b.d_stack;
@@ -702,6 +719,7 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
         if (prm->weights[i] == 1.0f) a.use_mask |= 1u << i;
         else if (prm->weights[i] != 0.0f) int_path = false;
     }
+    st->last_tables.clear();  // this call overwrites the shared table buffers
     std::vector<uint32_t> masks((size_t)win.n_groups * 4);
     byte_masks(win.frames, win.g0, win.n_groups, masks.data());
     bool all_in = true;
