@@ -322,6 +322,36 @@ def test_full_size_properties_200_frames(ctx):
     fs.close()
 
 
+def test_config5_chrono_video_with_shake_crop(ctx):
+    # BASELINE config 5 in miniature: per-frame shake offsets realigned through Crop::create (src/shake.rs:136-176), the
+    # stack uploaded once with the crop origins, then one compositing call per output frame with the window of
+    # create_video (src/main.rs:230-286); --video-in 0/7/1 and a stepped variant
+    rng = np.random.default_rng(83)
+    n, H, W = 36, 30, 44
+    offs = rng.integers(-3, 4, size=(n, 2))
+    offs[0] = 0
+    xy, w, h = cp.crop_create(offs, W, H)
+    scene = make_stack(rng, n, H + 8, W + 8, 3, n_obj=40)  # a stable scene seen through a shaking camera
+    frames = np.stack([scene[i, 4 + offs[i][1]:4 + offs[i][1] + H, 4 + offs[i][0]:4 + offs[i][0] + W] for i in range(n)])
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    for i in range(n):
+        fs.upload(i, np.ascontiguousarray(frames[i]), tuple(xy[i]))
+    fs.sync()
+    st = np.stack([frames[i, xy[i][1]:xy[i][1] + h, xy[i][0]:xy[i][0] + w] for i in range(n)])
+    t_gpu, t_orc = thr_pair((True, 0.05, 0.2))
+    fade = (0, True, [(0, 1.0), (20, 0.2)])
+    for vin in (cp.FrameRange(0, 7, 1), cp.FrameRange(-9, 1, 3)):
+        wins = cp.video_windows(n, vin, cp.FrameRange.empty())
+        assert len(wins) > 20
+        for number, idx in wins[::3]:
+            proc = cp.OutlierProcessor(t_gpu, BG["first"], OM["extreme"], fade=cp.Fade(*fade))
+            img, msk = proc.process(fs, idx)
+            oimg, omsk, _ = orc.outlier(st, t_orc, BG["first"], OM["extreme"], fade_=orc.fade(*fade), indices=idx)
+            assert np.array_equal(img, oimg) and np.array_equal(msk, omsk), (number, idx)
+            assert np.array_equal(cp.SimpleProcessor(darker=False).process(fs, idx), orc.simple(st, False, indices=idx))
+    fs.close()
+
+
 def test_multi_gpu_row_shards_match_single_gpu(ctx):
     import torch
     if torch.cuda.device_count() < 2:

@@ -1,0 +1,217 @@
+// chrono_b200_cli -- CLI-compatible driver for the compositing path (mirrors src/cli.rs:19-243 and src/main.rs:21-429
+// for the hot-path flags). Frames are binary PPM (P6, maxval 255): this image has no JPEG/PNG codec library, the
+// reference's decode/encode (`image` crate) stays outside the path. Flags that only steer the reference's temp files
+// (--slice, --compression, --temp-dir) or its thread pools / JPEG quality are accepted and ignored.
+#include <glob.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+
+#include "../include/chrono_b200.hpp"
+
+using namespace chrono_b200;
+
+struct Image {
+    int w = 0, h = 0;
+    std::vector<uint8_t> px;
+};
+
+static Image read_ppm(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("Unable to open image " + path);
+    std::string magic;
+    f >> magic;
+    if (magic != "P6") throw std::runtime_error("Unexpected format. Not a binary PPM (P6): " + path);
+    auto next_int = [&]() {
+        int v;
+        while (true) {
+            f >> std::ws;
+            if (f.peek() == '#') { std::string line; std::getline(f, line); continue; }
+            f >> v;
+            return v;
+        }
+    };
+    Image im;
+    im.w = next_int(); im.h = next_int();
+    int maxv = next_int();
+    if (maxv != 255) throw std::runtime_error("Unexpected format. Not an 8 bit image.");
+    f.get();
+    im.px.resize((size_t)im.w * im.h * 3);
+    f.read(reinterpret_cast<char*>(im.px.data()), (std::streamsize)im.px.size());
+    if (!f) throw std::runtime_error("Truncated PPM: " + path);
+    return im;
+}
+static void write_ppm(const std::string& path, int w, int h, const std::vector<uint8_t>& px) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("Unable to create output file " + path);
+    f << "P6\n" << w << " " << h << "\n255\n";
+    f.write(reinterpret_cast<const char*>(px.data()), (std::streamsize)px.size());
+}
+
+// Cli::from_str quote handling (src/cli.rs:245-266)
+static std::vector<std::string> split_option_string(const std::string& str) {
+    std::vector<std::string> args;
+    auto parts = split(str, '"');
+    for (size_t i = 0; i < parts.size(); i++) {
+        if (i % 2 == 0) {
+            std::istringstream is(parts[i]);
+            std::string tok;
+            while (is >> tok) args.push_back(tok);
+        } else {
+            std::string t = parts[i];
+            t.erase(0, t.find_first_not_of(" \t"));
+            t.erase(t.find_last_not_of(" \t") + 1);
+            args.push_back(t);
+        }
+    }
+    return args;
+}
+
+static std::pair<std::string, std::string> name_and_extension(const std::string& path) {  // src/main.rs:431-451
+    size_t slash = path.find_last_of('/');
+    std::string file = slash == std::string::npos ? path : path.substr(slash + 1);
+    size_t dot = file.find_last_of('.');
+    if (dot == std::string::npos || dot == 0) throw std::runtime_error("Unexpected format in " + path);
+    return {file.substr(0, dot), file.substr(dot + 1)};
+}
+static std::string parent_of(const std::string& path) {
+    size_t slash = path.find_last_of('/');
+    return slash == std::string::npos ? std::string(".") : path.substr(0, slash);
+}
+
+int main(int argc, char** argv) {
+    try {
+        std::vector<std::string> args(argv + 1, argv + argc);
+        if (args.size() == 1 && args[0][0] != '-') {  // option file (src/main.rs:33-43)
+            std::ifstream f(args[0]);
+            if (!f) throw std::runtime_error("Something went wrong reading the options file " + args[0]);
+            std::stringstream ss;
+            ss << f.rdbuf();
+            std::string content = ss.str();
+            std::replace(content.begin(), content.end(), '\r', ' ');
+            std::replace(content.begin(), content.end(), '\n', ' ');
+            args = split_option_string(content);
+        }
+        std::map<std::string, std::string> opt;
+        std::vector<float> weights;
+        const std::map<std::string, std::string> shorts = {{"-p", "--pattern"}, {"-f", "--frames"}, {"-o", "--output"}, {"-m", "--mode"}, {"-t", "--threshold"},
+                                                           {"-b", "--background"}, {"-l", "--outlier"}, {"-c", "--compression"}, {"-q", "--quality"}, {"-s", "--slice"}};
+        for (size_t i = 0; i < args.size(); i++) {
+            std::string a = args[i];
+            if (shorts.count(a)) a = shorts.at(a);
+            if (a == "--debug" || a == "-d" || a == "--wait" || a == "-w") continue;
+            if (a == "--weights") {
+                for (int k = 0; k < 4; k++) {
+                    if (++i >= args.size()) throw ParseOptionError("--weights requires 4 values");
+                    weights.push_back(parse_f32(args[i], "Can't parse weight " + args[i]));
+                }
+                continue;
+            }
+            if (a.rfind("--", 0) != 0) throw ParseOptionError("Found argument '" + a + "' which wasn't expected");
+            if (i + 1 >= args.size()) throw ParseOptionError("The argument '" + a + "' requires a value");
+            opt[a] = args[++i];
+        }
+        if (!opt.count("--pattern") || !opt.count("--output")) throw ParseOptionError("The following required arguments were not provided: --pattern --output");
+        // defaults: src/cli.rs:192-216
+        SelectionMode mode = opt.count("--mode") ? parse_selection_mode(opt["--mode"]) : SelectionMode::Outlier;
+        Threshold threshold = opt.count("--threshold") ? Threshold::from_str(opt["--threshold"]) : Threshold::abs(0.05f, 0.2f);
+        BackgroundMode background = opt.count("--background") ? parse_background_mode(opt["--background"]) : BackgroundMode::Random;
+        OutlierSelectionMode outlier = opt.count("--outlier") ? parse_outlier_mode(opt["--outlier"]) : OutlierSelectionMode::Extreme;
+        Fade fade = opt.count("--fade") ? Fade::from_str(opt["--fade"]) : Fade::none();
+        float w[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        for (size_t i = 0; i < weights.size() && i < 4; i++) w[i] = weights[i];
+        std::optional<size_t> sample;
+        if (opt.count("--sample")) sample = (size_t)parse_i32(opt["--sample"], "Can't parse --sample");
+        std::optional<FrameRange> frames, video_in, video_out;
+        if (opt.count("--frames")) frames = FrameRange::from_str(opt["--frames"]);
+        if (opt.count("--video-in")) video_in = FrameRange::from_str(opt["--video-in"]);
+        if (opt.count("--video-out")) video_out = FrameRange::from_str(opt["--video-out"]);
+        if (opt.count("--shake") != opt.count("--shake-anchors")) throw ParseOptionError("Provide both options or none: `--shake` and `--shake-anchors`");
+        if (opt.count("--shake")) throw ParseOptionError("--shake: camera-shake analysis is outside this driver (SURVEY.md 8f); pass pre-cropped frames");
+        if (mode != SelectionMode::Outlier) {  // src/cli.rs:141-167, :233-239
+            std::vector<std::string> unused;
+            for (const char* k : {"--output-blend", "--threshold", "--outlier", "--background", "--temp-dir", "--sample", "--slice", "--compression"})
+                if (opt.count(k)) unused.push_back(k);
+            if (!unused.empty()) {
+                std::cout << "WARNING! The following options are not used, as they are required only for `--mode outlier`:\n";
+                for (auto& u : unused) std::cout << u << "\n";
+                std::cout << "\n";
+            }
+        }
+        // FileLister::files_vec (src/flist.rs:121-143): glob, then take(end).skip(start), then every step-th
+        glob_t g;
+        std::vector<std::string> files;
+        if (glob(opt["--pattern"].c_str(), 0, nullptr, &g) == 0) {
+            for (size_t i = 0; i < g.gl_pathc; i++) files.push_back(g.gl_pathv[i]);
+        }
+        globfree(&g);
+        std::sort(files.begin(), files.end());
+        if (frames) {
+            size_t end = frames->end ? (size_t)std::max(0, *frames->end) : files.size();
+            size_t start = frames->start ? (size_t)std::max(0, *frames->start) : 0;
+            std::vector<std::string> sel;
+            for (size_t i = start, k = 0; i < std::min(end, files.size()); i++, k++)
+                if (k % frames->step == 0) sel.push_back(files[i]);
+            files.swap(sel);
+        }
+        if (files.empty()) throw std::runtime_error("Unable to process search pattern " + opt["--pattern"]);
+
+        // ---- upload (replaces to_time_slices, src/main.rs:574-602)
+        Context ctx;
+        Image first = read_ppm(files[0]);
+        GpuStack stack(ctx, first.w, first.h, 3, (int)files.size());
+        for (size_t i = 0; i < files.size(); i++) {
+            Image im = i == 0 ? first : read_ppm(files[i]);
+            if (im.w != first.w || im.h != first.h) throw std::runtime_error("Image layout does not fit!");  // src/simple.rs:62-66
+            stack.upload((int)i, im.px.data(), (size_t)im.w * 3);
+        }
+        stack.sync();
+
+        auto run_frame = [&](const std::vector<int32_t>* indices, const std::string& out, const std::optional<std::string>& out_blend) {
+            if (mode == SelectionMode::Outlier) {
+                OutlierProcessor proc(threshold, background, outlier, w, fade, sample, /*seed=*/0x9E3779B97F4A7C15ULL);
+                auto res = proc.process(stack, indices);
+                if (proc.warnings() > 0) std::cout << "Warning: " << proc.warnings() << " pixels seem to consist of only outliers\n";
+                write_ppm(out, first.w, first.h, res.first);
+                if (out_blend) write_ppm(*out_blend, first.w, first.h, res.second);
+            } else {
+                SimpleProcessor proc(w, fade, mode == SelectionMode::Darker);
+                write_ppm(out, first.w, first.h, proc.process(stack, indices));
+            }
+        };
+        std::optional<std::string> out_blend;
+        if (opt.count("--output-blend")) out_blend = opt["--output-blend"];
+
+        if (video_in || video_out) {  // create_video / create_video_simple (src/main.rs:214-429)
+            FrameRange vin = video_in.value_or(FrameRange::empty()), vout = video_out.value_or(FrameRange::empty());
+            const int cap = 4 * (int)files.size() + 16;
+            std::vector<int32_t> ws(cap), we(cap), num(cap);
+            int n = chb_video_windows((int)files.size(), vin.start.has_value(), vin.start.value_or(0), vin.end.has_value(), vin.end.value_or(0), (int)vin.step,
+                                      vout.start.has_value(), vout.start.value_or(0), vout.end.has_value(), vout.end.value_or(0), (int)vout.step, ws.data(),
+                                      we.data(), num.data(), cap);
+            auto ne = name_and_extension(opt["--output"]);
+            std::string dir = parent_of(opt["--output"]);
+            for (int i = 0; i < std::min(n, cap); i++) {
+                std::vector<int32_t> idx;
+                for (int f = ws[i]; f < we[i]; f += (int)vin.step) idx.push_back(f);
+                char nm[64];
+                snprintf(nm, sizeof nm, "-%05d.", num[i]);
+                if (idx.empty()) { std::cout << "Skipping frame " << num[i] << "\n"; continue; }
+                std::optional<std::string> ob;
+                if (out_blend) { auto nb = name_and_extension(*out_blend); ob = dir + "/" + nb.first + nm + nb.second; }
+                std::cout << "Processing frame " << num[i] << " -> \n";
+                run_frame(&idx, dir + "/" + ne.first + nm + ne.second, ob);
+            }
+        } else {
+            run_frame(nullptr, opt["--output"], out_blend);
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "error: " << e.what() << "\n";
+        return 1;
+    }
+}
