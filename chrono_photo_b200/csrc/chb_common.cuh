@@ -80,7 +80,7 @@ enum SynthKind { kSynthS1 = 1, kSynthS2 = 2, kSynthUniform = 3, kSynthGauss = 4 
 // kind 1 (S1): recipe of src/util/create_example_data.rs:10-49 without the JPEG round trip: bands 0,1 uniform in
 //   [240,250), band 2 uniform in [140,150); a 17x17 square centred (100+10f, H/3+5f) and a fixed one centred
 //   (W-24, H-68) with band 0 set to 0 (the reference writes only the first byte of the pixel, :36-38, :44-48).
-// kind 2 (S2): smooth gradient + uniform noise in [-5,5] + 8 discs of radius 40 on linear tracks.
+// kind 2 (S2): smooth gradient + uniform noise in [-5,5] + 8 discs of radius 40 on linear tracks of fixed length.
 // kind 3: iid uniform bytes (worst case for the selection search).
 // kind 4: gradient + approximately Gaussian noise (sigma ~ 3, sum of 4 uniforms) + the discs of kind 2.
 CHB_HD uint8_t synth_byte(int kind, uint64_t seed, int f, int n_frames, int y, int x, int ch, int W, int H) {
@@ -110,14 +110,17 @@ CHB_HD uint8_t synth_byte(int kind, uint64_t seed, int f, int n_frames, int y, i
     int v = base + noise;
 #pragma unroll 1
     for (int k = 0; k < 8; k++) {
-        // disc k: start (x0, y0), velocity (vx, vy) px/frame, wrapping around the image
+        // disc k: start (x0, y0) and a linear track of fixed length over the whole clip (200*(1 + k%3) px in x, +-200 px in y),
+        // wrapping around the image: 1..3 px/frame for a 200-frame series, slower for longer clips, so the share of pixels
+        // a disc ever touches (~1.3 % at 24 MP) does not depend on the frame count
         long long x0 = ((long long)W * (2 * k + 1)) / 16, y0 = ((long long)H * ((5 * k + 3) % 16)) / 16;
-        int vx = 1 + (k % 3), vy = (k & 1) ? 1 : -1;
-        long long cx = (x0 + (long long)vx * f) % W, cy = ((y0 + (long long)vy * f) % H + H) % H;
+        long long lx = 200LL * (1 + (k % 3)), ly = (k & 1) ? 200LL : -200LL;
+        long long nf = n_frames > 0 ? n_frames : 1;
+        long long dxk = (lx * f) / nf, dyk = (ly * f) / nf;  // C division truncates toward zero on host and device alike
+        long long cx = (x0 + dxk) % W, cy = ((y0 + dyk) % H + H) % H;
         long long dx = x - cx, dy = y - cy;
         if (dx * dx + dy * dy <= 1600) v = (k & 1) ? 232 - 8 * ch : 24 + 8 * ch;
     }
-    (void)n_frames;
     return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
