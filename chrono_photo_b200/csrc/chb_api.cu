@@ -472,7 +472,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
                         const chb_debug_planes* dbg, float* kernel_ms) {
     if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_outlier: null argument");
     if (prm->background > CHB_BG_MEDIAN || prm->outlier > CHB_OUT_BACKWARD) return fail(CHB_ERR_INVALID, "chb_outlier: unknown background / outlier mode");
-    std::lock_guard<std::mutex> lk(st->call_mu);
+    // the caller holds st->call_mu: launch and fetch form one critical section per stack
     Window win;
     int rc = build_window(st, indices, n_indices, win, "chb_outlier");
     if (rc) return rc;
@@ -671,12 +671,12 @@ static int fetch_impl(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint
 
 extern "C" int chb_outlier_debug(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, uint8_t* out_image,
                                  uint8_t* out_mask, uint64_t* n_warnings, const chb_debug_planes* dbg) {
-    if (!out_image) return fail(CHB_ERR_INVALID, "chb_outlier: out_image is null");
+    if (!out_image || !st) return fail(CHB_ERR_INVALID, "chb_outlier: null argument");
     int rc = chb_stack_sync(st);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(st->call_mu);
     rc = outlier_impl(st, prm, indices, n_indices, out_mask != nullptr, dbg, nullptr);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(st->call_mu);
     return fetch_impl(st, out_image, out_mask, n_warnings);
 }
 extern "C" int chb_outlier(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, uint8_t* out_image,
@@ -684,6 +684,8 @@ extern "C" int chb_outlier(chb_stack* st, const chb_outlier_params* prm, const i
     return chb_outlier_debug(st, prm, indices, n_indices, out_image, out_mask, n_warnings, nullptr);
 }
 extern "C" int chb_outlier_device(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, int want_mask, float* kernel_ms) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_outlier_device: null stack");
+    std::lock_guard<std::mutex> lk(st->call_mu);
     return outlier_impl(st, prm, indices, n_indices, want_mask != 0, nullptr, kernel_ms);
 }
 extern "C" int chb_fetch_last(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
@@ -695,7 +697,7 @@ extern "C" int chb_fetch_last(chb_stack* st, uint8_t* out_image, uint8_t* out_ma
 // ------------------------------------------------------------------------------------------------ K2 dispatch
 static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, float* kernel_ms) {
     if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_simple: null argument");
-    std::lock_guard<std::mutex> lk(st->call_mu);
+    // the caller holds st->call_mu
     Window win;
     // SimpleProcessor accepts any index order in principle (src/simple.rs:142-146), but every caller passes ascending
     // windows (src/main.rs:398-404); the time-sliced stack relies on it.
@@ -788,15 +790,17 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
 }
 
 extern "C" int chb_simple(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, uint8_t* out_image) {
-    if (!out_image) return fail(CHB_ERR_INVALID, "chb_simple: out_image is null");
+    if (!out_image || !st) return fail(CHB_ERR_INVALID, "chb_simple: null argument");
     int rc = chb_stack_sync(st);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(st->call_mu);
     rc = simple_impl(st, prm, indices, n_indices, nullptr);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(st->call_mu);
     return fetch_impl(st, out_image, nullptr, nullptr);
 }
 extern "C" int chb_simple_device(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, float* kernel_ms) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_simple_device: null stack");
+    std::lock_guard<std::mutex> lk(st->call_mu);
     return simple_impl(st, prm, indices, n_indices, kernel_ms);
 }
 

@@ -148,8 +148,9 @@ int chb_simple(chb_stack *stack, const chb_simple_params *params, const int32_t 
 
 /* Device-resident variants used for kernel-only timing: results stay in the library's device buffers, nothing is
  * copied to the host. kernel_ms (may be NULL) receives the device time of the launches, measured with CUDA events
- * on the launching stream, max over the context's devices. chb_fetch_last copies the results of the calling
- * thread's last *_device call to the host. */
+ * on the launching stream, max over the context's devices. chb_fetch_last copies the results of the stack's last
+ * *_device call to the host (threads that share a stack must use chb_outlier / chb_simple, which launch and fetch in one
+ * critical section). */
 int chb_outlier_device(chb_stack *stack, const chb_outlier_params *params, const int32_t *indices, int n_indices,
                        int want_mask, float *kernel_ms);
 int chb_simple_device(chb_stack *stack, const chb_simple_params *params, const int32_t *indices, int n_indices, float *kernel_ms);

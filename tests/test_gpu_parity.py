@@ -352,6 +352,31 @@ def test_config5_chrono_video_with_shake_crop(ctx):
     fs.close()
 
 
+def test_concurrent_callers_like_the_rayon_video_pool(ctx):
+    # create_video calls one processor per output frame from a rayon pool (src/main.rs:260-261); decode threads upload
+    # distinct frames concurrently. The library must give every caller its own correct result.
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(97)
+    st = make_stack(rng, 48, 18, 40, 3, n_obj=40)
+    fs = cp.FrameStack(ctx, 40, 18, 3, 48)
+    with ThreadPoolExecutor(6) as pool:
+        list(pool.map(lambda i: fs.upload(i, st[i]), range(48)))
+    fs.sync()
+    wins = [list(range(s0, s0 + 12)) for s0 in range(0, 36, 2)]
+    t_gpu, t_orc = thr_pair((True, 0.05, 0.2))
+
+    def one(idx):
+        p = cp.OutlierProcessor(t_gpu, BG["median"], OM["extreme"])
+        return p.process(fs, idx)
+
+    with ThreadPoolExecutor(6) as pool:
+        got = list(pool.map(one, wins))
+    for idx, (img, msk) in zip(wins, got):
+        oimg, omsk, _ = orc.outlier(st, t_orc, BG["median"], OM["extreme"], indices=idx)
+        assert np.array_equal(img, oimg) and np.array_equal(msk, omsk)
+    fs.close()
+
+
 def test_multi_gpu_row_shards_match_single_gpu(ctx):
     import torch
     if torch.cuda.device_count() < 2:
