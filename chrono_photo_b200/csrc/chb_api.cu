@@ -468,8 +468,10 @@ static int fade_to_dev(const chb_fade& f, FadeDev& out, const char* who) {
     return CHB_OK;
 }
 
+static int collect_outlier(chb_stack* st, const chb_debug_planes* dbg, float* kernel_ms, bool want_mask);
+
 static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, bool want_mask,
-                        const chb_debug_planes* dbg, float* kernel_ms) {
+                        const chb_debug_planes* dbg, float* kernel_ms, bool enqueue_only = false) {
     if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_outlier: null argument");
     if (prm->background > CHB_BG_MEDIAN || prm->outlier > CHB_OUT_BACKWARD) return fail(CHB_ERR_INVALID, "chb_outlier: unknown background / outlier mode");
     // the caller holds st->call_mu: launch and fetch form one critical section per stack
@@ -620,6 +622,16 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         CU(cudaEventRecord(b.ev1, s));
         CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
     }
+    (void)P;
+    if (enqueue_only && tables_cached) {  // nothing on the host is reused before the launch has read it: return without waiting
+        st->last_has_mask = want_mask;
+        return CHB_OK;
+    }
+    return collect_outlier(st, dbg, kernel_ms, want_mask);
+}
+
+// Waits for the launches of every band and gathers timing, counters and debug planes.
+static int collect_outlier(chb_stack* st, const chb_debug_planes* dbg, float* kernel_ms, bool want_mask) {
     float ms_max = 0.0f;
     uint64_t warnings = 0, slow = 0, hard = 0;
     for (Band& b : st->bands) {
@@ -640,7 +652,6 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             if (dbg->n_outliers) CU(cudaMemcpy(dbg->n_outliers + off, b.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
         }
     }
-    (void)P;
     if (kernel_ms) *kernel_ms = ms_max;
     st->last_has_mask = want_mask;
     st->last_warnings = warnings;
@@ -687,6 +698,19 @@ extern "C" int chb_outlier_device(chb_stack* st, const chb_outlier_params* prm, 
     if (!st) return fail(CHB_ERR_INVALID, "chb_outlier_device: null stack");
     std::lock_guard<std::mutex> lk(st->call_mu);
     return outlier_impl(st, prm, indices, n_indices, want_mask != 0, nullptr, kernel_ms);
+}
+extern "C" int chb_outlier_enqueue(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, int want_mask) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_outlier_enqueue: null stack");
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    return outlier_impl(st, prm, indices, n_indices, want_mask != 0, nullptr, nullptr, true);
+}
+extern "C" int chb_stack_wait(chb_stack* st, float* last_kernel_ms, uint64_t* n_warnings) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_stack_wait: null stack");
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    int rc = collect_outlier(st, nullptr, last_kernel_ms, st->last_has_mask);
+    if (rc) return rc;
+    if (n_warnings) *n_warnings = st->last_warnings;
+    return CHB_OK;
 }
 extern "C" int chb_fetch_last(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_fetch_last: null stack");

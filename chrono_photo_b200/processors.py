@@ -93,6 +93,12 @@ class FrameStack:
     def sync(self):
         _lib.check(_lib.lib().chb_stack_sync(self._h))
 
+    def wait(self):
+        """Waits for enqueued compositing launches; returns (device ms of the last launch, its warning count)."""
+        ms, warn = C.c_float(0), C.c_uint64(0)
+        _lib.check(_lib.lib().chb_stack_wait(self._h, C.byref(ms), C.byref(warn)))
+        return ms.value, warn.value
+
     def fill_synthetic(self, kind, seed=42, row0_global=0, full_height=None):
         _lib.check(_lib.lib().chb_stack_fill_synthetic(self._h, int(kind), int(seed), int(row0_global),
                                                       int(self.height if full_height is None else full_height)))
@@ -192,6 +198,13 @@ class OutlierProcessor:
         _lib.check(_lib.lib().chb_outlier_device(stack._h, C.byref(p), ip, n, 1 if want_mask else 0, C.byref(ms)))
         self.kernel_ms = ms.value
         return ms.value
+
+
+    def enqueue_device(self, stack, image_indices=None, want_mask=True):
+        """Launch only (no host wait); pair with FrameStack.wait()."""
+        ip, n, _keep = _indices(image_indices)
+        p = self._params()
+        _lib.check(_lib.lib().chb_outlier_enqueue(stack._h, C.byref(p), ip, n, 1 if want_mask else 0))
 
 
 class SimpleProcessor:

@@ -155,6 +155,11 @@ int chb_outlier_device(chb_stack *stack, const chb_outlier_params *params, const
                        int want_mask, float *kernel_ms);
 int chb_simple_device(chb_stack *stack, const chb_simple_params *params, const int32_t *indices, int n_indices, float *kernel_ms);
 int chb_fetch_last(chb_stack *stack, uint8_t *out_image, uint8_t *out_mask, uint64_t *n_warnings);
+/* Back-to-back launches without a host round trip per call: chb_outlier_enqueue only launches (it waits by itself when
+ * the window / sample / fade tables differ from the previous call's), chb_stack_wait waits for everything enqueued and
+ * returns the device time of the last launch and its warning count. */
+int chb_outlier_enqueue(chb_stack *stack, const chb_outlier_params *params, const int32_t *indices, int n_indices, int want_mask);
+int chb_stack_wait(chb_stack *stack, float *last_kernel_ms, uint64_t *n_warnings);
 
 /* Counters for bench.py: kernels launched by this library since the last reset (process-wide),
  * and, for the last outlier call on this thread, how many pixels left the certified fast path. */
