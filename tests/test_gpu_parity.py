@@ -377,6 +377,87 @@ def test_concurrent_callers_like_the_rayon_video_pool(ctx):
     fs.close()
 
 
+@pytest.mark.parametrize("seed", range(48))
+def test_random_option_fuzz_against_oracle(ctx, seed):
+    # seeded random walk through the option space: frame count, channels, data regime, threshold kind and size, policies,
+    # weights, fades, windows, --sample; every case bit-compared with the oracle (composite, mask, medians, counts)
+    rng = np.random.default_rng(10_000 + seed)
+    n = int(rng.choice([1, 2, 3, 5, 9, 16, 17, 31, 48, 65, 100, 129, 200, 260]))
+    c = int(rng.choice([3, 4]))
+    h, w = int(rng.integers(3, 9)), int(rng.integers(5, 70))
+    regime = rng.integers(0, 4)
+    if regime == 0:
+        st = make_stack(rng, n, h, w, c, noise=int(rng.integers(0, 12)), n_obj=int(rng.integers(0, 30)))
+    elif regime == 1:
+        st = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    elif regime == 2:
+        st = rng.choice(np.array([0, 255, 3, 252], np.uint8), size=(n, h, w, c))
+    else:
+        base = rng.integers(0, 256, size=(1, h, w, c))
+        st = np.clip(base + np.rint(rng.normal(0, rng.uniform(0.5, 9), size=(n, h, w, c))), 0, 255).astype(np.uint8)
+    absolute = bool(rng.integers(0, 2))
+    if absolute:
+        mn = float(rng.choice([0.0, 0.01, 0.05, 0.1, 0.3]))
+        spec = (True, mn, mn + float(rng.choice([0.0, 0.05, 0.15, 0.5])))
+    else:
+        mn = float(rng.choice([0.5, 1.0, 3.0, 6.0]))
+        spec = (False, mn, mn + float(rng.choice([0.0, 1.0, 2.0])))
+    idx = None
+    if n >= 4 and rng.integers(0, 2):
+        a0 = int(rng.integers(0, n // 2))
+        step = int(rng.choice([1, 1, 2, 3]))
+        idx = list(range(a0, int(rng.integers(a0 + 1, n + 1)), step))
+    nwin = len(idx) if idx is not None else n
+    if not absolute and nwin < 3:
+        spec = (True, 0.05, 0.2)
+    weights = tuple(float(x) for x in rng.choice([1.0, 1.0, 1.0, 0.0, 0.5, 2.0], size=4))
+    if not any(weights[:c]):
+        weights = (1.0,) + weights[1:]
+    fade = None
+    if rng.integers(0, 3) == 0:
+        f0 = int(rng.integers(-3, 5))
+        fade = (int(rng.integers(0, 2)), bool(rng.integers(0, 2)), [(f0, float(rng.uniform(-0.2, 1.3))), (f0 + int(rng.integers(1, 12)), float(rng.uniform(-0.2, 1.3)))])
+    sample = None
+    if rng.integers(0, 4) == 0:
+        sample = int(rng.integers(3 if not absolute else 1, nwin + 3))
+        if not absolute and min(sample, nwin) < 3:
+            sample = None
+    bg = str(rng.choice(["first", "random", "average", "median"]))
+    om = str(rng.choice(["first", "last", "extreme", "average", "forward", "backward"]))
+    check_outlier(ctx, st, spec, bg, om, weights=weights, fade=fade, indices=idx, sample=sample, seed=seed)
+    fs = upload(ctx, st)
+    darker = bool(rng.integers(0, 2))
+    wsimple = weights if rng.integers(0, 2) else (1, 1, 1, 1)
+    got = cp.SimpleProcessor(wsimple, cp.Fade(*fade) if fade else None, darker).process(fs, idx)
+    assert np.array_equal(got, orc.simple(st, darker, wsimple, orc.fade(*fade) if fade else None, idx))
+    fs.close()
+
+
+def test_error_paths_report_instead_of_panicking(ctx):
+    from chrono_photo_b200._lib import ChbError
+    st = np.zeros((6, 4, 8, 3), np.uint8)
+    fs = cp.FrameStack(ctx, 8, 4, 3, 6)
+    for i in range(5):
+        fs.upload(i, st[i])
+    proc = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2)
+    with pytest.raises(ChbError) as e:  # frame 5 was never uploaded
+        proc.process(fs)
+    assert e.value.code == 4
+    proc.process(fs, [0, 1, 2, 3, 4])  # a window that avoids it is fine
+    for bad in ([3, 2], [0, 0], [-1, 2], [0, 6], []):
+        with pytest.raises(ChbError) as e:
+            proc.process(fs, bad)
+        assert e.value.code == 1
+    with pytest.raises(ChbError):
+        cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2, sample_count=0).process(fs, [0, 1, 2])
+    with pytest.raises(ChbError) as e:
+        cp.FrameStack(ctx, 8, 4, 2, 6)  # only Rgb8 / Rgba8 (src/main.rs:550-567)
+    assert e.value.code == 3
+    with pytest.raises(ChbError):
+        cp.FrameStack(ctx, 0, 4, 3, 6)
+    fs.close()
+
+
 def test_multi_gpu_row_shards_match_single_gpu(ctx):
     import torch
     if torch.cuda.device_count() < 2:
