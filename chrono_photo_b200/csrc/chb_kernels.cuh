@@ -30,16 +30,18 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// The G lanes that share a pixel are lanes j * (32/G) + pl, j = 0..G-1 (pixel index in the low bits, so a quarter warp
+// reads 128 contiguous bytes of a staged row): reductions over j use xor masks 32/G, 2*32/G, .., 16.
 template <int G>
 __device__ __forceinline__ uint32_t group_sum(uint32_t v) {
 #pragma unroll
-    for (int m = 1; m < G; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    for (int m = 32 / G; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     return v;
 }
 template <int G>
 __device__ __forceinline__ uint32_t group_or(uint32_t v) {
 #pragma unroll
-    for (int m = 1; m < G; m <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
+    for (int m = 32 / G; m < 32; m <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
     return v;
 }
 
@@ -647,7 +649,14 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center,
     int p = center - 2;
     p = p < 0 ? 0 : (p > 251 ? 251 : p);
     const uint32_t c0 = rep4(p), c1 = c0 + 0x01010101u, c2 = c1 + 0x01010101u, c3 = c2 + 0x01010101u, c4 = c3 + 0x01010101u;
-    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+#ifdef CHB_WINDOW_CHAINS5
+#pragma unroll
+    for (int q = 0; q < W4; q++) {
+        f0 = sad4_acc(x[q], c0, f0); f1 = sad4_acc(x[q], c1, f1); f2 = sad4_acc(x[q], c2, f2); f3 = sad4_acc(x[q], c3, f3); f4 = sad4_acc(x[q], c4, f4);
+    }
+#else
+    uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
 #pragma unroll
     for (int q = 0; q < W4; q += 2) {
         f0 = sad4_acc(x[q], c0, f0); f1 = sad4_acc(x[q], c1, f1); f2 = sad4_acc(x[q], c2, f2); f3 = sad4_acc(x[q], c3, f3); f4 = sad4_acc(x[q], c4, f4);
@@ -655,6 +664,7 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center,
         h4 = sad4_acc(x[q + 1], c4, h4);
     }
     f0 += h0; f1 += h1; f2 += h2; f3 += h3; f4 += h4;
+#endif
     int n0, n1, n2, n3;
     if (G == 1) {
         n0 = ((int)f1 - (int)f0 + cap) >> 1; n1 = ((int)f2 - (int)f1 + cap) >> 1;
@@ -936,7 +946,7 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* h
                                          uint32_t* acc_slot) {
     constexpr int W4 = 4 * WPL;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
-    const int j = lane % G, pl = lane / G;
+    const int j = lane / (32 / G), pl = lane % (32 / G);
     const bool active = pl < count;
     const long long pix = hq[active ? pl : 0];
     const long long tile = pix >> 5;
@@ -965,10 +975,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     constexpr int W4 = 4 * WPL;
     constexpr int PPW = 32 / G;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
-    constexpr bool kStage = (G == 1);  // a tile's band is one contiguous slab: stage it with one TMA bulk copy per pixel-band
+    // G == 1: a tile's band is one contiguous slab, staged by ONE TMA bulk copy per pixel-band. With G > 1 a slab is
+    // n_groups rows of 512/G bytes; staging those with one small bulk copy per row measured slower than direct 128-bit
+    // loads (10.4 vs 8.7 ms on the 1000-frame UHD stack), so those variants load straight into registers.
+    constexpr bool kStage = (G == 1);
+    constexpr int kRowBytes = 512 / G;  // bytes of one (band, group) row that belong to this warp's 32/G pixels
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
-    const int j = lane % G, pl = lane / G;
+    const int j = lane / PPW, pl = lane % PPW;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long n_tasks = a.n_tiles * G;
     const int cap = W4 * 4 * G;     // bytes per pixel-band across the G lanes
@@ -982,17 +996,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     uint32_t* const acc_slot = reinterpret_cast<uint32_t*>(smem_raw + kQueueBytes + kHardBytes + kBarBytes) + threadIdx.x;
     uint8_t* const stage = smem_raw + kQueueBytes + kHardBytes + kBarBytes + kAccBytes + warp_in_cta * (WPL * 512);
     int qcount = 0, hcount = 0;
-    const int staged_groups = a.n_groups < WPL ? a.n_groups : WPL;
+    const int staged_groups = a.n_groups < WPL * G ? a.n_groups : WPL * G;
     uint32_t parity = 0;
     if (kStage) {
         if (lane == 0) mbar_init(bar, 1);
         __syncwarp();
     }
-    auto stage_band = [&](long long task, int c) {  // one lane starts the copy of a whole pixel-band slab
-        if (lane == 0) {
-            const uint8_t* src = a.stack + task * tbytes + ((long long)c * a.NG + a.g0) * (kTilePixels * kUnitBytes);
-            mbar_expect_tx(bar, (uint32_t)staged_groups * 512u);
-            bulk_g2s(stage, src, (uint32_t)staged_groups * 512u, bar);
+    // Starts the copy of one pixel-band of a tile slice: with G == 1 the slab is contiguous (one bulk copy by one lane);
+    // with G > 1 every frame group contributes a row of 512/G bytes, copied by the lanes in parallel onto one mbarrier.
+    auto stage_band = [&](long long task, int c) {
+        const long long tile = task / G;
+        const uint8_t* src = a.stack + tile * tbytes + ((long long)c * a.NG + a.g0) * (kTilePixels * kUnitBytes) + (task % G) * kRowBytes;
+        if (G == 1) {
+            if (lane == 0) {
+                mbar_expect_tx(bar, (uint32_t)staged_groups * 512u);
+                bulk_g2s(stage, src, (uint32_t)staged_groups * 512u, bar);
+            }
+        } else {
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)staged_groups * kRowBytes);
+            __syncwarp();
+            for (int r = lane; r < staged_groups; r += 32) bulk_g2s(stage + r * kRowBytes, src + (long long)r * 512, kRowBytes, bar);
         }
     };
 
@@ -1016,7 +1039,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
 #pragma unroll
                 for (int i = 0; i < WPL; i++) {
                     uint4 v = make_uint4(0, 0, 0, 0);
-                    if ((!GENERIC && i < WPL - 1) || i < staged_groups) v = *reinterpret_cast<const uint4*>(stage + i * 512 + lane * 16);
+                    if ((!GENERIC && i < WPL - 1) || i * G + j < staged_groups)
+                        v = *reinterpret_cast<const uint4*>(stage + (i * G + j) * kRowBytes + pl * 16);  // a quarter warp reads 128 contiguous bytes
                     A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
                 }
                 __syncwarp();  // every lane has read the slab before the next copy may overwrite it
