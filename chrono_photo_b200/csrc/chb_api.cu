@@ -527,6 +527,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     if (rc) return rc;
     a.frame_offset = indices ? indices[0] : 0;  // src/chrono.rs:102-103
     a.contig_f0 = (win.frames.back() - win.frames.front() + 1 == n) ? win.frames.front() : -1;
+    a.exact_quartiles = (dbg && (dbg->q1 || dbg->q3)) ? 1 : 0;
     a.seed = prm->seed;
 
     // host tables

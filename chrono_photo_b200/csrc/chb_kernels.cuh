@@ -95,6 +95,7 @@ struct OutlierArgs {
     int bg, om;
     FadeDev fade;
     int frame_offset;
+    int exact_quartiles;     // 1: the fast tier computes exact quartiles (debug planes requested) instead of an IQR bound
     int contig_f0;           // >= 0: the window is the contiguous frame range starting here (position s = frame contig_f0 + s)
     unsigned long long seed, pixel_offset;
     uint8_t* out_image;
@@ -639,51 +640,61 @@ __device__ __forceinline__ void band_stats(int cap, const uint32_t (&xs)[W4], ui
     }
 }
 
-// Straight-line median pair for the common case: F at five consecutive values p..p+4 around the band mean (ten
-// independent accumulator chains, no loop, no divergence) gives the four exact counts #{x <= p..p+3}; if both ranks fall
-// inside the window the pair is read off directly. Returns false when a rank lies outside (the pixel then takes the
-// iterative solver). The byte-range ends count as known: #{x <= -1} = 0, #{x <= 255} = cap.
-template <int W4, int G>
+// Straight-line median pair for the common case: F at NP consecutive values p..p+NP-1 around the band mean (independent
+// accumulator chains, no loop, no divergence) gives the NP-1 exact counts #{x <= p..p+NP-2}; if both ranks fall inside
+// the window the pair is read off directly. Returns false when a rank lies outside (the pixel then takes the iterative
+// solver). The byte-range ends count as known: #{x <= -1} = 0, #{x <= 255} = cap. NP = 5 for the median pair; NP = 7
+// when the counts also have to bound the inter-quartile range (relative thresholds).
+template <int W4, int G, int NP>
 __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center, int kp1, int kp2, int cap, int& v1, int& v2, bool want_f,
-                                            uint32_t& f_mid, int& p_mid) {
-    int p = center - 2;
-    p = p < 0 ? 0 : (p > 251 ? 251 : p);
-    const uint32_t c0 = rep4(p), c1 = c0 + 0x01010101u, c2 = c1 + 0x01010101u, c3 = c2 + 0x01010101u, c4 = c3 + 0x01010101u;
-    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
-#ifdef CHB_WINDOW_CHAINS5
+                                            uint32_t& f_mid, int& p_out, int (&cn)[NP - 1]) {
+    constexpr int kHalf = NP / 2;
+    int p = center - kHalf;
+    p = p < 0 ? 0 : (p > 256 - NP ? 256 - NP : p);
+    uint32_t cc[NP], f[NP];
 #pragma unroll
-    for (int q = 0; q < W4; q++) {
-        f0 = sad4_acc(x[q], c0, f0); f1 = sad4_acc(x[q], c1, f1); f2 = sad4_acc(x[q], c2, f2); f3 = sad4_acc(x[q], c3, f3); f4 = sad4_acc(x[q], c4, f4);
-    }
-#else
-    uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+    for (int k = 0; k < NP; k++) { cc[k] = rep4(p) + 0x01010101u * (uint32_t)k; f[k] = 0; }
+    if (NP <= 5) {  // two chains per value
+        uint32_t h[NP];
 #pragma unroll
-    for (int q = 0; q < W4; q += 2) {
-        f0 = sad4_acc(x[q], c0, f0); f1 = sad4_acc(x[q], c1, f1); f2 = sad4_acc(x[q], c2, f2); f3 = sad4_acc(x[q], c3, f3); f4 = sad4_acc(x[q], c4, f4);
-        h0 = sad4_acc(x[q + 1], c0, h0); h1 = sad4_acc(x[q + 1], c1, h1); h2 = sad4_acc(x[q + 1], c2, h2); h3 = sad4_acc(x[q + 1], c3, h3);
-        h4 = sad4_acc(x[q + 1], c4, h4);
+        for (int k = 0; k < NP; k++) h[k] = 0;
+#pragma unroll
+        for (int q = 0; q < W4; q += 2) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) f[k] = sad4_acc(x[q], cc[k], f[k]);
+#pragma unroll
+            for (int k = 0; k < NP; k++) h[k] = sad4_acc(x[q + 1], cc[k], h[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < NP; k++) f[k] += h[k];
+    } else {
+#pragma unroll
+        for (int q = 0; q < W4; q++) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) f[k] = sad4_acc(x[q], cc[k], f[k]);
+        }
     }
-    f0 += h0; f1 += h1; f2 += h2; f3 += h3; f4 += h4;
-#endif
-    int n0, n1, n2, n3;
     if (G == 1) {
-        n0 = ((int)f1 - (int)f0 + cap) >> 1; n1 = ((int)f2 - (int)f1 + cap) >> 1;
-        n2 = ((int)f3 - (int)f2 + cap) >> 1; n3 = ((int)f4 - (int)f3 + cap) >> 1;
+#pragma unroll
+        for (int k = 0; k < NP - 1; k++) cn[k] = ((int)f[k + 1] - (int)f[k] + cap) >> 1;
     } else {
         // per lane |F(c+1) - F(c)| <= bytes per lane = 4*W4: bias, pack two differences per word, one reduction each
         constexpr uint32_t kBias = 4 * W4;
-        uint32_t pa = (f1 - f0 + kBias) | ((f2 - f1 + kBias) << 16), pb = (f3 - f2 + kBias) | ((f4 - f3 + kBias) << 16);
-        pa = group_sum<G>(pa);
-        pb = group_sum<G>(pb);
-        n0 = (int)((pa & 0xffffu) >> 1); n1 = (int)(pa >> 17);  // sum(d + bias) = 2 * count because G * bias = cap
-        n2 = (int)((pb & 0xffffu) >> 1); n3 = (int)(pb >> 17);
+#pragma unroll
+        for (int k = 0; k < NP - 1; k += 2) {
+            uint32_t pk = (f[k + 1] - f[k] + kBias) | ((f[k + 2 < NP ? k + 2 : k + 1] - f[k + 1] + kBias) << 16);
+            pk = group_sum<G>(pk);
+            cn[k] = (int)((pk & 0xffffu) >> 1);  // sum(d + bias) = 2 * count because G * bias = cap
+            if (k + 1 < NP - 1) cn[k + 1] = (int)(pk >> 17);
+        }
     }
     f_mid = 0;
-    p_mid = p + 2;
-    if (want_f) f_mid = group_sum<G>(f2);  // F(p + 2): spread estimate for the quartile guesses (relative thresholds)
-    v1 = p + (n0 <= kp1) + (n1 <= kp1) + (n2 <= kp1) + (n3 <= kp1);
-    v2 = p + (n0 <= kp2) + (n1 <= kp2) + (n2 <= kp2) + (n3 <= kp2);
-    return ((n0 <= kp1) || p == 0) && ((kp2 < n3) || p == 251);
+    p_out = p;
+    if (want_f) f_mid = group_sum<G>(f[kHalf]);  // F(p + NP/2): spread estimate for the quartile guesses (relative thresholds)
+    v1 = p; v2 = p;
+#pragma unroll
+    for (int k = 0; k < NP - 1; k++) { v1 += (cn[k] <= kp1); v2 += (cn[k] <= kp2); }
+    return ((cn[0] <= kp1) || p == 0) && ((kp2 < cn[NP - 2]) || p == 256 - NP);
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -771,10 +782,11 @@ struct PixelAcc {
     uint32_t first_px;  // bytes of window position 0, band c in byte c
     float bound;        // certificate: upper bound of dist_sq over the window's frames
     bool hard;          // a median pair fell outside the 5-value window
+    bool approx;        // iqr_inv holds an upper bound, not the exact value (relative thresholds, fast tier)
     __device__ __forceinline__ void reset() {
 #pragma unroll
         for (int i = 0; i < kAccWords; i++) slot[i * stride] = 0u;
-        first_px = 0; bound = 0.0f; hard = false;
+        first_px = 0; bound = 0.0f; hard = false; approx = false;
     }
     __device__ __forceinline__ void set_median(int c, float v) { slot[c * stride] = __float_as_uint(v); }
     __device__ __forceinline__ void set_iqr_inv(int c, float v) { slot[(4 + c) * stride] = __float_as_uint(v); }
@@ -829,26 +841,48 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         band_stats<W4, G>(cap, xs, group_sum<G>(s), a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
         solved = true;
     } else if (FAST) {
-        int mlo, mhi, pm;
+        int mlo, mhi, p0;
         uint32_t fm;
         const bool rel = !a.absolute;
-        bool ok = band_window<W4, G>(A, __float2int_rn((float)bsum * a.inv_n_sub), a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, rel, fm, pm);
-        med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
-        center = (mlo + mhi) >> 1;
-        halfw = med - (float)center;
-        if (rel) {  // quartile pairs in their own windows around median -/+ 0.95 * mean absolute deviation
-            const float mad = ((float)fm - (float)pad * (float)pm) * a.inv_n_sub;
+        const int guess = __float2int_rn((float)bsum * a.inv_n_sub);
+        bool ok;
+        if (!rel) {
+            int cn[4];
+            ok = band_window<W4, G, 5>(A, guess, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, false, fm, p0, cn);
+        } else if (!a.exact_quartiles) {
+            // The certificate only needs an UPPER bound of 1/IQR, i.e. a lower bound of the IQR, and the counts of a
+            // 7-value window give one: Q1 <= d[hi rank of the Q1 pair] <= p + #{counts <= that rank} (valid when the rank is
+            // reached inside the window) and Q3 >= d[lo rank of the Q3 pair] >= p + #{counts <= that rank} (valid when at
+            // least the first count is). A pixel this bound cannot clear gets exact quartiles on the iterative tier.
+            int cn[6];
+            ok = band_window<W4, G, 7>(A, guess, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, false, fm, p0, cn);
+            const int r1 = a.rk[1] + pad, r4 = a.rk[4] + pad;
+            int ub1 = p0, lb4 = p0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { ub1 += (cn[k] <= r1); lb4 += (cn[k] <= r4); }
+            const bool ub_ok = cn[5] >= r1 + 1, lb_ok = (cn[0] <= r4) || p0 == 0;
+            const int L = lb4 - ub1;
+            if (ub_ok && lb_ok && L >= 1) iqi = 1.0f / (float)L;
+            else ok = false;
+            acc.approx = true;
+        } else {  // exact quartile pairs in their own windows around median -/+ 0.95 * mean absolute deviation
+            int cn[4];
+            ok = band_window<W4, G, 5>(A, guess, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, true, fm, p0, cn);
+            const float mad = ((float)fm - (float)pad * (float)(p0 + 2)) * a.inv_n_sub;
             const int dq = __float2int_rn(0.95f * mad);
             int alo, ahi, blo, bhi, pd;
             uint32_t fd;
-            ok = band_window<W4, G>(A, mlo - dq, a.rk[0] + pad, a.rk[1] + pad, cap, alo, ahi, false, fd, pd) && ok;
-            ok = band_window<W4, G>(A, mhi + dq, a.rk[4] + pad, a.rk[5] + pad, cap, blo, bhi, false, fd, pd) && ok;
+            ok = band_window<W4, G, 5>(A, mlo - dq, a.rk[0] + pad, a.rk[1] + pad, cap, alo, ahi, false, fd, pd, cn) && ok;
+            ok = band_window<W4, G, 5>(A, mhi + dq, a.rk[4] + pad, a.rk[5] + pad, cap, blo, bhi, false, fd, pd, cn) && ok;
             q1 = (a.rk[0] == a.rk[1]) ? (float)alo : (1.0f - a.q1_frac) * (float)alo + a.q1_frac * (float)ahi;  // src/chrono.rs:568-579
             q3 = (a.rk[4] == a.rk[5]) ? (float)blo : (1.0f - a.q3_frac) * (float)blo + a.q3_frac * (float)bhi;
             float iq = q3 - q1;
             if (iq == 0.0f) iq = 1.0f;
             iqi = 1.0f / iq;  // :246-252
         }
+        med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
+        center = (mlo + mhi) >> 1;
+        halfw = med - (float)center;
         acc.hard = acc.hard || !ok;
         solved = true;
     }
@@ -1064,7 +1098,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
             process_band<C, WPL, G, GENERIC, true>(a, A, c, j, pix, owner, cap, pad, acc);
         }
         // ---- hard pixels wait in the warp's queue until a warp-full can run the iterative solver together
-        const bool hard = owner && acc.hard;
+        // iterative tier: an order statistic outside its window, or a pixel the IQR bound could not clear
+        const bool to_hard = acc.hard || (acc.approx && !(acc.bound * 1.0001f < a.thr_sq));
+        const bool hard = owner && to_hard;
         const unsigned hb = __ballot_sync(0xffffffffu, hard);
         if (hb) {
             if (hard) hq[hcount + __popc(hb & ((1u << lane) - 1u))] = pix;
@@ -1077,7 +1113,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
             }
             __syncwarp();
         }
-        finish_pixel<C>(a, acc, pix, p, owner && !acc.hard, lane, queue, qcount);
+        finish_pixel<C>(a, acc, pix, p, owner && !to_hard, lane, queue, qcount);
         task += n_warps;
     }
     __syncwarp();

@@ -55,6 +55,9 @@ def check_outlier(ctx, st, spec, bg, om, weights=(1, 1, 1, 1), fade=None, indice
     assert np.array_equal(msk, omsk), "mask " + tag
     assert np.array_equal(img, oimg), "composite " + tag
     assert proc.warnings == owarn, "warnings " + tag
+    # the production call (no debug planes) may take shortcuts the debug call does not (IQR bound on the fast tier)
+    img2, msk2 = proc.process(fs, indices)
+    assert np.array_equal(img2, oimg) and np.array_equal(msk2, omsk) and proc.warnings == owarn, "non-debug call " + tag
     if own:
         fs.close()
     return img, msk
