@@ -1,0 +1,22 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every tier of K1, both K2 kernels."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import chrono_photo_b200 as cp
+from test_oracle import make_stack
+rng = np.random.default_rng(1)
+ctx = cp.Context([0])
+for n, c in ((25, 3), (200, 3), (70, 4), (300, 3)):
+    st = make_stack(rng, n, 6, 70, c, noise=5, n_obj=30)
+    fs = cp.FrameStack(ctx, 70, 6, c, n)
+    fs.upload_all(st)
+    for thr in (cp.Threshold.abs(0.05, 0.2), cp.Threshold.rel(3.0, 5.0)):
+        for bg, om in ((0, 2), (1, 4), (2, 3), (3, 5)):
+            cp.OutlierProcessor(thr, bg, om, seed=3).process(fs)
+            cp.OutlierProcessor(thr, bg, om, seed=3).process(fs, list(range(1, n - 1, 2)))
+    cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2, sample_count=max(3, n // 3)).process(fs)
+    cp.SimpleProcessor(darker=True).process(fs)
+    cp.SimpleProcessor((1, 0.5, 0.25, 0), cp.Fade(0, False, [(0, 1.0), (9, 0.0)]), False).process(fs, list(range(0, n, 3)))
+    fs.close()
+print("sanitize run done")
