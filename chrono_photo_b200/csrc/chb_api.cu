@@ -427,7 +427,7 @@ struct Variant { int wpl, g; };
 static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {8, 1}, {13, 1}, {7, 2}, {8, 2}, {8, 4}, {16, 4}, {8, 8}, {8, 16}, {8, 32}};
 static constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
-template <int C, bool GENERIC>
+template <int C, int GENERIC>  // GENERIC here is the kernel MODE: 0 generic, 1 absolute, 2 relative thresholds
 static OutlierKernel kernel_for(int v) {
     switch (v) {
         case 0: return outlier_kernel<C, 1, 1, GENERIC>;
@@ -554,10 +554,11 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
 
     // the lean kernel covers whole-stack launches whose leading register slots are all real frame groups
-    const bool generic = sub || a.window_masked || a.patch_slots || !a.lead_slots_full;
+    const bool generic = sub || a.window_masked || a.patch_slots || !a.lead_slots_full || a.exact_quartiles;
+    const int kmode = generic ? 0 : (a.absolute ? 1 : 2);
     OutlierKernel kern;
-    if (st->C == 3) kern = generic ? kernel_for<3, true>(vidx) : kernel_for<3, false>(vidx);
-    else kern = generic ? kernel_for<4, true>(vidx) : kernel_for<4, false>(vidx);
+    if (st->C == 3) kern = kmode == 0 ? kernel_for<3, 0>(vidx) : (kmode == 1 ? kernel_for<3, 1>(vidx) : kernel_for<3, 2>(vidx));
+    else kern = kmode == 0 ? kernel_for<4, 0>(vidx) : (kmode == 1 ? kernel_for<4, 1>(vidx) : kernel_for<4, 2>(vidx));
 
     // fingerprint of the device-side tables of this call
     std::vector<uint8_t> blob;
@@ -609,6 +610,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             ab.dbg_nout = dbg->n_outliers ? b.d_dbg_nout : nullptr;
         }
         const long long n_tasks = b.n_tiles * var.g;
+        if (n_tasks >= (1LL << 31)) return fail(CHB_ERR_UNSUPPORTED, "chb_outlier: band too large (%lld tile slices)", n_tasks);
         int occ = 1;
         const int smem = outlier_smem_bytes(var.wpl, var.g);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

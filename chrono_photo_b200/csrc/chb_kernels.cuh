@@ -48,6 +48,17 @@ __device__ __forceinline__ uint32_t group_or(uint32_t v) {
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier, used to stage the next pixel-band in shared memory
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr));
+    return r;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -764,44 +775,36 @@ __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry*
     }
 }
 
-__device__ __forceinline__ void set4(float (&v)[4], int c, float x) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
-}
-__device__ __forceinline__ void set4(uint32_t (&v)[4], int c, uint32_t x) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = (c == i) ? x : v[i];
-}
-
 // What a pixel accumulates over its bands. The per-band results (median, 1/IQR, sum) are only needed when the pixel
 // is finished, so they live in per-thread shared-memory slots ([field][thread], conflict-free) instead of registers.
 constexpr int kAccWords = 12;
 struct PixelAcc {
-    uint32_t* slot;     // this thread's slots: slot[k * stride]
-    int stride;
+    uint32_t slot;      // shared-memory address of this thread's slots: field k at slot + k * kAccStride
     uint32_t first_px;  // bytes of window position 0, band c in byte c
     float bound;        // certificate: upper bound of dist_sq over the window's frames
     bool hard;          // a median pair fell outside the 5-value window
     bool approx;        // iqr_inv holds an upper bound, not the exact value (relative thresholds, fast tier)
+    static constexpr uint32_t kAccStride = CHB_WARPS * 32 * 4;
     __device__ __forceinline__ void reset() {
 #pragma unroll
-        for (int i = 0; i < kAccWords; i++) slot[i * stride] = 0u;
+        for (int i = 0; i < kAccWords; i++) sts32(slot + i * kAccStride, 0u);
         first_px = 0; bound = 0.0f; hard = false; approx = false;
     }
-    __device__ __forceinline__ void set_median(int c, float v) { slot[c * stride] = __float_as_uint(v); }
-    __device__ __forceinline__ void set_iqr_inv(int c, float v) { slot[(4 + c) * stride] = __float_as_uint(v); }
-    __device__ __forceinline__ void set_sum(int c, uint32_t v) { slot[(8 + c) * stride] = v; }
-    __device__ __forceinline__ float median(int c) const { return __uint_as_float(slot[c * stride]); }
-    __device__ __forceinline__ float iqr_inv(int c) const { return __uint_as_float(slot[(4 + c) * stride]); }
-    __device__ __forceinline__ uint32_t sum(int c) const { return slot[(8 + c) * stride]; }
+    __device__ __forceinline__ void set_median(int c, float v) { sts32(slot + c * kAccStride, __float_as_uint(v)); }
+    __device__ __forceinline__ void set_iqr_inv(int c, float v) { sts32(slot + (4 + c) * kAccStride, __float_as_uint(v)); }
+    __device__ __forceinline__ void set_sum(int c, uint32_t v) { sts32(slot + (8 + c) * kAccStride, v); }
+    __device__ __forceinline__ float median(int c) const { return __uint_as_float(lds32(slot + c * kAccStride)); }
+    __device__ __forceinline__ float iqr_inv(int c) const { return __uint_as_float(lds32(slot + (4 + c) * kAccStride)); }
+    __device__ __forceinline__ uint32_t sum(int c) const { return lds32(slot + (8 + c) * kAccStride); }
 };
 
 // One pixel-band held in A: window mask, sum, order statistics, certificate term. FAST: try the straight-line window first
 // (absolute thresholds only); otherwise run the iterative solver.
-template <int C, int WPL, int G, bool GENERIC, bool FAST>
+template <int C, int WPL, int G, int MODE, bool FAST>
 __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)[4 * WPL], int c, int j, long long pix, bool write_dbg,
                                              int cap, int pad, PixelAcc& acc) {
     constexpr int W4 = 4 * WPL;
+    constexpr bool GENERIC = (MODE == 0);  // MODE 1 / 2: lean whole-stack kernels for absolute / relative thresholds
     const float w = a.w[c];
     if (GENERIC && a.window_masked) {  // frames outside the window must read as zero
 #pragma unroll
@@ -840,16 +843,17 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         for (int q = 0; q < W4; q++) s = __dp4a(xs[q], 0x01010101u, s);
         band_stats<W4, G>(cap, xs, group_sum<G>(s), a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
         solved = true;
-    } else if (FAST) {
+    } else if (FAST && (MODE != 0 || a.absolute || !a.exact_quartiles)) {
+        // (exact quartiles for the debug planes are only produced by the iterative solver below, GENERIC kernel)
         int mlo, mhi, p0;
         uint32_t fm;
-        const bool rel = !a.absolute;
+        const bool rel = (MODE == 2) || (MODE == 0 && !a.absolute);
         const int guess = __float2int_rn((float)bsum * a.inv_n_sub);
         bool ok;
         if (!rel) {
             int cn[4];
             ok = band_window<W4, G, 5>(A, guess, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, false, fm, p0, cn);
-        } else if (!a.exact_quartiles) {
+        } else {
             // The certificate only needs an UPPER bound of 1/IQR, i.e. a lower bound of the IQR, and the counts of a
             // 7-value window give one: Q1 <= d[hi rank of the Q1 pair] <= p + #{counts <= that rank} (valid when the rank is
             // reached inside the window) and Q3 >= d[lo rank of the Q3 pair] >= p + #{counts <= that rank} (valid when at
@@ -865,20 +869,6 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
             if (ub_ok && lb_ok && L >= 1) iqi = 1.0f / (float)L;
             else ok = false;
             acc.approx = true;
-        } else {  // exact quartile pairs in their own windows around median -/+ 0.95 * mean absolute deviation
-            int cn[4];
-            ok = band_window<W4, G, 5>(A, guess, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, true, fm, p0, cn);
-            const float mad = ((float)fm - (float)pad * (float)(p0 + 2)) * a.inv_n_sub;
-            const int dq = __float2int_rn(0.95f * mad);
-            int alo, ahi, blo, bhi, pd;
-            uint32_t fd;
-            ok = band_window<W4, G, 5>(A, mlo - dq, a.rk[0] + pad, a.rk[1] + pad, cap, alo, ahi, false, fd, pd, cn) && ok;
-            ok = band_window<W4, G, 5>(A, mhi + dq, a.rk[4] + pad, a.rk[5] + pad, cap, blo, bhi, false, fd, pd, cn) && ok;
-            q1 = (a.rk[0] == a.rk[1]) ? (float)alo : (1.0f - a.q1_frac) * (float)alo + a.q1_frac * (float)ahi;  // src/chrono.rs:568-579
-            q3 = (a.rk[4] == a.rk[5]) ? (float)blo : (1.0f - a.q3_frac) * (float)blo + a.q3_frac * (float)bhi;
-            float iq = q3 - q1;
-            if (iq == 0.0f) iq = 1.0f;
-            iqi = 1.0f / iq;  // :246-252
         }
         med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
         center = (mlo + mhi) >> 1;
@@ -975,9 +965,9 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
 }
 
 // Hard pixels, 32/G at a time: each pixel group reloads its own bands (L2) and runs the iterative solver.
-template <int C, int WPL, int G, bool GENERIC>
+template <int C, int WPL, int G, int MODE>
 __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* hq, int count, int lane, int cap, int pad, QueueEntry* queue, int& qcount,
-                                         uint32_t* acc_slot) {
+                                         uint32_t acc_slot) {
     constexpr int W4 = 4 * WPL;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
     const int j = lane / (32 / G), pl = lane % (32 / G);
@@ -988,7 +978,7 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* h
     const long long band_stride = (long long)a.NG * (kTilePixels * kUnitBytes);
     const uint8_t* base = a.stack + tile * tile_bytes(C, a.NG) + ((long long)(a.g0 + j) * kTilePixels + p) * kUnitBytes;
     PixelAcc acc;
-    acc.slot = acc_slot; acc.stride = kWarpsPerCta * 32;
+    acc.slot = acc_slot;
     acc.reset();
     uint32_t A[W4];
 #pragma unroll 1
@@ -999,13 +989,14 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* h
             if (i * G + j < a.n_groups) v = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + i * kSlotStride));
             A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
         }
-        process_band<C, WPL, G, GENERIC, false>(a, A, c, j, pix, active && j == 0, cap, pad, acc);
+        process_band<C, WPL, G, MODE, false>(a, A, c, j, pix, active && j == 0, cap, pad, acc);
     }
     finish_pixel<C>(a, acc, pix, p, active && j == 0, lane, queue, qcount);
 }
 
-template <int C, int WPL, int G, bool GENERIC>
+template <int C, int WPL, int G, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(const __grid_constant__ OutlierArgs a) {
+    constexpr bool GENERIC = (MODE == 0);
     constexpr int W4 = 4 * WPL;
     constexpr int PPW = 32 / G;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
@@ -1017,18 +1008,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
     const int j = lane / PPW, pl = lane % PPW;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long n_tasks = a.n_tiles * G;
+    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n_tasks = (int)(a.n_tiles * G);  // the host keeps n_tiles * G below 2^31
     const int cap = W4 * 4 * G;     // bytes per pixel-band across the G lanes
     const int pad = cap - a.n_sub;  // zero bytes that take part in the selection
-    const long long tbytes = tile_bytes(C, a.NG);
-    const long long band_stride = (long long)a.NG * (kTilePixels * kUnitBytes);
-    const long long lane_off = ((long long)(a.g0 + j) * kTilePixels) * kUnitBytes;
     QueueEntry* const queue = reinterpret_cast<QueueEntry*>(smem_raw) + warp_in_cta * kQueueCap;
     long long* const hq = reinterpret_cast<long long*>(smem_raw + kQueueBytes) + warp_in_cta * kQueueCap;
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + kQueueBytes + kHardBytes) + warp_in_cta;
-    uint32_t* const acc_slot = reinterpret_cast<uint32_t*>(smem_raw + kQueueBytes + kHardBytes + kBarBytes) + threadIdx.x;
+    const uint32_t acc_slot = smem_u32(smem_raw + kQueueBytes + kHardBytes + kBarBytes) + threadIdx.x * 4;
     uint8_t* const stage = smem_raw + kQueueBytes + kHardBytes + kBarBytes + kAccBytes + warp_in_cta * (WPL * 512);
+    const uint32_t stage_lane = smem_u32(stage) + j * kRowBytes + pl * 16;  // this lane's 16 bytes of row (slot * G + j)
     int qcount = 0, hcount = 0;
     const int staged_groups = a.n_groups < WPL * G ? a.n_groups : WPL * G;
     uint32_t parity = 0;
@@ -1038,9 +1027,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     }
     // Starts the copy of one pixel-band of a tile slice: with G == 1 the slab is contiguous (one bulk copy by one lane);
     // with G > 1 every frame group contributes a row of 512/G bytes, copied by the lanes in parallel onto one mbarrier.
-    auto stage_band = [&](long long task, int c) {
-        const long long tile = task / G;
-        const uint8_t* src = a.stack + tile * tbytes + ((long long)c * a.NG + a.g0) * (kTilePixels * kUnitBytes) + (task % G) * kRowBytes;
+    auto stage_band = [&](int task, int c) {
+        const int tile = task / G;
+        const uint8_t* src = a.stack + (long long)tile * tile_bytes(C, a.NG) + ((long long)c * a.NG + a.g0) * (kTilePixels * kUnitBytes) + (task % G) * kRowBytes;
         if (G == 1) {
             if (lane == 0) {
                 mbar_expect_tx(bar, (uint32_t)staged_groups * 512u);
@@ -1054,15 +1043,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     };
 
     uint32_t A[W4];  // the current pixel-band
-    long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int task = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (kStage && task < n_tasks) stage_band(task, 0);
     while (task < n_tasks) {
-        const long long tile = task / G;
-        const int p = (int)(task % G) * PPW + pl;
-        const long long pix = tile * kTilePixels + p;
+        const int tile = task / G;
+        const int p = (task % G) * PPW + pl;
+        const long long pix = (long long)tile * kTilePixels + p;
         const bool owner = pix < a.n_pixels && j == 0;
         PixelAcc acc;
-        acc.slot = acc_slot; acc.stride = kWarpsPerCta * 32;
+        acc.slot = acc_slot;
         acc.reset();
 #pragma unroll 1
         for (int c = 0; c < C; c++) {
@@ -1074,15 +1063,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
                 for (int i = 0; i < WPL; i++) {
                     uint4 v = make_uint4(0, 0, 0, 0);
                     if ((!GENERIC && i < WPL - 1) || i * G + j < staged_groups)
-                        v = *reinterpret_cast<const uint4*>(stage + (i * G + j) * kRowBytes + pl * 16);  // a quarter warp reads 128 contiguous bytes
+                        v = lds128(stage_lane + i * (G * kRowBytes));  // a quarter warp reads 128 contiguous bytes
                     A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
                 }
                 __syncwarp();  // every lane has read the slab before the next copy may overwrite it
                 const bool last = (c == C - 1);
-                const long long nt = last ? task + n_warps : task;
+                const int nt = last ? task + n_warps : task;
                 if (nt < n_tasks) stage_band(nt, last ? 0 : c + 1);
             } else {
-                const uint8_t* cb = a.stack + tile * tbytes + lane_off + (long long)p * kUnitBytes + c * band_stride;
+                const uint8_t* cb = a.stack + (long long)tile * tile_bytes(C, a.NG) + ((long long)(c * a.NG + a.g0 + j) * kTilePixels + p) * kUnitBytes;
 #pragma unroll
                 for (int i = 0; i < WPL; i++) {
                     uint4 v;
@@ -1095,7 +1084,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
                     A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
                 }
             }
-            process_band<C, WPL, G, GENERIC, true>(a, A, c, j, pix, owner, cap, pad, acc);
+            process_band<C, WPL, G, MODE, true>(a, A, c, j, pix, owner, cap, pad, acc);
         }
         // ---- hard pixels wait in the warp's queue until a warp-full can run the iterative solver together
         // iterative tier: an order statistic outside its window, or a pixel the IQR bound could not clear
@@ -1108,7 +1097,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
             if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(hb));
             __syncwarp();
             while (hcount >= PPW) {
-                drain_hard<C, WPL, G, GENERIC>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount, acc_slot);
+                drain_hard<C, WPL, G, MODE>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount, acc_slot);
                 hcount -= PPW;
             }
             __syncwarp();
@@ -1117,7 +1106,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
         task += n_warps;
     }
     __syncwarp();
-    if (hcount > 0) drain_hard<C, WPL, G, GENERIC>(a, hq, hcount, lane, cap, pad, queue, qcount, acc_slot);
+    if (hcount > 0) drain_hard<C, WPL, G, MODE>(a, hq, hcount, lane, cap, pad, queue, qcount, acc_slot);
     __syncwarp();
     if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
 }
