@@ -6,7 +6,9 @@
 
 A "step" is one pass of the hot path over one frame stack. Default workload = BASELINE.json configs[2]:
 `--mode outlier -t abs/0.05/0.2 -l extreme -b first`, 200 frames x 6000x4000 RGB8 (synthetic series S2, seed 42),
-row-sharded over the ranks (strong scaling: the image is fixed, every rank owns H/N rows; no data-path collective).
+row-sharded over the ranks with no data-path collective. N > 1 (torchrun): weak scaling by default -- every rank owns one
+full-size band (its own series of the workload's recipe) of an N-times taller image; the workload's own image cut into N
+bands (strong scaling, H/N rows per rank) is timed in the same run and reported as `strong_scaling`.
 value  = pixel-frames/s, stack resident in HBM, CUDA events around K steps, max over ranks.
 e2e    = same metric through the C ABI with pinned HOST frames: H2D upload of all frames + kernel + D2H of composite and
          mask inside the timed region.
@@ -149,7 +151,7 @@ def run_reference(args, wl):
     sample = f"rows [{min(H // 2, H - rows)}, +{rows}) x {W} px x {n} frames of the workload per step, in-memory stack (no JPEG decode / temp files)"
     print(json.dumps({
         "impl": "reference", "metric": "pixel-frames/s", "value": value, "unit": "pixel-frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": {"workload": wl, "description": desc, "frames": n, "height": H, "width": W, "channels": 3},
         "cpu_baseline": {"value": value, "unit": "pixel-frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pixel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,6 +222,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank owns a full-size band of an N-times taller image (default); strong = the workload's image row-sharded H/N")
     args = ap.parse_args()
     wl = args.workload
     if args.impl == "reference":
@@ -250,12 +254,22 @@ def main():
         torch.cuda.set_device(0)
     n_gpus = world if multi_proc else args.gpus
 
-    row0, rows = shard_rows(H, shard_rank, shard_world)
+    # Row-sharding: every rank owns a horizontal band, no data-path collective. Weak scaling (default): the image grows with
+    # the rank count (W x H*N, each rank a full H-row band); strong scaling: the W x H image itself is cut into N bands.
+    weak = args.scaling == "weak" and shard_world > 1
+    H_band = H
+    if weak:
+        row0, rows, H = shard_rank * H_band, H_band, H_band * shard_world
+    else:
+        row0, rows = shard_rows(H, shard_rank, shard_world)
     ctx = cp.Context(devices)
     if len(devices) == 1:
         ctx.set_stream(0, torch.cuda.current_stream().cuda_stream)  # torch events then bracket the launches
     stack = cp.FrameStack(ctx, W, rows, 3, n)
-    stack.fill_synthetic(kind, seed=42, row0_global=row0, full_height=H)
+    if weak:  # every band is its own full-size series of the workload's recipe (same per-GPU work as N = 1), seeds 42 + rank
+        stack.fill_synthetic(kind, seed=42 + shard_rank, row0_global=0, full_height=H_band)
+    else:
+        stack.fill_synthetic(kind, seed=42, row0_global=row0, full_height=H)
     proc = make_processor(cp, mode, pixel_offset=row0 * W)
     is_outlier = mode.startswith("outlier")
 
@@ -273,29 +287,32 @@ def main():
         return float(t.item())
 
     # ---- kernel-only: stack resident in HBM
-    for _ in range(args.warmup):
-        proc.process_device(stack)
+    def timed_steps(st, pr):
+        for _ in range(args.warmup):
+            pr.process_device(st)
+        barrier()
+        _lib.lib().chb_launch_count_reset()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        ev0.record()
+        if is_outlier:  # K launches back to back, one wait at the end: no host round trip inside the timed region
+            for _ in range(args.steps):
+                pr.enqueue_device(st)
+            st.wait()
+        else:
+            for _ in range(args.steps):
+                pr.process_device(st)
+        ev1.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        n_launch = int(_lib.lib().chb_launch_count())
+        ms_total = ev0.elapsed_time(ev1) if len(devices) == 1 else t_wall * 1e3
+        return max_over_ranks(ms_total / args.steps), n_launch
+
     sampler = ClockSampler(devices[0])
-    barrier()
-    _lib.lib().chb_launch_count_reset()
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record()
-    if is_outlier:  # K launches back to back, one wait at the end: no host round trip inside the timed region
-        for _ in range(args.steps):
-            proc.enqueue_device(stack)
-        stack.wait()
-    else:
-        for _ in range(args.steps):
-            proc.process_device(stack)
-    ev1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
+    ms_step, launches = timed_steps(stack, proc)
     clocks = sampler.stop()
-    launches = int(_lib.lib().chb_launch_count())
-    ms_total = ev0.elapsed_time(ev1) if len(devices) == 1 else t_wall * 1e3
-    ms_step = max_over_ranks(ms_total / args.steps)
     launch_ms = [proc.process_device(stack) for _ in range(min(5, args.steps))]  # per-launch device time (CUDA events on the launching stream)
     kernel_ms = max_over_ranks(sum(launch_ms) / len(launch_ms))
     total_pf = float(n) * H * W
@@ -312,10 +329,32 @@ def main():
                 "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "peak_source": peak_src,
                 "slow_path_pixels_per_launch": int(_lib.lib().chb_last_slow_pixels()) if is_outlier else 0}
 
+    # ---- the workload's own image cut into N bands (strong scaling), reported beside the weak-scaling headline
+    strong = None
+    if weak:
+        s_row0, s_rows = shard_rows(H_band, shard_rank, shard_world)
+        s_stack = cp.FrameStack(ctx, W, s_rows, 3, n)
+        s_stack.fill_synthetic(kind, seed=42, row0_global=s_row0, full_height=H_band)
+        s_proc = make_processor(cp, mode, pixel_offset=s_row0 * W)
+        s_ms, _ = timed_steps(s_stack, s_proc)
+        strong = {"value": float(n) * H_band * W / (s_ms / 1e3), "unit": "pixel-frames/s", "ms_per_step": s_ms,
+                  "image": f"{W}x{H_band} cut into {n_gpus} bands of {s_rows} rows"}
+
     # ---- end to end through the C ABI with pinned host frames
     e2e = None
     host = None
+    e_stack, e_rows, e_proc, e_pf, e_note = stack, rows, proc, float(n) * H * W, None
+    if weak and not args.no_e2e:
+        # pinned host copies of N full-size series may not fit the box's RAM: then the end-to-end leg runs on the strong shards
+        import psutil
+        avail = torch.tensor([float(psutil.virtual_memory().available)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(avail, op=dist.ReduceOp.MIN)
+        if float(avail.item()) < 1.5 * shard_world * n * rows * W * 3:
+            e_stack, e_rows, e_proc, e_pf = s_stack, s_rows, s_proc, float(n) * H_band * W
+            e_note = f"host RAM too small for {shard_world} pinned full-size series: measured on the {W}x{H_band} image cut into {shard_world} bands"
     if not args.no_e2e:
+        stack_w, rows_w, proc_w = stack, rows, proc
+        stack, rows, proc = e_stack, e_rows, e_proc
         frame_bytes = rows * W * 3
         host = torch.empty((n, rows, W, 3), dtype=torch.uint8, pin_memory=True)
         base, pitch = host.data_ptr(), W * 3
@@ -342,9 +381,14 @@ def main():
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
         d2h = frame_bytes * (2 if is_outlier else 1)
-        e2e = {"value": total_pf / e2e_s, "unit": "pixel-frames/s", "h2d_bytes_per_step": n * frame_bytes * (shard_world if multi_proc else 1),
+        e2e = {"value": e_pf / e2e_s, "unit": "pixel-frames/s", "h2d_bytes_per_step": n * frame_bytes * (shard_world if multi_proc else 1),
                "d2h_bytes_per_step": d2h * (shard_world if multi_proc else 1), "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps}
+        if e_note:
+            e2e["note"] = e_note
         stack2.close()
+        stack, rows, proc = stack_w, rows_w, proc_w
+    if weak:
+        s_stack.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
     cpu_baseline = None
@@ -382,12 +426,14 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "pixel-frames/s", "value": value, "unit": "pixel-frames/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (weak or n_gpus == 1) else "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl, "description": desc, "frames": n, "height": H, "width": W, "channels": 3, "series": f"S{kind} seed 42",
-                       "sharding": f"rows/{n_gpus}", "l2": "inputs (%.1f GB per GPU) larger than L2, no flush needed" % (stack.device_bytes(0) / 1e9),
+                       "sharding": (f"{n_gpus} bands of {rows} rows: a {W}x{H} image, every GPU owns one full-size band of the workload" if weak
+                                    else f"rows/{n_gpus}"), "l2": "inputs (%.1f GB per GPU) larger than L2, no flush needed" % (stack.device_bytes(0) / 1e9),
                        "launcher": "torchrun" if multi_proc else "single-process"},
             "hbm_gbs": achieved * n_gpus if n_gpus > 1 else achieved,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "strong_scaling": strong, "gpu_launches": launches, "clocks": clocks}))
     stack.close()
     ctx.close()
     if multi_proc:

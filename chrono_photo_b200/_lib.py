@@ -60,6 +60,8 @@ SYMBOLS = {
     "chb_fetch_last": (_i, [_vp, _vp, _vp, _u64p]),
     "chb_outlier_enqueue": (_i, [_vp, C.POINTER(OutlierParams), _i32p, _i, _i]),
     "chb_stack_wait": (_i, [_vp, _f32p, _u64p]),
+    "chb_outlier_video": (_i, [_vp, C.POINTER(OutlierParams), _i, _i, _i, _vp, _vp, _u64p]),
+    "chb_outlier_video_device": (_i, [_vp, C.POINTER(OutlierParams), _i, _i, _i, _i, _f32p]),
     "chb_launch_count": (C.c_uint64, []),
     "chb_launch_count_reset": (None, []),
     "chb_last_slow_pixels": (C.c_uint64, []),

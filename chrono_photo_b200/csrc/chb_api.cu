@@ -78,6 +78,14 @@ struct Band {
     float *d_dbg_median = nullptr, *d_dbg_q1 = nullptr, *d_dbg_q3 = nullptr;
     int* d_dbg_nout = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // chrono-video: two slots of window planes (composites, masks), per-window warning counters
+    uint8_t* d_vout[2] = {nullptr, nullptr};
+    uint8_t* d_vmask[2] = {nullptr, nullptr};
+    int v_cap_windows = 0;
+    unsigned long long* d_vwarn = nullptr;
+    int vwarn_cap = 0;
+    cudaEvent_t v_done[2] = {nullptr, nullptr};    // kernel writing slot s finished
+    cudaEvent_t v_copied[2] = {nullptr, nullptr};  // D2H of slot s finished
 };
 
 struct chb_stack {
@@ -171,6 +179,12 @@ static void free_band(Band& b) {
     cudaFree(b.d_dbg_median); cudaFree(b.d_dbg_q1); cudaFree(b.d_dbg_q3); cudaFree(b.d_dbg_nout);
     if (b.ev0) cudaEventDestroy(b.ev0);
     if (b.ev1) cudaEventDestroy(b.ev1);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(b.d_vout[s]); cudaFree(b.d_vmask[s]);
+        if (b.v_done[s]) cudaEventDestroy(b.v_done[s]);
+        if (b.v_copied[s]) cudaEventDestroy(b.v_copied[s]);
+    }
+    cudaFree(b.d_vwarn);
 }
 
 extern "C" int chb_stack_destroy(chb_stack* st) {
@@ -719,6 +733,205 @@ extern "C" int chb_fetch_last(chb_stack* st, uint8_t* out_image, uint8_t* out_ma
     if (!st) return fail(CHB_ERR_INVALID, "chb_fetch_last: null stack");
     std::lock_guard<std::mutex> lk(st->call_mu);
     return fetch_impl(st, out_image, out_mask, n_warnings);
+}
+
+// ------------------------------------------------------------------------------------------------ K3 dispatch (chrono-video)
+typedef void (*VideoKernel)(VideoArgs);
+template <int C>
+static VideoKernel video_kernel_for(int nw) {
+    switch (nw) {
+        case 2: return video_kernel<C, 2>;
+        case 4: return video_kernel<C, 4>;
+        case 6: return video_kernel<C, 6>;
+        case 8: return video_kernel<C, 8>;
+        case 10: return video_kernel<C, 10>;
+        case 12: return video_kernel<C, 12>;
+        case 14: return video_kernel<C, 14>;
+        default: return video_kernel<C, 16>;
+    }
+}
+static constexpr int kMaxVideoWindow = 64;
+
+// A run of n_windows windows of window_len consecutive frames, window i starting at frame first_start + i (the windows
+// create_video builds for `--video-in a/b/1`, src/main.rs:262-286). Host outputs (may be null: results stay on the devices,
+// only the last chunk's) are [n_windows][H*W*C] planes.
+static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_start, int window_len, int n_windows, uint8_t* out_images,
+                      uint8_t* out_masks, bool want_mask, uint64_t* warnings, float* kernel_ms) {
+    if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_outlier_video: null argument");
+    if (prm->background > CHB_BG_MEDIAN || prm->outlier > CHB_OUT_BACKWARD) return fail(CHB_ERR_INVALID, "chb_outlier_video: unknown background / outlier mode");
+    const int n = window_len;
+    if (n < 1 || n_windows < 1 || first_start < 0 || (long long)first_start + n_windows - 1 + n > st->N)
+        return fail(CHB_ERR_INVALID, "chb_outlier_video: windows [%d + i, %d + i + %d), i < %d leave the stack of %d frames", first_start, first_start, n,
+                    n_windows, st->N);
+    if (n > kMaxVideoWindow)
+        return fail(CHB_ERR_UNSUPPORTED, "chb_outlier_video: windows of %d frames; the sliding kernel holds at most %d (use chb_outlier per window)", n, kMaxVideoWindow);
+    if (prm->sample_count >= 0 && prm->sample_count < n)
+        return fail(CHB_ERR_UNSUPPORTED, "chb_outlier_video: --sample below the window length is not supported by the sliding kernel (use chb_outlier per window)");
+    if (!prm->thr_absolute && n < 3)
+        return fail(CHB_ERR_INVALID, "chb_outlier_video: relative thresholds need at least 3 samples (quantile() underflows, src/chrono.rs:569-570)");
+    for (int f = first_start; f < first_start + n_windows - 1 + n; f++)
+        if (!st->uploaded[f]) return fail(CHB_ERR_STATE, "chb_outlier_video: frame %d was never uploaded", f);
+
+    VideoArgs va;
+    memset(&va, 0, sizeof va);
+    OutlierArgs& a = va.o;
+    a.NG = st->NG; a.C = st->C;
+    a.n = n; a.n_sub = n;
+    a.inv_n_sub = 1.0f / (float)n;
+    if ((n + 1) % 2 == 0) a.rk[2] = a.rk[3] = (n + 1) / 2 - 1;  // median ranks (src/chrono.rs:582-591)
+    else { a.rk[2] = (n + 1) / 2 - 1; a.rk[3] = (n + 1) / 2; }
+    if (!prm->thr_absolute) {
+        quantile_ranks(n, 0.25f, a.rk[0], a.rk[1], a.q1_frac);
+        quantile_ranks(n, 0.75f, a.rk[4], a.rk[5], a.q3_frac);
+    }
+    a.absolute = prm->thr_absolute ? 1 : 0;
+    a.thr_min = prm->thr_min; a.thr_max = prm->thr_max; a.thr_scale = prm->thr_scale;
+    a.thr_sq = prm->thr_min * prm->thr_min;  // src/chrono.rs:220
+    for (int i = 0; i < 4; i++) a.w[i] = prm->weights[i];
+    a.bg = prm->background; a.om = prm->outlier;
+    int rc = fade_to_dev(prm->fade, a.fade, "chb_outlier_video");
+    if (rc) return rc;
+    a.seed = prm->seed;
+    const int nw = std::max(2, 2 * (((n + 3) / 4 + 1) / 2));  // window words, rounded up to an even count
+    auto word_mask = [&](int q) {
+        uint32_t m = 0;
+        for (int b = 0; b < 4; b++)
+            if (4 * q + b < n) m |= 0xffu << (8 * b);
+        return m;
+    };
+    va.mask_a = word_mask(nw - 2);
+    va.mask_b = word_mask(nw - 1);
+    va.res_words = (!prm->thr_absolute || prm->background == CHB_BG_AVERAGE) ? 2 : 1;
+    const int smem = video_smem_bytes(st->C, va.res_words);
+    VideoKernel kern = st->C == 3 ? video_kernel_for<3>(nw) : video_kernel_for<4>(nw);
+    if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
+    st->last_tables.clear();  // the fade table on the devices no longer belongs to a single-window call
+
+    // chunks of whole 16-start blocks; two slots of output planes per band (kernel of chunk k+1 overlaps the D2H of chunk k)
+    size_t max_frame_bytes = 0;
+    for (Band& b : st->bands) max_frame_bytes = std::max(max_frame_bytes, b.frame_bytes);
+    const int blocks_per_chunk = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)4 << 30) / (64 * max_frame_bytes)));
+    const int chunk_windows = blocks_per_chunk * kVideoBlock;
+    const int blk_first = first_start / kVideoBlock, blk_last = (first_start + n_windows - 1) / kVideoBlock;
+    const int n_chunks = (blk_last - blk_first + blocks_per_chunk) / blocks_per_chunk;
+    const size_t P = (size_t)st->W * st->H;
+
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        if (b.v_cap_windows < chunk_windows) {
+            for (int s = 0; s < 2; s++) {
+                cudaFree(b.d_vout[s]); cudaFree(b.d_vmask[s]);
+                b.d_vout[s] = b.d_vmask[s] = nullptr;
+                CU(cudaMalloc(&b.d_vout[s], b.frame_bytes * (size_t)chunk_windows));
+                CU(cudaMalloc(&b.d_vmask[s], b.frame_bytes * (size_t)chunk_windows));
+                if (!b.v_done[s]) CU(cudaEventCreateWithFlags(&b.v_done[s], cudaEventDisableTiming));
+                if (!b.v_copied[s]) CU(cudaEventCreateWithFlags(&b.v_copied[s], cudaEventDisableTiming));
+            }
+            b.v_cap_windows = chunk_windows;
+        }
+        if (b.vwarn_cap < n_windows) {
+            cudaFree(b.d_vwarn);
+            b.d_vwarn = nullptr;
+            CU(cudaMalloc(&b.d_vwarn, sizeof(unsigned long long) * (size_t)n_windows));
+            b.vwarn_cap = n_windows;
+        }
+        cudaStream_t s = d.compute;
+        if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
+        CU(cudaMemsetAsync(b.d_vwarn, 0, sizeof(unsigned long long) * (size_t)n_windows, s));
+        CU(cudaEventRecord(b.ev0, s));
+    }
+    std::vector<bool> slot_in_flight(2 * st->bands.size(), false);
+    for (int k = 0; k < n_chunks; k++) {
+        const int slot = k & 1;
+        const int cb0 = blk_first + k * blocks_per_chunk;
+        const int cb1 = std::min(blk_last, cb0 + blocks_per_chunk - 1);
+        const int s_lo = std::max(first_start, cb0 * kVideoBlock);                       // first window start of this chunk
+        const int s_hi = std::min(first_start + n_windows - 1, cb1 * kVideoBlock + kVideoBlock - 1);
+        const int w_lo = s_lo - first_start, cw = s_hi - s_lo + 1;
+        for (size_t bi = 0; bi < st->bands.size(); bi++) {
+            Band& b = st->bands[bi];
+            Dev& d = st->ctx->devs[b.dev_slot];
+            CU(cudaSetDevice(d.id));
+            cudaStream_t s = d.compute;
+            if (slot_in_flight[2 * bi + slot]) CU(cudaStreamWaitEvent(s, b.v_copied[slot], 0));  // the slot's previous planes have left
+            VideoArgs vb = va;
+            vb.o.stack = b.d_stack;
+            vb.o.n_pixels = b.n_pixels; vb.o.n_tiles = b.n_tiles;
+            vb.o.fade.values = b.d_fade;
+            vb.o.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
+            vb.o.counters = b.d_counters;
+            vb.first_start = s_lo; vb.n_windows = cw;
+            vb.blk0 = cb0; vb.n_blocks = cb1 - cb0 + 1;
+            vb.out_stride = (long long)b.frame_bytes;
+            vb.out_images = b.d_vout[slot];
+            vb.out_masks = want_mask ? b.d_vmask[slot] : nullptr;
+            vb.win_warnings = b.d_vwarn + w_lo;
+            const long long n_tasks = b.n_tiles * vb.n_blocks;
+            if (n_tasks >= (1LL << 31)) return fail(CHB_ERR_UNSUPPORTED, "chb_outlier_video: band too large (%lld tasks)", n_tasks);
+            int occ = 1;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kVideoWarps * 32, smem));
+            const int blocks = grid_for(n_tasks * 32, kVideoWarps * 32, d.sm_count, std::max(1, occ));
+            kern<<<blocks, kVideoWarps * 32, smem, s>>>(vb);
+            g_launches++;
+            CU(cudaGetLastError());
+            if (out_images) {
+                CU(cudaEventRecord(b.v_done[slot], s));
+                CU(cudaStreamWaitEvent(d.copy, b.v_done[slot], 0));
+                const size_t off = ((size_t)w_lo * P + (size_t)b.row0 * st->W) * st->C;
+                CU(cudaMemcpy2DAsync(out_images + off, P * st->C, b.d_vout[slot], b.frame_bytes, b.frame_bytes, (size_t)cw, cudaMemcpyDeviceToHost, d.copy));
+                if (out_masks)
+                    CU(cudaMemcpy2DAsync(out_masks + off, P * st->C, b.d_vmask[slot], b.frame_bytes, b.frame_bytes, (size_t)cw, cudaMemcpyDeviceToHost, d.copy));
+                CU(cudaEventRecord(b.v_copied[slot], d.copy));
+                slot_in_flight[2 * bi + slot] = true;
+            }
+        }
+    }
+    float ms_max = 0.0f;
+    uint64_t slow = 0, hard = 0, warn_total = 0;
+    std::vector<unsigned long long> wtmp((size_t)n_windows);
+    if (warnings) memset(warnings, 0, sizeof(uint64_t) * (size_t)n_windows);
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        CU(cudaSetDevice(d.id));
+        CU(cudaEventRecord(b.ev1, d.compute));
+        CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, d.compute));
+        CU(cudaStreamSynchronize(d.compute));
+        CU(cudaStreamSynchronize(d.copy));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
+        ms_max = std::max(ms_max, ms);
+        slow += st->h_counters[4 * b.dev_slot + 1];
+        hard += st->h_counters[4 * b.dev_slot + 2];
+        CU(cudaMemcpy(wtmp.data(), b.d_vwarn, sizeof(unsigned long long) * (size_t)n_windows, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n_windows; i++) {
+            warn_total += wtmp[i];
+            if (warnings) warnings[i] += wtmp[i];
+        }
+    }
+    if (kernel_ms) *kernel_ms = ms_max;
+    st->last_warnings = warn_total;
+    g_last_slow = slow;
+    g_last_hard = hard;
+    return CHB_OK;
+}
+
+extern "C" int chb_outlier_video(chb_stack* st, const chb_outlier_params* prm, int first_start, int window_len, int n_windows, uint8_t* out_images,
+                                 uint8_t* out_masks, uint64_t* n_warnings) {
+    if (!st || !out_images) return fail(CHB_ERR_INVALID, "chb_outlier_video: null argument");
+    int rc = chb_stack_sync(st);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    return video_impl(st, prm, first_start, window_len, n_windows, out_images, out_masks, out_masks != nullptr, n_warnings, nullptr);
+}
+extern "C" int chb_outlier_video_device(chb_stack* st, const chb_outlier_params* prm, int first_start, int window_len, int n_windows, int want_mask,
+                                        float* kernel_ms) {
+    if (!st) return fail(CHB_ERR_INVALID, "chb_outlier_video_device: null stack");
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    return video_impl(st, prm, first_start, window_len, n_windows, nullptr, nullptr, want_mask != 0, nullptr, kernel_ms);
 }
 
 // ------------------------------------------------------------------------------------------------ K2 dispatch

@@ -441,8 +441,11 @@ __device__ __forceinline__ void blend_into_f32_u8(float (&pa)[4], const uint8_t 
 // `active` lanes hold a pixel; inactive lanes run along (uniform loops) and their results are discarded.
 __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const PixelSrc& src, unsigned long long pixel_id,
                                                const float (&median)[4], const float (&iqr_inv)[4], const uint32_t (&band_sum)[4],
-                                               uint8_t (&pixel)[4], int& n_out, int& warn) {
+                                               uint8_t (&pixel)[4], int& n_out, int& warn, int contig_f0, int frame_offset) {
+    // contig_f0 / frame_offset: OutlierArgs' values for a single-window launch; per lane in the chrono-video kernel,
+    // where the pixels of one batch belong to different windows
     const int n = a.n, C = a.C;
+    auto frame_at = [&](int s) { return contig_f0 >= 0 ? contig_f0 + s : __ldg(a.win_frames + s); };
     const float thr_sq = a.thr_sq;
     DistCtx dc;
     make_dist_ctx(a, median, iqr_inv, dc);
@@ -470,10 +473,10 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
             first_non = s;
         }
     };
-    if (a.contig_f0 >= 0) {  // contiguous window: position s is frame contig_f0 + s; aligned words are pre-tested four frames at a time
+    if (contig_f0 >= 0) {  // contiguous window: position s is frame contig_f0 + s; aligned words are pre-tested four frames at a time
         int s = 0;
         while (s < n) {
-            const int f = a.contig_f0 + s;
+            const int f = contig_f0 + s;
             if ((f & 3) == 0 && s + 4 <= n) {
                 uint32_t xw[4];
                 rd.fetch_word(f, xw);
@@ -501,7 +504,7 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         }
     } else {
         for (int s = 0; s < n; s++) {
-            rd.fetch(__ldg(a.win_frames + s), px);
+            rd.fetch(frame_at(s), px);
             visit(s, dist_sq_px(dc, px));
         }
     }
@@ -545,18 +548,18 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
                 const int r = (int)rng_range(a.seed, pixel_id, 0, (uint32_t)(n - k));
                 uint8_t tmp[4] = {0, 0, 0, 0};
                 idx = r;
-                rd.fetch(__ldg(a.win_frames + r), tmp);
+                rd.fetch(frame_at(r), tmp);
                 if (dist_sq_px(dc, tmp) >= thr_sq) {
                     int order = 0;  // number of outliers before r
                     for (int s = 0; s < r; s++) {
-                        rd.fetch(__ldg(a.win_frames + s), tmp);
+                        rd.fetch(frame_at(s), tmp);
                         if (dist_sq_px(dc, tmp) >= thr_sq) order++;
                     }
                     idx = n - 1 - order;
                 }
             }
         }
-        const int f = __ldg(a.win_frames + idx);
+        const int f = frame_at(idx);
 #pragma unroll
         for (int i = 0; i < 4; i++)
             if (i < C) pixel[i] = src.at(f, i);
@@ -566,11 +569,11 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
 
     uint8_t sample[4] = {0, 0, 0, 0};
     if (k == 1) {  // src/chrono.rs:379-388
-        const int f = __ldg(a.win_frames + first_idx);
+        const int f = frame_at(first_idx);
 #pragma unroll
         for (int i = 0; i < 4; i++)
             if (i < C) sample[i] = src.at(f, i);
-        const float fade = fade_for(a.fade, first_idx, n, a.frame_offset);
+        const float fade = fade_for(a.fade, first_idx, n, frame_offset);
         const float blend = fade * blend_value(a, sqrtf(first_d));
         blend_into_u8(pixel, sample, C, blend);
         return sat_u8(roundf(blend * 255.0f));
@@ -582,11 +585,11 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         // only the span [first_idx, last_idx] holds outliers; in a contiguous window whole words without a candidate are skipped
         for (int ss = first_idx; ss <= last_idx; ss++) {
             const int s = (a.om == 4) ? ss : last_idx - (ss - first_idx);
-            const int f = a.contig_f0 >= 0 ? a.contig_f0 + s : __ldg(a.win_frames + s);
-            if (a.contig_f0 >= 0) {
+            const int f = frame_at(s);
+            if (contig_f0 >= 0) {
                 const int wf = f & ~3;  // word of this frame; when entering a word from its far end, test it once
                 const bool entering = (a.om == 4) ? ((f & 3) == 0) : ((f & 3) == 3);
-                if (entering && wf - a.contig_f0 >= first_idx && wf + 3 - a.contig_f0 <= last_idx) {
+                if (entering && wf - contig_f0 >= first_idx && wf + 3 - contig_f0 <= last_idx) {
                     uint32_t xw[4];
                     rd.fetch_word(wf, xw);
                     if (may_exceed(ws, xw) == 0) { ss += 3; continue; }
@@ -595,7 +598,7 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
             rd.fetch(f, sample);
             const float d = dist_sq_px(dc, sample);
             if (d >= thr_sq) {
-                const float fade = fade_for(a.fade, s, n, a.frame_offset);
+                const float fade = fade_for(a.fade, s, n, frame_offset);
                 const float blend = fade * blend_value(a, sqrtf(d));
                 blend_into_f32_u8(pix_new, sample, C, blend);
                 blend_inv *= 1.0f - blend;
@@ -619,13 +622,13 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         if (a.om == 0) { sidx = first_idx; dsq = first_d; }
         else if (a.om == 1) { sidx = last_idx; dsq = last_d; }
         else { sidx = max_index; dsq = max_dist_sq; }
-        const int f = __ldg(a.win_frames + sidx);
+        const int f = frame_at(sidx);
 #pragma unroll
         for (int i = 0; i < 4; i++)
             if (i < C) sample[i] = src.at(f, i);
         dist = sqrtf(dsq);
     }
-    const float fade = fade_for(a.fade, sidx, n, a.frame_offset);  // src/chrono.rs:485-488
+    const float fade = fade_for(a.fade, sidx, n, frame_offset);  // src/chrono.rs:485-488
     const float blend = fade * blend_value(a, dist);
     blend_into_u8(pixel, sample, C, blend);
     return sat_u8(roundf(blend * 255.0f));
@@ -763,7 +766,7 @@ __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry*
     const PixelSrc src{a.stack + tile * tile_bytes(C, a.NG), a.NG, C, (int)(e.pix & 31)};
     uint8_t pixel[4] = {0, 0, 0, 0};
     int n_out = 0, warn = 0;
-    const uint8_t mask = exact_pixel(a, src, a.pixel_offset + (unsigned long long)e.pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn);
+    const uint8_t mask = exact_pixel(a, src, a.pixel_offset + (unsigned long long)e.pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn, a.contig_f0, a.frame_offset);
     if (active) {
         store_pixel<C>(a, e.pix, pixel, mask);
         if (a.dbg_nout) a.dbg_nout[e.pix] = n_out;
@@ -1109,6 +1112,383 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     if (hcount > 0) drain_hard<C, WPL, G, MODE>(a, hq, hcount, lane, cap, pad, queue, qcount, acc_slot);
     __syncwarp();
     if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
+}
+
+// ------------------------------------------------------------------------------------------------ K3 chrono-video
+// create_video (src/main.rs:230-331) composites one window per output frame; the windows of a `--video-in a/b/1` run have
+// the same length and start one frame apart. One launch composites a whole run of such windows: a warp takes a tile and a
+// block of 16 consecutive window starts and loads the frame groups those windows span ONCE (lane = pixel). Phase 1 goes
+// band by band with the band's bytes in registers: 16 packed counts #{x <= p + k} around the median summarise the window
+// and are updated incrementally as it slides (see "sliding counts" below); median pair, quartiles and the smallest /
+// largest sample -- hence the exact certificate term max |x - centre| -- are read off the counts. Counts are rebuilt from
+// scratch (VABSDIFF4 F evaluations) at the start of a block and, after the iterative solver, for pixels whose order
+// statistics left the counted values. Per (window, band) results are parked in shared memory. Phase 2 goes window by
+// window: certificate, background pixel, or the exact-path queue (exact_pixel, 32 queued pixel-windows at a time).
+constexpr int kVideoWarps = 4;
+constexpr int kVideoQueueCap = 64;
+constexpr int kVideoBlock = 16;  // window starts per task
+struct VideoArgs {
+    OutlierArgs o;            // what every window shares: n, ranks, thresholds, weights, policies, fade, seed, stack, counters
+    int first_start;          // window i covers frames [first_start + i, first_start + i + o.n)
+    int n_windows;
+    int blk0, n_blocks;       // blocks of 16 starts: block b holds starts [16 * (blk0 + b), 16 * (blk0 + b) + 16)
+    int res_words;            // result words per band and window: 1, or 2 when sums / inter-quartile ranges are needed
+    long long out_stride;     // bytes between the planes of consecutive windows
+    uint8_t* out_images;      // [n_windows][n_pixels * C]
+    uint8_t* out_masks;       // may be null
+    unsigned long long* win_warnings;  // [n_windows] all-outlier pixels per window
+    uint32_t mask_a, mask_b;  // byte masks of window words NW-2 and NW-1 (0xFF = position < n)
+};
+struct VideoQueueEntry {
+    long long pix;
+    int win, unused;
+    float median[4];
+    float iqr_inv[4];
+    uint32_t sum[4];
+};
+__host__ __device__ constexpr int video_smem_bytes(int C, int res_words) {
+    return kVideoWarps * kVideoQueueCap * (int)sizeof(VideoQueueEntry) + kVideoBlock * C * res_words * kVideoWarps * 32 * 4;
+}
+
+template <int NW>
+__device__ __noinline__ void video_solve(const uint32_t* xl, int guess, const OutlierArgs& a, int pad, int& med2, int& iq4) {
+    uint32_t x[NW];
+#pragma unroll
+    for (int q = 0; q < NW; q++) x[q] = xl[q];
+    BandRanks r;
+    band_solve<NW, 1>(x, (uint32_t)(guess * a.n_sub), a.inv_n_sub, a, pad, 4 * NW, r);  // the solver only derives its first guess from the sum
+    med2 = r.mlo + r.mhi;
+    iq4 = 0;
+    if (!a.absolute) {  // quartiles (src/chrono.rs:559-579) are multiples of 1/4: 4 * (q3 - q1) is an exact integer
+        const float q1 = (a.rk[0] == a.rk[1]) ? (float)r.q1a : (1.0f - a.q1_frac) * (float)r.q1a + a.q1_frac * (float)r.q1b;
+        const float q3 = (a.rk[4] == a.rk[5]) ? (float)r.q3a : (1.0f - a.q3_frac) * (float)r.q3a + a.q3_frac * (float)r.q3b;
+        iq4 = __float2int_rn((q3 - q1) * 4.0f);
+    }
+}
+// 1 / IQR from 4 * IQR (src/chrono.rs:246-252: an IQR of zero counts as one)
+__device__ __forceinline__ float iqr_inv_of(int iq4) { return iq4 == 0 ? 1.0f : 1.0f / ((float)iq4 * 0.25f); }
+
+// ---- sliding counts. A band's window is summarised by 16 counts cn_k = #{x <= p + k}, k = 0..15, packed one per byte in
+// four words (window lengths <= 64 fit a byte). Sliding the window by one frame adds the entering sample's and removes the
+// leaving sample's "<=" indicator -- a few integer instructions instead of a pass over the window -- and every order
+// statistic whose value lies in [p + 1, p + 15] is read off the counts: d[r] = p + #{k : cn_k <= r}.
+struct VideoCounts {
+    uint32_t c0, c1, c2, c3;
+    int p;
+};
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int s) {  // shifts of 32 and more give 0
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+}
+// byte k of word j = 1 iff x <= p + 4j + k
+__device__ __forceinline__ void le_masks(int x, int p, uint32_t (&m)[4]) {
+    const int d8 = (x - p) * 8;
+    m[0] = shl_clamp(0x01010101u, max(d8, 0));
+    m[1] = shl_clamp(0x01010101u, __viaddmax_s32(d8, -32, 0));
+    m[2] = shl_clamp(0x01010101u, __viaddmax_s32(d8, -64, 0));
+    m[3] = shl_clamp(0x01010101u, __viaddmax_s32(d8, -96, 0));
+}
+// p + #{k : cn_k <= r} with kk = rep4(127 - r): adding 127 - r sets bit 7 of a count byte iff the count exceeds r
+__device__ __forceinline__ int stat_at(const VideoCounts& v, uint32_t kk) {
+    uint32_t acc = __dp4a((v.c0 + kk) & 0x80808080u, 0x01010101u, 0u);
+    acc = __dp4a((v.c1 + kk) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a((v.c2 + kk) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a((v.c3 + kk) & 0x80808080u, 0x01010101u, acc);
+    return v.p + 16 - (int)(acc >> 7);
+}
+// Counts from scratch around `center`: F at the 17 values p .. p + 16 (VABSDIFF4.ACC), cn_k = (F(p+k+1) - F(p+k) + cap) / 2
+// minus the zero bytes that pad the window words.
+template <int NW>
+__device__ __noinline__ VideoCounts video_recount(const uint32_t* xl, int center, int n) {
+    uint32_t x[NW];
+#pragma unroll
+    for (int q = 0; q < NW; q++) x[q] = xl[q];
+    int p = center - 8;
+    p = p < 0 ? 0 : (p > 240 ? 240 : p);
+    uint32_t f[17], cc[17];
+#pragma unroll
+    for (int k = 0; k < 17; k++) { cc[k] = rep4(min(p + k, 255)); f[k] = 0; }
+#pragma unroll
+    for (int q = 0; q < NW; q++) {
+#pragma unroll
+        for (int k = 0; k < 17; k++) f[k] = sad4_acc(x[q], cc[k], f[k]);
+    }
+    constexpr int cap = 4 * NW;
+    const int pad = cap - n;
+    uint32_t cn[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        cn[k] = (uint32_t)((((int)f[k + 1] - (int)f[k] + cap) >> 1) - pad);
+        if (p + k >= 255) cn[k] = (uint32_t)n;  // F(256) does not exist: every byte is <= 255
+    }
+    VideoCounts r;
+    r.p = p;
+    r.c0 = cn[0] | (cn[1] << 8) | (cn[2] << 16) | (cn[3] << 24);
+    r.c1 = cn[4] | (cn[5] << 8) | (cn[6] << 16) | (cn[7] << 24);
+    r.c2 = cn[8] | (cn[9] << 8) | (cn[10] << 16) | (cn[11] << 24);
+    r.c3 = cn[12] | (cn[13] << 8) | (cn[14] << 16) | (cn[15] << 24);
+    return r;
+}
+
+template <int C>
+__device__ __noinline__ void drain_video_queue(const VideoArgs& v, const VideoQueueEntry* q, int count, int lane) {
+    const OutlierArgs& a = v.o;
+    const bool active = lane < count;
+    const VideoQueueEntry e = q[active ? lane : 0];
+    const PixelSrc src{a.stack + (e.pix >> 5) * tile_bytes(C, a.NG), a.NG, C, (int)(e.pix & 31)};
+    const int f0 = v.first_start + e.win;  // frame of window position 0 = the window's frame_offset (src/chrono.rs:102-103)
+    uint8_t pixel[4] = {0, 0, 0, 0};
+    int n_out = 0, warn = 0;
+    const uint8_t mask = exact_pixel(a, src, a.pixel_offset + (unsigned long long)e.pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn, f0, f0);
+    if (active) {
+        uint8_t* oi = v.out_images + (long long)e.win * v.out_stride + e.pix * C;
+#pragma unroll
+        for (int c = 0; c < C; c++) oi[c] = pixel[c];
+        if (v.out_masks) {
+            uint8_t* om = v.out_masks + (long long)e.win * v.out_stride + e.pix * C;
+#pragma unroll
+            for (int c = 0; c < C; c++) om[c] = (c < 3) ? mask : 255;  // src/chrono.rs:183-191
+        }
+        if (warn) atomicAdd(v.win_warnings + e.win, 1ULL);
+    }
+    if (lane == 0) atomicAdd(a.counters + 1, (unsigned long long)count);
+}
+
+// Result word 0 of a (window, band): bits 0-8 mlo + mhi (twice the median), 9-16 max |x - centre|, 17-24 the byte of
+// window position 0. Word 1 (when present): bits 0-13 band sum, 14-23 4 * IQR.
+template <int C, int NW>
+__global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid_constant__ VideoArgs v) {
+    constexpr int KG = (NW + 3) / 4 + 1;  // frame groups a block of 16 starts spans
+    constexpr int NWL = 4 * KG;           // words per lane
+    constexpr int kThreads = kVideoWarps * 32;
+    const OutlierArgs& a = v.o;
+    extern __shared__ __align__(16) uint8_t vsm[];
+    const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    VideoQueueEntry* const queue = reinterpret_cast<VideoQueueEntry*>(vsm) + warp_in_cta * kVideoQueueCap;
+    uint32_t* const res = reinterpret_cast<uint32_t*>(vsm + kVideoWarps * kVideoQueueCap * sizeof(VideoQueueEntry)) + threadIdx.x;
+    const int rw = v.res_words;
+    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n_tasks = (int)a.n_tiles * v.n_blocks;  // the host keeps this below 2^31
+    constexpr int cap = 4 * NW;
+    const int n = a.n;
+    const int pad = cap - n;
+    const bool rel = !a.absolute;
+    // rank constants of stat_at(): median pair, quartile pairs, smallest and largest sample
+    const uint32_t kk_m1 = rep4(127 - a.rk[2]), kk_m2 = rep4(127 - a.rk[3]);
+    const uint32_t kk_q1a = rep4(127 - a.rk[0]), kk_q1b = rep4(127 - a.rk[1]), kk_q3a = rep4(127 - a.rk[4]), kk_q3b = rep4(127 - a.rk[5]);
+    const uint32_t kk_min = rep4(127), kk_max = rep4(127 - (n - 1));
+    const int r_lo = rel ? a.rk[0] : a.rk[2], r_hi = rel ? a.rk[5] : a.rk[3];  // smallest / largest rank a band needs
+    int qcount = 0;
+    for (int task = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); task < n_tasks; task += n_warps) {
+        const int tile = task / v.n_blocks;
+        const int blk = v.blk0 + task % v.n_blocks;
+        const long long pix = (long long)tile * kTilePixels + lane;
+        const bool owner = pix < a.n_pixels;
+        const uint8_t* tb = a.stack + (long long)tile * tile_bytes(C, a.NG) + lane * kUnitBytes;
+        const int i_lo = max(0, v.first_start - blk * kVideoBlock);                            // windows of this block that belong to the run
+        const int i_hi = min(kVideoBlock, v.first_start + v.n_windows - blk * kVideoBlock);
+        // ---- phase 1, band by band: the band's bytes in registers, the window slides over them
+#pragma unroll 1
+        for (int c = 0; c < C; c++) {
+            uint32_t A[NWL];
+#pragma unroll
+            for (int k = 0; k < KG; k++) {
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (blk + k < a.NG) u = ldg_stream(tb + ((long long)c * a.NG + (blk + k)) * (kTilePixels * kUnitBytes));
+                A[4 * k] = u.x; A[4 * k + 1] = u.y; A[4 * k + 2] = u.z; A[4 * k + 3] = u.w;
+            }
+            for (int r = 0; r < (i_lo >> 2); r++) {  // skip the words in front of the first window of the run
+#pragma unroll
+                for (int q = 0; q < NWL - 1; q++) A[q] = A[q + 1];
+                A[NWL - 1] = 0;
+            }
+            const float w = a.w[c];
+            const bool stats = (w != 0.0f);
+            VideoCounts cn = {0, 0, 0, 0, 0};
+            uint32_t bsum = 0;
+            bool fresh = true;
+#pragma unroll 1
+            for (int i = i_lo; i < i_hi; i++) {
+                const int bo = i & 3;  // byte of A[0] the window starts at
+                auto build_x = [&](uint32_t (&X)[NW]) {  // the window's words, positions >= n zeroed
+#pragma unroll
+                    for (int q = 0; q < NW; q++) X[q] = __funnelshift_r(A[q], A[q + 1], 8 * bo);
+                    X[NW - 2] &= v.mask_a;
+                    X[NW - 1] &= v.mask_b;
+                };
+                const uint32_t x_first = __byte_perm(A[0], 0, 0x4440 + bo);
+                if (fresh) {  // first window of the block: sum and counts from scratch
+                    fresh = false;
+                    if (a.bg == 2 || stats) {
+                        uint32_t X[NW];
+                        build_x(X);
+                        uint32_t s0 = 0, s1 = 0;
+#pragma unroll
+                        for (int q = 0; q < NW; q += 2) { s0 = __dp4a(X[q], 0x01010101u, s0); s1 = __dp4a(X[q + 1], 0x01010101u, s1); }
+                        bsum = s0 + s1;
+                        if (stats) {
+                            uint32_t tmp[NW];
+#pragma unroll
+                            for (int q = 0; q < NW; q++) tmp[q] = X[q];
+                            cn = video_recount<NW>(tmp, __float2int_rn((float)bsum * a.inv_n_sub), n);
+                        }
+                    }
+                }
+                int med2 = 0, iq4 = 0;
+                uint32_t odev = 0;
+                if (stats) {
+                    // every rank the band needs must resolve inside the counted values (the byte-range ends count as known)
+                    bool ok = ((int)(cn.c0 & 0xffu) <= r_lo || cn.p == 0) && ((int)(cn.c3 >> 24) > r_hi);
+                    bool solved = false;
+                    const unsigned nb = __ballot_sync(0xffffffffu, !ok && owner);
+                    if (nb) {  // iterative solver, then counts around the exact median; the whole warp together
+                        if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(nb));
+                        uint32_t tmp[NW];
+                        build_x(tmp);
+                        int m2 = 0, i4 = 0;
+                        video_solve<NW>(tmp, min(cn.p + 8, 254), a, pad, m2, i4);
+                        const VideoCounts rc = video_recount<NW>(tmp, m2 >> 1, n);
+                        if (!ok) { cn = rc; med2 = m2; iq4 = i4; solved = true; }
+                    }
+                    if (!solved) {
+                        const int mlo = stat_at(cn, kk_m1);
+                        const int mhi = (a.rk[2] == a.rk[3]) ? mlo : stat_at(cn, kk_m2);
+                        med2 = mlo + mhi;
+                        if (rel) {  // quartiles (src/chrono.rs:559-579)
+                            const int q1a = stat_at(cn, kk_q1a), q3a = stat_at(cn, kk_q3a);
+                            const int q1b = (a.rk[0] == a.rk[1]) ? q1a : stat_at(cn, kk_q1b);
+                            const int q3b = (a.rk[4] == a.rk[5]) ? q3a : stat_at(cn, kk_q3b);
+                            const float q1 = (a.rk[0] == a.rk[1]) ? (float)q1a : (1.0f - a.q1_frac) * (float)q1a + a.q1_frac * (float)q1b;
+                            const float q3 = (a.rk[4] == a.rk[5]) ? (float)q3a : (1.0f - a.q3_frac) * (float)q3a + a.q3_frac * (float)q3b;
+                            iq4 = __float2int_rn((q3 - q1) * 4.0f);
+                        }
+                    }
+                    if (!(w < 0.0f)) {  // max |x - centre| from the smallest and largest sample
+                        const int center = med2 >> 1;
+                        const bool in_range = ((cn.c0 & 0xffu) == 0u || cn.p == 0) && ((int)(cn.c3 >> 24) == n);
+                        const int minv = stat_at(cn, kk_min), maxv = stat_at(cn, kk_max);
+                        odev = (uint32_t)max(center - minv, maxv - center);
+                        const unsigned ob = __ballot_sync(0xffffffffu, !in_range && owner);
+                        if (ob) {
+                            if (__popc(ob) >= 3) {  // many pixels with samples beyond the counted values: scan the window
+                                uint32_t X[NW];
+                                build_x(X);
+                                const uint32_t cc = rep4(center);
+                                X[NW - 2] |= cc & ~v.mask_a;
+                                X[NW - 1] |= cc & ~v.mask_b;
+                                uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+                                for (int q = 0; q < NW; q += 2) {
+                                    const uint32_t d0 = absdiff4(X[q], cc), d1 = absdiff4(X[q + 1], cc);
+                                    m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);  // the high byte of each half is a byte-wise maximum
+                                    m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
+                                }
+                                const uint32_t m = __vmaxu2(m0, m1);
+                                if (!in_range) odev = max((m >> 8) & 0xffu, m >> 24);
+                            } else if (!in_range) {
+                                odev = 255;  // a few such pixels: they take the exact path (most of them hold an outlier anyway)
+                            }
+                        }
+                    }
+                }
+                uint32_t* r = res + ((i * C + c) * rw) * kThreads;
+                r[0] = (uint32_t)med2 | (odev << 9) | (x_first << 17);
+                if (rw > 1) r[kThreads] = bsum | ((uint32_t)iq4 << 14);
+                // ---- slide by one frame: the sample at window position n enters, position 0 leaves
+                if (i + 1 < i_hi) {
+                    const int pos = bo + n, wi = pos >> 2;  // NW - 2 <= wi <= NW
+                    const uint32_t wv = wi == NW - 2 ? A[NW - 2] : (wi == NW - 1 ? A[NW - 1] : A[NW]);
+                    const uint32_t x_in = __byte_perm(wv, 0, 0x4440 + (pos & 3));
+                    bsum += x_in - x_first;
+                    if (stats) {
+                        uint32_t mi[4], mo[4];
+                        le_masks((int)x_in, cn.p, mi);
+                        le_masks((int)x_first, cn.p, mo);
+                        cn.c0 += mi[0] - mo[0]; cn.c1 += mi[1] - mo[1]; cn.c2 += mi[2] - mo[2]; cn.c3 += mi[3] - mo[3];
+                    }
+                    if (bo == 3) {
+#pragma unroll
+                        for (int q = 0; q < NWL - 1; q++) A[q] = A[q + 1];
+                        A[NWL - 1] = 0;
+                    }
+                }
+            }
+        }
+        // ---- phase 2, window by window: certificate, background pixel or exact-path queue
+#pragma unroll 1
+        for (int i = i_lo; i < i_hi; i++) {
+            const int win = blk * kVideoBlock + i - v.first_start;
+            uint32_t r0[C], r1[C];
+            float bound = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const uint32_t* r = res + ((i * C + c) * rw) * kThreads;
+                r0[c] = r[0];
+                r1[c] = rw > 1 ? r[kThreads] : 0u;
+                const float w = a.w[c];
+                if (w != 0.0f && !(w < 0.0f)) {
+                    const float aw = a.absolute ? w : w * iqr_inv_of((int)(r1[c] >> 14));
+                    const float t = aw * ((float)((r0[c] >> 9) & 0xffu) + 0.5f * (float)(r0[c] & 1u));
+                    bound += t * t;
+                }
+            }
+            const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
+            if (owner && clean) {
+                uint8_t pixel[4] = {0, 0, 0, 0};
+                if (a.bg == 2) {
+#pragma unroll
+                    for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf((float)(r1[c] & 0x3fffu) / (float)n));  // src/chrono.rs:297-306,335-337
+                } else if (a.bg == 3) {
+#pragma unroll
+                    for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(0.5f * (float)(r0[c] & 0x1ffu)));  // :340-345
+                } else if (a.bg == 0) {
+#pragma unroll
+                    for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((r0[c] >> 17) & 0xffu);  // :348-350: window position 0
+                } else {
+                    const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)n);  // :357
+                    const PixelSrc src{a.stack + (long long)tile * tile_bytes(C, a.NG), a.NG, C, lane};
+#pragma unroll
+                    for (int c = 0; c < C; c++) pixel[c] = src.at(v.first_start + win + pos, c);
+                }
+                uint8_t* oi = v.out_images + (long long)win * v.out_stride + pix * C;
+#pragma unroll
+                for (int c = 0; c < C; c++) oi[c] = pixel[c];
+                if (v.out_masks) {
+                    uint8_t* om = v.out_masks + (long long)win * v.out_stride + pix * C;
+#pragma unroll
+                    for (int c = 0; c < C; c++) om[c] = (c < 3) ? 0 : 255;
+                }
+            }
+            const bool dirty = owner && !clean;
+            const unsigned db = __ballot_sync(0xffffffffu, dirty);
+            if (db) {
+                const int nd = __popc(db);
+                if (qcount + nd > kVideoQueueCap) {
+                    __syncwarp();
+                    while (qcount >= 32) { drain_video_queue<C>(v, queue + (qcount - 32), 32, lane); qcount -= 32; }
+                    __syncwarp();
+                }
+                if (dirty) {
+                    VideoQueueEntry& e = queue[qcount + __popc(db & ((1u << lane) - 1u))];
+                    e.pix = pix; e.win = win; e.unused = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t w0 = c < C ? r0[c < C ? c : 0] : 0u, w1 = c < C ? r1[c < C ? c : 0] : 0u;
+                        e.median[c] = 0.5f * (float)(w0 & 0x1ffu);
+                        e.iqr_inv[c] = (c < C && rel && a.w[c < C ? c : 0] != 0.0f) ? iqr_inv_of((int)(w1 >> 14)) : 0.0f;
+                        e.sum[c] = w1 & 0x3fffu;
+                    }
+                }
+                qcount += nd;
+                __syncwarp();
+                while (qcount >= 32) { drain_video_queue<C>(v, queue + (qcount - 32), 32, lane); qcount -= 32; }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    if (qcount > 0) drain_video_queue<C>(v, queue, qcount, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ K2

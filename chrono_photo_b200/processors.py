@@ -207,6 +207,63 @@ class OutlierProcessor:
         _lib.check(_lib.lib().chb_outlier_enqueue(stack._h, C.byref(p), ip, n, 1 if want_mask else 0))
 
 
+    # ---- chrono-video: runs of sliding windows (src/main.rs:254-331) ------------------------------------------------
+    MAX_VIDEO_WINDOW = 64
+
+    def process_video_run(self, stack, first_start, window_len, n_windows, want_mask=True):
+        """n_windows windows of window_len consecutive frames, window i = frames [first_start + i, ... + window_len):
+        one sliding-window launch sequence (chb_outlier_video). Returns (images, masks, warnings) with images / masks of
+        shape (n_windows, H, W, C)."""
+        shape = (n_windows, stack.height, stack.width, stack.channels)
+        out = np.empty(shape, dtype=np.uint8)
+        mask = np.empty(shape, dtype=np.uint8) if want_mask else None
+        warn = (C.c_uint64 * n_windows)()
+        p = self._params()
+        _lib.check(_lib.lib().chb_outlier_video(stack._h, C.byref(p), int(first_start), int(window_len), int(n_windows), C.c_void_p(out.ctypes.data),
+                                                C.c_void_p(mask.ctypes.data) if want_mask else None, warn))
+        return out, mask, [int(w) for w in warn]
+
+    def process_video_run_device(self, stack, first_start, window_len, n_windows, want_mask=True):
+        """Kernel-only variant of process_video_run: returns the device time of the run in ms."""
+        ms = C.c_float(0)
+        p = self._params()
+        _lib.check(_lib.lib().chb_outlier_video_device(stack._h, C.byref(p), int(first_start), int(window_len), int(n_windows),
+                                                       1 if want_mask else 0, C.byref(ms)))
+        return ms.value
+
+    def video_runs(self, windows):
+        """Splits create_video's window list [(number, indices)] into maximal runs the sliding kernel takes -- consecutive
+        windows of equal length <= MAX_VIDEO_WINDOW, each a contiguous frame range starting one frame after the previous
+        one -- and single windows. Returns [(first_position_in_windows, count)], count > 1 only for runs."""
+        def slidable(idx):
+            return (1 <= len(idx) <= self.MAX_VIDEO_WINDOW and idx[-1] - idx[0] + 1 == len(idx)
+                    and (self.sample_count is None or self.sample_count >= len(idx)))
+        runs, i = [], 0
+        while i < len(windows):
+            idx = windows[i][1]
+            j = i + 1
+            if slidable(idx):
+                while (j < len(windows) and len(windows[j][1]) == len(idx) and slidable(windows[j][1])
+                       and windows[j][1][0] == windows[j - 1][1][0] + 1):
+                    j += 1
+            runs.append((i, j - i))
+            i = j
+        return runs
+
+    def process_video(self, stack, windows, want_mask=True):
+        """Composites every window of `windows` (as returned by video_windows): runs through chb_outlier_video, the
+        remaining windows one by one through chb_outlier. Yields (number, image, mask, warnings) in window order."""
+        for pos, count in self.video_runs(windows):
+            if count > 1:
+                idx0 = windows[pos][1]
+                imgs, masks, warns = self.process_video_run(stack, idx0[0], len(idx0), count, want_mask)
+                for k in range(count):
+                    yield windows[pos + k][0], imgs[k], (masks[k] if want_mask else None), warns[k]
+            else:
+                img, mask = self.process(stack, windows[pos][1], want_mask=want_mask)
+                yield windows[pos][0], img, mask, self.warnings
+
+
 class SimpleProcessor:
     """SimpleProcessor::new(weights, fade, darker) (src/simple.rs:18)."""
 

@@ -161,6 +161,21 @@ int chb_fetch_last(chb_stack *stack, uint8_t *out_image, uint8_t *out_mask, uint
 int chb_outlier_enqueue(chb_stack *stack, const chb_outlier_params *params, const int32_t *indices, int n_indices, int want_mask);
 int chb_stack_wait(chb_stack *stack, float *last_kernel_ms, uint64_t *n_warnings);
 
+/* ---- chrono-video: a run of sliding windows in one call --------------------------------------------------------
+ * Replaces the per-output-frame loop of create_video (src/main.rs:254-331: one OutlierProcessor::process per frame of the
+ * video, each re-reading its window) for a run of n_windows windows of window_len consecutive frames, window i =
+ * frames [first_start + i, first_start + i + window_len) -- what `--video-in a/b/1` produces once the window has its
+ * full length (src/main.rs:262-286); frame_offset of window i is first_start + i (src/chrono.rs:102-103). Every frame
+ * group is loaded once per 16 windows and the window slides inside registers. out_images / out_masks (nullable) are
+ * [n_windows][H*W*C] planes; n_warnings (nullable) receives n_windows per-window counts. Limits: window_len <= 64 and no
+ * --sample below the window length (CHB_ERR_UNSUPPORTED: composite such windows one by one with chb_outlier). Results
+ * are identical to n_windows chb_outlier calls. */
+int chb_outlier_video(chb_stack *stack, const chb_outlier_params *params, int first_start, int window_len, int n_windows,
+                      uint8_t *out_images, uint8_t *out_masks, uint64_t *n_warnings);
+/* Same, results stay on the device(s); kernel_ms = device time of all launches of the run (max over devices). */
+int chb_outlier_video_device(chb_stack *stack, const chb_outlier_params *params, int first_start, int window_len,
+                             int n_windows, int want_mask, float *kernel_ms);
+
 /* Counters for bench.py: kernels launched by this library since the last reset (process-wide),
  * and, for the last outlier call on this thread, how many pixels left the certified fast path. */
 uint64_t chb_launch_count(void);

@@ -355,6 +355,97 @@ def test_config5_chrono_video_with_shake_crop(ctx):
     fs.close()
 
 
+# ---------------------------------------------------------------------------------------------------- chrono-video runs
+def _check_video_run(ctx, fs, st, first, wl, count, spec, bg, om, weights=(1, 1, 1, 1), fade=None, seed=5):
+    t_gpu, t_orc = thr_pair(spec)
+    f_gpu = cp.Fade(*fade) if fade else None
+    proc = cp.OutlierProcessor(t_gpu, BG[bg], OM[om], weights, f_gpu, None, None, seed=seed)
+    imgs, masks, warns = proc.process_video_run(fs, first, wl, count)
+    for k in range(count):
+        idx = list(range(first + k, first + k + wl))
+        oimg, omsk, owarn = orc.outlier(st, t_orc, BG[bg], OM[om], weights, orc.fade(*fade) if fade else None, idx, None, seed=seed)
+        tag = f"{spec} bg={bg} om={om} w={weights} window {idx[0]}..{idx[-1]}"
+        assert np.array_equal(masks[k], omsk), "mask " + tag
+        assert np.array_equal(imgs[k], oimg), "composite " + tag
+        assert warns[k] == owarn, "warnings " + tag
+
+
+@pytest.mark.parametrize("wl", [1, 2, 3, 5, 8, 9, 16, 17, 25, 32, 33, 48, 63, 64])
+def test_video_run_window_lengths(ctx, wl):
+    rng = np.random.default_rng(500 + wl)
+    n = wl + 37
+    st = make_stack(rng, n, 9, 41, 3, n_obj=30)
+    fs = upload(ctx, st)
+    _check_video_run(ctx, fs, st, 0, wl, n - wl + 1, (True, 0.05, 0.2), "first", "extreme")  # every window of the clip
+    if wl >= 3:
+        _check_video_run(ctx, fs, st, 3, wl, min(20, n - wl - 2), (False, 3.0, 5.0), "first", "forward")
+    fs.close()
+
+
+@pytest.mark.parametrize("bg", ["first", "random", "average", "median"])
+@pytest.mark.parametrize("om", ["first", "last", "extreme", "average", "forward", "backward"])
+def test_video_run_policies(ctx, bg, om):
+    rng = np.random.default_rng(77)
+    st = make_stack(rng, 60, 12, 37, 3, n_obj=40)
+    fs = upload(ctx, st)
+    fade = (0, True, [(0, 1.0), (30, 0.2)])
+    _check_video_run(ctx, fs, st, 5, 25, 30, (True, 0.05, 0.2), bg, om, fade=fade)
+    _check_video_run(ctx, fs, st, 17, 12, 19, (False, 2.0, 4.0), bg, om, weights=(1, 0.5, 0.5, 0))
+    fs.close()
+
+
+def test_video_run_adversarial_series(ctx):
+    rng = np.random.default_rng(99)
+    n, H, W = 70, 8, 64
+    uni = rng.integers(0, 256, size=(n, H, W, 3), dtype=np.uint8)          # iid bytes: every band takes the iterative solver
+    const = np.full((n, H, W, 3), 200, dtype=np.uint8)                      # IQR = 0
+    alt = np.where((np.arange(n) % 2 == 0)[:, None, None, None], 10, 250).astype(np.uint8) * np.ones((1, H, W, 3), np.uint8)
+    edge = rng.choice(np.array([0, 1, 254, 255], dtype=np.uint8), size=(n, H, W, 3))
+    for st in (uni, const, alt, edge):
+        fs = upload(ctx, st)
+        _check_video_run(ctx, fs, st, 0, 25, 40, (True, 0.05, 0.2), "first", "extreme")
+        _check_video_run(ctx, fs, st, 2, 26, 30, (False, 3.0, 5.0), "median", "backward")
+        _check_video_run(ctx, fs, st, 1, 7, 50, (True, 0.0, 0.2), "first", "average")  # threshold 0: all-outlier warnings
+        fs.close()
+
+
+def test_video_run_rgba_and_process_video_grouping(ctx):
+    rng = np.random.default_rng(31)
+    n = 48
+    st = make_stack(rng, n, 10, 33, 4, n_obj=30)
+    fs = upload(ctx, st)
+    _check_video_run(ctx, fs, st, 0, 10, 39, (True, 0.05, 0.2), "first", "extreme")
+    # create_video's windows for --video-in 0/9/1: a growing head (single calls) and a run of full-length windows
+    t_gpu, t_orc = thr_pair((True, 0.05, 0.2))
+    wins = cp.video_windows(n, cp.FrameRange(0, 9, 1), cp.FrameRange.empty())
+    proc = cp.OutlierProcessor(t_gpu, BG["first"], OM["extreme"])
+    runs = proc.video_runs(wins)
+    assert max(c for _, c in runs) > 20 and sum(c for _, c in runs) == len(wins)
+    seen = 0
+    for (number, img, msk, warn), (wnum, idx) in zip(proc.process_video(fs, wins), wins):
+        assert number == wnum
+        oimg, omsk, owarn = orc.outlier(st, t_orc, BG["first"], OM["extreme"], indices=idx)
+        assert np.array_equal(img, oimg) and np.array_equal(msk, omsk) and warn == owarn, idx
+        seen += 1
+    assert seen == len(wins)
+    fs.close()
+
+
+def test_video_run_error_paths(ctx):
+    from chrono_photo_b200._lib import ChbError
+    rng = np.random.default_rng(3)
+    st = make_stack(rng, 80, 4, 32, 3)
+    fs = upload(ctx, st)
+    proc = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2)
+    with pytest.raises(ChbError):
+        proc.process_video_run(fs, 0, 65, 2)       # window too long for the sliding kernel
+    with pytest.raises(ChbError):
+        proc.process_video_run(fs, 70, 10, 5)      # leaves the stack
+    with pytest.raises(ChbError):
+        cp.OutlierProcessor(cp.Threshold.rel(3.0, 5.0), 0, 2).process_video_run(fs, 0, 2, 5)  # rel needs 3 samples
+    fs.close()
+
+
 def test_concurrent_callers_like_the_rayon_video_pool(ctx):
     # create_video calls one processor per output frame from a rayon pool (src/main.rs:260-261); decode threads upload
     # distinct frames concurrently. The library must give every caller its own correct result.
