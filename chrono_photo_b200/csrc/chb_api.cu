@@ -84,6 +84,8 @@ struct Band {
     int v_cap_windows = 0;
     unsigned long long* d_vwarn = nullptr;
     int vwarn_cap = 0;
+    VideoQueueEntry* d_vqueue = nullptr;  // exact-path queue of a chunk + its counter
+    unsigned int* d_vqcount = nullptr;
     cudaEvent_t v_done[2] = {nullptr, nullptr};    // kernel writing slot s finished
     cudaEvent_t v_copied[2] = {nullptr, nullptr};  // D2H of slot s finished
 };
@@ -184,7 +186,7 @@ static void free_band(Band& b) {
         if (b.v_done[s]) cudaEventDestroy(b.v_done[s]);
         if (b.v_copied[s]) cudaEventDestroy(b.v_copied[s]);
     }
-    cudaFree(b.d_vwarn);
+    cudaFree(b.d_vwarn); cudaFree(b.d_vqueue); cudaFree(b.d_vqcount);
 }
 
 extern "C" int chb_stack_destroy(chb_stack* st) {
@@ -751,6 +753,7 @@ static VideoKernel video_kernel_for(int nw) {
     }
 }
 static constexpr int kMaxVideoWindow = 64;
+static constexpr unsigned int kVideoQueueEntries = 2u << 20;  // 128 MB; pixel-windows beyond it are finished inside video_kernel
 
 // A run of n_windows windows of window_len consecutive frames, window i starting at frame first_start + i (the windows
 // create_video builds for `--video-in a/b/1`, src/main.rs:262-286). Host outputs (may be null: results stay on the devices,
@@ -830,6 +833,10 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             }
             b.v_cap_windows = chunk_windows;
         }
+        if (!b.d_vqueue) {
+            CU(cudaMalloc(&b.d_vqueue, sizeof(VideoQueueEntry) * (size_t)kVideoQueueEntries));
+            CU(cudaMalloc(&b.d_vqcount, 2 * sizeof(unsigned int)));
+        }
         if (b.vwarn_cap < n_windows) {
             cudaFree(b.d_vwarn);
             b.d_vwarn = nullptr;
@@ -868,6 +875,11 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             vb.out_images = b.d_vout[slot];
             vb.out_masks = want_mask ? b.d_vmask[slot] : nullptr;
             vb.win_warnings = b.d_vwarn + w_lo;
+            vb.gq = b.d_vqueue; vb.gq_count = b.d_vqcount; vb.gq_cap = kVideoQueueEntries;
+            if (const char* qc = getenv("CHB_VIDEO_QUEUE_CAP"))  // test aid: a small capacity exercises the in-place fallback
+                vb.gq_cap = (unsigned int)std::min<long long>(kVideoQueueEntries, std::max<long long>(0, atoll(qc)));
+            CU(cudaMemsetAsync(b.d_vqcount, 0, sizeof(unsigned int), s));
+            CU(cudaMemsetAsync(b.d_vqcount + 1, 0xff, sizeof(unsigned int), s));
             const long long n_tasks = b.n_tiles * vb.n_blocks;
             if (n_tasks >= (1LL << 31)) return fail(CHB_ERR_UNSUPPORTED, "chb_outlier_video: band too large (%lld tasks)", n_tasks);
             int occ = 1;
@@ -876,7 +888,9 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kVideoWarps * 32, smem));
             const int blocks = grid_for(n_tasks * 32, kVideoWarps * 32, d.sm_count, std::max(1, occ));
             kern<<<blocks, kVideoWarps * 32, smem, s>>>(vb);
-            g_launches++;
+            if (st->C == 3) video_exact_kernel<3><<<d.sm_count * 8, 128, 0, s>>>(vb);
+            else video_exact_kernel<4><<<d.sm_count * 8, 128, 0, s>>>(vb);
+            g_launches += 2;
             CU(cudaGetLastError());
             if (out_images) {
                 CU(cudaEventRecord(b.v_done[slot], s));

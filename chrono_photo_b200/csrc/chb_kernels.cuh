@@ -1138,6 +1138,9 @@ struct VideoArgs {
     uint8_t* out_masks;       // may be null
     unsigned long long* win_warnings;  // [n_windows] all-outlier pixels per window
     uint32_t mask_a, mask_b;  // byte masks of window words NW-2 and NW-1 (0xFF = position < n)
+    struct VideoQueueEntry* gq;  // global exact-path queue of this launch, drained by video_exact_kernel
+    unsigned int* gq_count;   // [0] entries requested, [1] end of the entries that were written (first refused request)
+    unsigned int gq_cap;
 };
 struct VideoQueueEntry {
     long long pix;
@@ -1191,11 +1194,11 @@ __device__ __forceinline__ void le_masks(int x, int p, uint32_t (&m)[4]) {
 }
 // p + #{k : cn_k <= r} with kk = rep4(127 - r): adding 127 - r sets bit 7 of a count byte iff the count exceeds r
 __device__ __forceinline__ int stat_at(const VideoCounts& v, uint32_t kk) {
-    uint32_t acc = __dp4a((v.c0 + kk) & 0x80808080u, 0x01010101u, 0u);
-    acc = __dp4a((v.c1 + kk) & 0x80808080u, 0x01010101u, acc);
-    acc = __dp4a((v.c2 + kk) & 0x80808080u, 0x01010101u, acc);
-    acc = __dp4a((v.c3 + kk) & 0x80808080u, 0x01010101u, acc);
-    return v.p + 16 - (int)(acc >> 7);
+    uint32_t acc0 = __dp4a((v.c0 + kk) & 0x80808080u, 0x01010101u, 0u);
+    uint32_t acc1 = __dp4a((v.c1 + kk) & 0x80808080u, 0x01010101u, 0u);
+    acc0 = __dp4a((v.c2 + kk) & 0x80808080u, 0x01010101u, acc0);
+    acc1 = __dp4a((v.c3 + kk) & 0x80808080u, 0x01010101u, acc1);
+    return v.p + 16 - (int)((acc0 + acc1) >> 7);
 }
 // Counts from scratch around `center`: F at the 17 values p .. p + 16 (VABSDIFF4.ACC), cn_k = (F(p+k+1) - F(p+k) + cap) / 2
 // minus the zero bytes that pad the window words.
@@ -1253,6 +1256,44 @@ __device__ __noinline__ void drain_video_queue(const VideoArgs& v, const VideoQu
         if (warn) atomicAdd(v.win_warnings + e.win, 1ULL);
     }
     if (lane == 0) atomicAdd(a.counters + 1, (unsigned long long)count);
+}
+
+// Pixel-windows the certificate cannot clear go to the launch's global queue and are finished by video_exact_kernel, so
+// the (large) exact-path code stays out of video_kernel's instruction stream. Only when that queue is full does the warp
+// fall back to its own shared-memory queue and drain it in place. (Result words passed by value: no local memory.)
+template <int C>
+__device__ __noinline__ void video_enqueue(const VideoArgs& v, VideoQueueEntry* queue, int& qcount, int lane, unsigned db, bool dirty, long long pix,
+                                           int win, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    const OutlierArgs& a = v.o;
+    const int nd = __popc(db);
+    unsigned int gbase = 0;
+    if (lane == 0) gbase = atomicAdd(v.gq_count, (unsigned int)nd);
+    gbase = __shfl_sync(0xffffffffu, gbase, 0);
+    const bool to_global = gbase + (unsigned int)nd <= v.gq_cap;
+    if (!to_global && lane == 0) atomicMin(v.gq_count + 1, gbase);
+    if (!to_global && qcount + nd > kVideoQueueCap) {
+        __syncwarp();
+        while (qcount >= 32) { drain_video_queue<C>(v, queue + (qcount - 32), 32, lane); qcount -= 32; }
+        __syncwarp();
+    }
+    if (dirty) {
+        const int rank = __popc(db & ((1u << lane) - 1u));
+        VideoQueueEntry& e = to_global ? v.gq[gbase + rank] : queue[qcount + rank];
+        const uint32_t w0[4] = {a0, a1, a2, a3}, w1[4] = {b0, b1, b2, b3};
+        e.pix = pix; e.win = win; e.unused = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            e.median[c] = 0.5f * (float)(w0[c] & 0x1ffu);
+            e.iqr_inv[c] = (c < C && !a.absolute && a.w[c] != 0.0f) ? iqr_inv_of((int)(w1[c] >> 14)) : 0.0f;
+            e.sum[c] = w1[c] & 0x3fffu;
+        }
+    }
+    if (!to_global) {
+        qcount += nd;
+        __syncwarp();
+        while (qcount >= 32) { drain_video_queue<C>(v, queue + (qcount - 32), 32, lane); qcount -= 32; }
+        __syncwarp();
+    }
 }
 
 // Result word 0 of a (window, band): bits 0-8 mlo + mhi (twice the median), 9-16 max |x - centre|, 17-24 the byte of
@@ -1463,32 +1504,25 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
             const bool dirty = owner && !clean;
             const unsigned db = __ballot_sync(0xffffffffu, dirty);
             if (db) {
-                const int nd = __popc(db);
-                if (qcount + nd > kVideoQueueCap) {
-                    __syncwarp();
-                    while (qcount >= 32) { drain_video_queue<C>(v, queue + (qcount - 32), 32, lane); qcount -= 32; }
-                    __syncwarp();
-                }
-                if (dirty) {
-                    VideoQueueEntry& e = queue[qcount + __popc(db & ((1u << lane) - 1u))];
-                    e.pix = pix; e.win = win; e.unused = 0;
+                uint32_t w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
 #pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const uint32_t w0 = c < C ? r0[c < C ? c : 0] : 0u, w1 = c < C ? r1[c < C ? c : 0] : 0u;
-                        e.median[c] = 0.5f * (float)(w0 & 0x1ffu);
-                        e.iqr_inv[c] = (c < C && rel && a.w[c < C ? c : 0] != 0.0f) ? iqr_inv_of((int)(w1 >> 14)) : 0.0f;
-                        e.sum[c] = w1 & 0x3fffu;
-                    }
-                }
-                qcount += nd;
-                __syncwarp();
-                while (qcount >= 32) { drain_video_queue<C>(v, queue + (qcount - 32), 32, lane); qcount -= 32; }
-                __syncwarp();
+                for (int c = 0; c < C; c++) { w0[c] = r0[c]; w1[c] = r1[c]; }
+                video_enqueue<C>(v, queue, qcount, lane, db, dirty, pix, win, w0[0], w0[1], w0[2], w0[3], w1[0], w1[1], w1[2], w1[3]);
             }
         }
     }
     __syncwarp();
     if (qcount > 0) drain_video_queue<C>(v, queue, qcount, lane);
+}
+
+// Second launch of a chrono-video chunk: the queued pixel-windows, 32 per warp.
+template <int C>
+__global__ void __launch_bounds__(128) video_exact_kernel(const __grid_constant__ VideoArgs v) {
+    const unsigned int total = min(v.gq_count[0], v.gq_count[1]);  // requests that did not fit were finished in place
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < total; base += n_warps * 32u)
+        drain_video_queue<C>(v, v.gq + base, (int)min(32u, total - base), lane);
 }
 
 // ------------------------------------------------------------------------------------------------ K2

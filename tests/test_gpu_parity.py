@@ -409,6 +409,19 @@ def test_video_run_adversarial_series(ctx):
         fs.close()
 
 
+def test_video_run_exact_queue_overflow_falls_back_in_place(ctx, monkeypatch):
+    # pixel-windows the certificate cannot clear go to a global queue finished by a second kernel; when it is full the
+    # warps finish them in place. Threshold 0 makes every pixel-window take that path.
+    rng = np.random.default_rng(12)
+    st = make_stack(rng, 50, 16, 64, 3, n_obj=30)
+    fs = upload(ctx, st)
+    for cap in ("0", "37", "100000"):
+        monkeypatch.setenv("CHB_VIDEO_QUEUE_CAP", cap)
+        _check_video_run(ctx, fs, st, 0, 25, 26, (True, 0.0, 0.2), "first", "extreme")
+        _check_video_run(ctx, fs, st, 3, 9, 30, (True, 0.05, 0.2), "random", "forward")
+    fs.close()
+
+
 def test_video_run_rgba_and_process_video_grouping(ctx):
     rng = np.random.default_rng(31)
     n = 48
