@@ -228,15 +228,7 @@ public:
     }
     // -> (buffer, is_outlier); image_indices = the window of a video frame (src/chrono.rs:102-139)
     std::pair<std::vector<uint8_t>, std::vector<uint8_t>> process(const GpuStack& stack, const std::vector<int32_t>* image_indices = nullptr) {
-        chb_outlier_params p{};
-        p.thr_absolute = threshold_.absolute() ? 1 : 0;
-        p.background = (uint8_t)bg_;
-        p.outlier = (uint8_t)om_;
-        p.thr_min = threshold_.min(); p.thr_max = threshold_.max(); p.thr_scale = threshold_.scale();
-        for (int i = 0; i < 4; i++) p.weights[i] = w_[i];
-        p.fade = fade_.to_c();
-        p.sample_count = sample_ ? (int32_t)*sample_ : -1;
-        p.seed = seed_;
+        chb_outlier_params p = params();
         std::vector<uint8_t> buffer(stack.image_bytes()), is_outlier(stack.image_bytes());
         uint64_t warnings = 0;
         check(chb_outlier(stack.raw(), &p, image_indices ? image_indices->data() : nullptr, image_indices ? (int)image_indices->size() : 0,
@@ -246,7 +238,32 @@ public:
     }
     uint64_t warnings() const { return warnings_; }  // "pixels seem to consist of only outliers", src/chrono.rs:198-203
 
+    // chrono-video: n_windows windows of window_len consecutive frames, window i starting at frame first_start + i -- the
+    // per-frame loop of create_video (src/main.rs:254-331) in one call (chb_outlier_video). Planes are [n_windows][H*W*C].
+    static constexpr int kMaxVideoWindow = 64;
+    bool slidable(int window_len) const { return window_len >= 1 && window_len <= kMaxVideoWindow && (!sample_ || (int)*sample_ >= window_len); }
+    void process_video_run(const GpuStack& stack, int first_start, int window_len, int n_windows, std::vector<uint8_t>& buffers,
+                           std::vector<uint8_t>& is_outlier, std::vector<uint64_t>& warnings) {
+        chb_outlier_params p = params();
+        buffers.resize(stack.image_bytes() * (size_t)n_windows);
+        is_outlier.resize(stack.image_bytes() * (size_t)n_windows);
+        warnings.assign((size_t)n_windows, 0);
+        check(chb_outlier_video(stack.raw(), &p, first_start, window_len, n_windows, buffers.data(), is_outlier.data(), warnings.data()));
+    }
+
 private:
+    chb_outlier_params params() const {
+        chb_outlier_params p{};
+        p.thr_absolute = threshold_.absolute() ? 1 : 0;
+        p.background = (uint8_t)bg_;
+        p.outlier = (uint8_t)om_;
+        p.thr_min = threshold_.min(); p.thr_max = threshold_.max(); p.thr_scale = threshold_.scale();
+        for (int i = 0; i < 4; i++) p.weights[i] = w_[i];
+        p.fade = fade_.to_c();
+        p.sample_count = sample_ ? (int32_t)*sample_ : -1;
+        p.seed = seed_;
+        return p;
+    }
     Threshold threshold_;
     BackgroundMode bg_;
     OutlierSelectionMode om_;

@@ -77,3 +77,18 @@ def test_cli_photo_video_and_option_file(tmp_path):
         if ws[i] < we[i]:
             got = read_ppm(tmp_path / f"vid-{num[i]:05d}.ppm")
             assert np.array_equal(got, orc.simple(st, False, indices=list(range(ws[i], we[i]))))
+    # outlier video: --video-in 0/5/1 -> a growing head (single windows), then a run of 5-frame windows composited by the
+    # sliding-window kernel in one call (chb_outlier_video); every frame and blend mask equals the oracle's
+    p = run("--pattern", pat, "--output", str(tmp_path / "ov.ppm"), "--output-blend", str(tmp_path / "ob.ppm"), "--video-in", "0/5/1",
+            "-t", "abs/0.05/0.2", "-b", "first", "-l", "extreme")
+    assert p.returncode == 0, p.stderr
+    n, ws, we, num = orc.video_windows(14, (0, 5, 1), (None, None, 1))
+    checked = 0
+    for i in range(n):
+        if ws[i] < we[i]:
+            idx = list(range(ws[i], we[i]))
+            oimg, omsk, _ = orc.outlier(st, orc.threshold(True, 0.05, 0.2), BG["first"], OM["extreme"], indices=idx)
+            assert np.array_equal(read_ppm(tmp_path / f"ov-{num[i]:05d}.ppm"), oimg), idx
+            assert np.array_equal(read_ppm(tmp_path / f"ob-{num[i]:05d}.ppm"), omsk), idx
+            checked += 1
+    assert checked >= 10

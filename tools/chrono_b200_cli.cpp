@@ -193,18 +193,46 @@ int main(int argc, char** argv) {
             int n = chb_video_windows((int)files.size(), vin.start.has_value(), vin.start.value_or(0), vin.end.has_value(), vin.end.value_or(0), (int)vin.step,
                                       vout.start.has_value(), vout.start.value_or(0), vout.end.has_value(), vout.end.value_or(0), (int)vout.step, ws.data(),
                                       we.data(), num.data(), cap);
-            auto ne = name_and_extension(opt["--output"]);
             std::string dir = parent_of(opt["--output"]);
-            for (int i = 0; i < std::min(n, cap); i++) {
+            auto frame_name = [&](const std::string& base, int number) {
+                char nm[64];
+                snprintf(nm, sizeof nm, "-%05d.", number);
+                auto nb = name_and_extension(base);
+                return dir + "/" + nb.first + nm + nb.second;
+            };
+            const int nwin = std::min(n, cap);
+            for (int i = 0; i < nwin;) {
+                const int len = (we[i] - ws[i] + (int)vin.step - 1) / (int)vin.step;
+                if (len <= 0) { std::cout << "Skipping frame " << num[i] << "\n"; i++; continue; }
+                // a run of equal-length windows sliding by one frame goes through the sliding-window kernel in one call
+                int j = i + 1;
+                OutlierProcessor vproc(threshold, background, outlier, w, fade, sample, /*seed=*/0x9E3779B97F4A7C15ULL);
+                if (mode == SelectionMode::Outlier && vin.step == 1 && vproc.slidable(len))
+                    while (j < nwin && we[j] - ws[j] == len && ws[j] == ws[j - 1] + 1) j++;
+                if (j - i > 1) {
+                    std::vector<uint8_t> bufs, masks;
+                    std::vector<uint64_t> warns;
+                    vproc.process_video_run(stack, ws[i], len, j - i, bufs, masks, warns);
+                    const size_t fb = (size_t)first.w * first.h * 3;
+                    for (int k = i; k < j; k++) {
+                        std::cout << "Processing frame " << num[k] << " -> \n";
+                        if (warns[k - i] > 0) std::cout << "Warning: " << warns[k - i] << " pixels seem to consist of only outliers\n";
+                        write_ppm(frame_name(opt["--output"], num[k]), first.w, first.h,
+                                  std::vector<uint8_t>(bufs.begin() + (k - i) * fb, bufs.begin() + (k - i + 1) * fb));
+                        if (out_blend)
+                            write_ppm(frame_name(*out_blend, num[k]), first.w, first.h,
+                                      std::vector<uint8_t>(masks.begin() + (k - i) * fb, masks.begin() + (k - i + 1) * fb));
+                    }
+                    i = j;
+                    continue;
+                }
                 std::vector<int32_t> idx;
                 for (int f = ws[i]; f < we[i]; f += (int)vin.step) idx.push_back(f);
-                char nm[64];
-                snprintf(nm, sizeof nm, "-%05d.", num[i]);
-                if (idx.empty()) { std::cout << "Skipping frame " << num[i] << "\n"; continue; }
                 std::optional<std::string> ob;
-                if (out_blend) { auto nb = name_and_extension(*out_blend); ob = dir + "/" + nb.first + nm + nb.second; }
+                if (out_blend) ob = frame_name(*out_blend, num[i]);
                 std::cout << "Processing frame " << num[i] << " -> \n";
-                run_frame(&idx, dir + "/" + ne.first + nm + ne.second, ob);
+                run_frame(&idx, frame_name(opt["--output"], num[i]), ob);
+                i++;
             }
         } else {
             run_frame(nullptr, opt["--output"], out_blend);
