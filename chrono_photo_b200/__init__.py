@@ -4,10 +4,10 @@
 (The directory is named chrono_photo_b200 because `chrono-photo_b200` is not an importable Python package name.)
 """
 from .options import (BackgroundMode, Fade, FadeMode, FrameRange, OutlierSelectionMode, ParseEnumError, ParseOptionError,
-                      SelectionMode, Threshold)
-from .processors import (Context, FrameStack, OutlierProcessor, SimpleProcessor, crop_create, fetch_last, sample_positions,
+                      SelectionMode, ShakeAnchor, ShakeParams, Threshold)
+from .processors import (Context, FrameStack, OutlierProcessor, ShakeAnalyzer, SimpleProcessor, crop_create, fetch_last, sample_positions,
                          synth_frame_host, video_windows)
 
 __all__ = ["BackgroundMode", "Fade", "FadeMode", "FrameRange", "OutlierSelectionMode", "ParseEnumError", "ParseOptionError",
-           "SelectionMode", "Threshold", "Context", "FrameStack", "OutlierProcessor", "SimpleProcessor", "crop_create",
+           "SelectionMode", "ShakeAnchor", "ShakeParams", "Threshold", "Context", "ShakeAnalyzer", "FrameStack", "OutlierProcessor", "SimpleProcessor", "crop_create",
            "fetch_last", "sample_positions", "synth_frame_host", "video_windows"]

@@ -70,6 +70,9 @@ SYMBOLS = {
     "chb_threshold_new": (None, [_i, C.c_float, C.c_float, _f32p, _f32p, _f32p]),
     "chb_fade_build": (_i, [_i32p, _f32p, _i, _f32p, _i, _i32p]),
     "chb_crop_create": (_i, [_i32p, _i, _i, _i, _i32p, _i32p, _i32p]),
+    "chb_shake_create": (_i, [_vp, _i, _i, _i, _i32p, _i, _i, _i, _vp, C.c_size_t, C.POINTER(_vp)]),
+    "chb_shake_offset": (_i, [_vp, _vp, C.c_size_t, _i32p, _i32p, _i32p]),
+    "chb_shake_destroy": (_i, [_vp]),
     "chb_video_windows": (_i, [_i] * 11 + [_i32p, _i32p, _i32p, _i]),
 }
 

@@ -1092,6 +1092,127 @@ extern "C" int chb_fade_build(const int32_t* frames, const float* values, int n_
     return len + 1;
 }
 
+// ------------------------------------------------------------------------------------------------ K4 dispatch (shake analysis)
+struct chb_shake {
+    chb_ctx* ctx = nullptr;
+    int W = 0, H = 0, C = 0, n_anchors = 0, radius = 0, search = 0, size = 0, psize = 0, search_size = 0;
+    std::vector<int32_t> anchors;
+    uint8_t *d_windows = nullptr, *d_patches = nullptr, *h_patches = nullptr;
+    int32_t *d_diffs = nullptr, *d_result = nullptr, *h_diffs = nullptr, *h_result = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+
+extern "C" int chb_shake_destroy(chb_shake* sh) {
+    if (!sh) return CHB_OK;
+    cudaSetDevice(sh->ctx->devs[0].id);
+    if (sh->stream) { cudaStreamSynchronize(sh->stream); cudaStreamDestroy(sh->stream); }
+    cudaFree(sh->d_windows); cudaFree(sh->d_patches); cudaFree(sh->d_diffs); cudaFree(sh->d_result);
+    if (sh->h_patches) cudaFreeHost(sh->h_patches);
+    if (sh->h_diffs) cudaFreeHost(sh->h_diffs);
+    if (sh->h_result) cudaFreeHost(sh->h_result);
+    delete sh;
+    return CHB_OK;
+}
+
+// ShakeAnalyzer::analyze up to the first frame (src/shake.rs:222-246): fill_windows (:307-336) on the host side of the
+// boundary (a gather of n_anchors * (2r+1)^2 pixels), uploaded once.
+extern "C" int chb_shake_create(chb_ctx* ctx, int width, int height, int channels, const int32_t* anchors_xy, int n_anchors, int anchor_radius,
+                                int search_radius, const uint8_t* first_frame, size_t row_pitch, chb_shake** out) {
+    if (!ctx || !anchors_xy || !first_frame || !out) return fail(CHB_ERR_INVALID, "chb_shake_create: null argument");
+    if (width < 1 || height < 1 || channels < 1 || channels > 4 || n_anchors < 1 || anchor_radius < 0 || search_radius < 0)
+        return fail(CHB_ERR_INVALID, "chb_shake_create: bad geometry (%dx%dx%d, %d anchors, radii %d/%d)", width, height, channels, n_anchors, anchor_radius,
+                    search_radius);
+    if (row_pitch < (size_t)width * channels) return fail(CHB_ERR_INVALID, "chb_shake_create: row pitch smaller than a row");
+    if ((long long)(2 * (anchor_radius + search_radius) + 1) > 8192) return fail(CHB_ERR_UNSUPPORTED, "chb_shake_create: radii too large");
+    for (int i = 0; i < n_anchors; i++) {
+        const int cx = anchors_xy[2 * i], cy = anchors_xy[2 * i + 1];
+        for (int k = 0; k < 4; k++) {
+            const int xx = cx + ((k & 1) ? anchor_radius : -anchor_radius), yy = cy + ((k & 2) ? anchor_radius : -anchor_radius);
+            if (xx < 0 || yy < 0 || xx >= width || yy >= height)
+                return fail(CHB_ERR_INVALID, "Image coordinate out of range: (%d, %d)", xx, yy);  // the reference panics here (src/shake.rs:325-328)
+        }
+    }
+    chb_shake* sh = new chb_shake();
+    sh->ctx = ctx;
+    sh->W = width; sh->H = height; sh->C = channels;
+    sh->n_anchors = n_anchors; sh->radius = anchor_radius; sh->search = search_radius;
+    sh->size = 2 * anchor_radius + 1;
+    sh->psize = 2 * (anchor_radius + search_radius) + 1;
+    sh->search_size = 2 * search_radius + 1;
+    sh->anchors.assign(anchors_xy, anchors_xy + 2 * n_anchors);
+    const size_t win_bytes = (size_t)n_anchors * sh->size * sh->size * channels;
+    const size_t patch_bytes = (size_t)n_anchors * sh->psize * sh->psize * channels;
+    const size_t n_off = (size_t)sh->search_size * sh->search_size;
+    auto bail = [&](cudaError_t e, const char* what) {
+        chb_shake_destroy(sh);
+        return fail(CHB_ERR_CUDA, "chb_shake_create: %s: %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(ctx->devs[0].id)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaMalloc(&sh->d_windows, win_bytes)) != cudaSuccess) return bail(e, "windows");
+    if ((e = cudaMalloc(&sh->d_patches, patch_bytes)) != cudaSuccess) return bail(e, "patches");
+    if ((e = cudaMalloc(&sh->d_diffs, n_off * sizeof(int32_t))) != cudaSuccess) return bail(e, "diffs");
+    if ((e = cudaMalloc(&sh->d_result, 2 * sizeof(int32_t))) != cudaSuccess) return bail(e, "result");
+    if ((e = cudaMallocHost(&sh->h_patches, std::max(patch_bytes, win_bytes))) != cudaSuccess) return bail(e, "pinned patches");
+    if ((e = cudaMallocHost(&sh->h_diffs, n_off * sizeof(int32_t))) != cudaSuccess) return bail(e, "pinned diffs");
+    if ((e = cudaMallocHost(&sh->h_result, 2 * sizeof(int32_t))) != cudaSuccess) return bail(e, "pinned result");
+    const size_t row = (size_t)sh->size * channels;
+    for (int i = 0; i < n_anchors; i++) {
+        const int x0 = anchors_xy[2 * i] - anchor_radius, y0 = anchors_xy[2 * i + 1] - anchor_radius;
+        for (int dy = 0; dy < sh->size; dy++)
+            memcpy(sh->h_patches + ((size_t)i * sh->size + dy) * row, first_frame + (size_t)(y0 + dy) * row_pitch + (size_t)x0 * channels, row);
+    }
+    if ((e = cudaMemcpyAsync(sh->d_windows, sh->h_patches, win_bytes, cudaMemcpyHostToDevice, sh->stream)) != cudaSuccess) return bail(e, "upload");
+    if ((e = cudaStreamSynchronize(sh->stream)) != cudaSuccess) return bail(e, "sync");
+    *out = sh;
+    return CHB_OK;
+}
+
+// One frame of the par_iter in ShakeAnalyzer::analyze (src/shake.rs:248-283): calc_diffs over the search square and the
+// first minimum. diffs (nullable) receives the (2s+1)^2 table. Thread-safe (calls on one analyzer are serialised).
+extern "C" int chb_shake_offset(chb_shake* sh, const uint8_t* frame, size_t row_pitch, int32_t* out_dx, int32_t* out_dy, int32_t* diffs) {
+    if (!sh || !frame || !out_dx || !out_dy) return fail(CHB_ERR_INVALID, "chb_shake_offset: null argument");
+    if (row_pitch < (size_t)sh->W * sh->C) return fail(CHB_ERR_INVALID, "chb_shake_offset: row pitch smaller than a row");
+    const int reach = sh->radius + sh->search;
+    for (int i = 0; i < sh->n_anchors; i++) {
+        const int cx = sh->anchors[2 * i], cy = sh->anchors[2 * i + 1];
+        for (int k = 0; k < 4; k++) {
+            const int xx = cx + ((k & 1) ? reach : -reach), yy = cy + ((k & 2) ? reach : -reach);
+            if (xx < 0 || yy < 0 || xx >= sh->W || yy >= sh->H)
+                return fail(CHB_ERR_INVALID, "Image coordinate out of range: (%d, %d)", xx, yy);  // src/shake.rs:371-374
+        }
+    }
+    std::lock_guard<std::mutex> lk(sh->mu);
+    CU(cudaSetDevice(sh->ctx->devs[0].id));
+    const size_t row = (size_t)sh->psize * sh->C;
+    for (int i = 0; i < sh->n_anchors; i++) {
+        const int x0 = sh->anchors[2 * i] - reach, y0 = sh->anchors[2 * i + 1] - reach;
+        for (int dy = 0; dy < sh->psize; dy++)
+            memcpy(sh->h_patches + ((size_t)i * sh->psize + dy) * row, frame + (size_t)(y0 + dy) * row_pitch + (size_t)x0 * sh->C, row);
+    }
+    const size_t patch_bytes = (size_t)sh->n_anchors * sh->psize * row;
+    const int n_off = sh->search_size * sh->search_size;
+    CU(cudaMemcpyAsync(sh->d_patches, sh->h_patches, patch_bytes, cudaMemcpyHostToDevice, sh->stream));
+    ShakeArgs a;
+    a.windows = sh->d_windows; a.patches = sh->d_patches;
+    a.n_anchors = sh->n_anchors; a.size = sh->size; a.psize = sh->psize; a.search_size = sh->search_size; a.C = sh->C;
+    a.diffs = sh->d_diffs; a.result = sh->d_result;
+    shake_diff_kernel<<<n_off, 256, 0, sh->stream>>>(a);
+    shake_argmin_kernel<<<1, 256, 0, sh->stream>>>(a);
+    g_launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sh->h_result, sh->d_result, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, sh->stream));
+    if (diffs) CU(cudaMemcpyAsync(sh->h_diffs, sh->d_diffs, sizeof(int32_t) * (size_t)n_off, cudaMemcpyDeviceToHost, sh->stream));
+    CU(cudaStreamSynchronize(sh->stream));
+    if (diffs) memcpy(diffs, sh->h_diffs, sizeof(int32_t) * (size_t)n_off);
+    const int min_idx = sh->h_result[0];
+    *out_dx = (min_idx % sh->search_size) - sh->search;  // src/shake.rs:277-278
+    *out_dy = (min_idx / sh->search_size) - sh->search;
+    return CHB_OK;
+}
+
 extern "C" int chb_crop_create(const int32_t* off, int n, int width, int height, int32_t* out_xy, int32_t* out_w, int32_t* out_h) {
     // Crop::create, src/shake.rs:136-176
     int32_t xmin = 0, ymin = 0, xmax = 0, ymax = 0;

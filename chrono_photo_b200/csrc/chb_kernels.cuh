@@ -1525,6 +1525,68 @@ __global__ void __launch_bounds__(128) video_exact_kernel(const __grid_constant_
         drain_video_queue<C>(v, v.gq + base, (int)min(32u, total - base), lane);
 }
 
+// ------------------------------------------------------------------------------------------------ K4 shake analysis
+// ShakeAnalyzer::calc_diffs (src/shake.rs:338-386): for every offset of the search square, the sum of squared differences
+// between the first frame's anchor windows and the frame's pixels at that offset, over all anchors and bands; i32 with
+// wrap-around like the release build of the reference. Only the (2(r+s)+1)^2 patch around every anchor is on the device.
+// One CTA per search offset; its threads stride over the window bytes of every anchor (a row of a window is contiguous in
+// both the window and the patch), then reduce.
+struct ShakeArgs {
+    const uint8_t* windows;  // [n_anchors][size][size * C]
+    const uint8_t* patches;  // [n_anchors][psize][psize * C], psize = 2 (r + s) + 1: the frame around every anchor
+    int n_anchors, size, psize, search_size, C;
+    int32_t* diffs;          // [search_size^2]
+    int32_t* result;         // [2]: index of the first minimum, its value
+};
+__global__ void __launch_bounds__(256) shake_diff_kernel(const ShakeArgs a) {
+    const int ox = blockIdx.x % a.search_size, oy = blockIdx.x / a.search_size;
+    const int row_bytes = a.size * a.C;
+    const int per_anchor = a.size * row_bytes;
+    const int total = a.n_anchors * per_anchor;
+    uint32_t acc = 0;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int i = e / per_anchor, r = e - i * per_anchor;
+        const int dy = r / row_bytes, xb = r - dy * row_bytes;
+        const int w = a.windows[e];
+        const int p = a.patches[((size_t)i * a.psize + (oy + dy)) * (a.psize * a.C) + ox * a.C + xb];
+        const int d = w - p;
+        acc += (uint32_t)(d * d);
+    }
+    __shared__ uint32_t part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) s += part[k];
+        a.diffs[blockIdx.x] = (int32_t)s;
+    }
+}
+// First minimum of the diff table (Iterator::min_by_key keeps the first of equal minima, src/shake.rs:275-276).
+__global__ void __launch_bounds__(256) shake_argmin_kernel(const ShakeArgs a) {
+    const int n = a.search_size * a.search_size;
+    long long best = (long long)0x7fffffff << 32 | 0x7fffffff;  // (value, index) packed so that one min orders by value, then index
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long key = ((long long)a.diffs[i] << 32) | (unsigned int)i;
+        best = key < best ? key : best;
+    }
+    __shared__ long long part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) best = part[k] < best ? part[k] : best;
+        if (part[0] < best) best = part[0];
+        a.result[0] = (int32_t)(best & 0xffffffffLL);
+        a.result[1] = (int32_t)(best >> 32);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K2
 struct SimpleArgs {
     const uint8_t* stack;

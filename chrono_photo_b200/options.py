@@ -228,3 +228,40 @@ class FrameRange:
                 except ValueError:
                     raise ParseOptionError(f"Can't parse element {i} in option --frames (start/end/step), got '{p}'.")
         return cls(vals[0], vals[1], vals[2] if vals[2] is not None else 1)
+
+
+class ShakeParams:
+    """src/shake.rs:44-86: `--shake <anchor-radius>/<search-radius>`."""
+
+    def __init__(self, anchor_radius, search_radius):
+        self.anchor_radius, self.search_radius = int(anchor_radius), int(search_radius)
+
+    @classmethod
+    def from_str(cls, s):
+        parts = s.split("/")
+        if len(parts) != 2:
+            raise ParseOptionError(f"Unexpected format in shake parameters, expected <rad>/<search-rad>: {s}")
+        try:
+            rad, search = int(parts[0]), int(parts[1])
+            if rad < 0 or search < 0:
+                raise ValueError
+        except ValueError:  # the reference panics here (`expect`), u32 parse
+            raise ParseOptionError(f"Unexpected format in shake parameter: {s}")
+        return cls(rad, search)
+
+
+class ShakeAnchor:
+    """src/shake.rs:88-119: `--shake-anchors x/y`."""
+
+    def __init__(self, x, y):
+        self.anchor = (int(x), int(y))
+
+    @classmethod
+    def from_str(cls, s):
+        parts = s.split("/")
+        if len(parts) != 2:
+            raise ParseOptionError(f"Unexpected format in shake anchor, expected x/y: {s}")
+        try:
+            return cls(int(parts[0]), int(parts[1]))
+        except ValueError:
+            raise ParseOptionError(f"Unexpected format in shake anchor, expected x/y: {s}")

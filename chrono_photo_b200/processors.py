@@ -306,6 +306,56 @@ def fetch_last(stack, want_mask=False):
     return out, mask, warn.value
 
 
+class ShakeAnalyzer:
+    """ShakeAnalyzer::analyze (src/shake.rs:190-305) over decoded frames: the first frame supplies the anchor windows, every
+    further frame gets its (dx, dy) from the GPU (sums of squared differences over the search square, first minimum)."""
+
+    def __init__(self, ctx, first_frame, anchors, anchor_radius, search_radius):
+        f = np.ascontiguousarray(first_frame, dtype=np.uint8)
+        if f.ndim != 3:
+            raise ValueError("frame must be (H, W, C) uint8")
+        self.shape = f.shape
+        anc = np.ascontiguousarray([a.anchor if hasattr(a, "anchor") else a for a in anchors], dtype=np.int32).reshape(-1, 2)
+        self.search_size = 2 * int(search_radius) + 1
+        h = C.c_void_p()
+        _lib.check(_lib.lib().chb_shake_create(ctx._h, f.shape[1], f.shape[0], f.shape[2], anc.ctypes.data_as(C.POINTER(C.c_int32)), len(anc),
+                                               int(anchor_radius), int(search_radius), C.c_void_p(f.ctypes.data), f.shape[1] * f.shape[2], C.byref(h)))
+        self._h = h
+
+    def offset(self, frame, want_diffs=False):
+        """One frame -> (dx, dy) [, diff table of shape (2s+1, 2s+1), rows = dy]."""
+        f = np.ascontiguousarray(frame, dtype=np.uint8)
+        if f.shape != self.shape:
+            raise ValueError("Image layout does not fit!")
+        dx, dy = C.c_int32(), C.c_int32()
+        diffs = np.zeros((self.search_size, self.search_size), np.int32) if want_diffs else None
+        _lib.check(_lib.lib().chb_shake_offset(self._h, C.c_void_p(f.ctypes.data), f.shape[1] * f.shape[2], C.byref(dx), C.byref(dy),
+                                               diffs.ctypes.data_as(C.POINTER(C.c_int32)) if want_diffs else None))
+        return ((dx.value, dy.value), diffs) if want_diffs else (dx.value, dy.value)
+
+    @classmethod
+    def analyze(cls, ctx, frames, anchors, anchor_radius, search_radius):
+        """-> [(0, 0), (dx1, dy1), ...] for an iterable of (H, W, C) frames, like the reference's return value."""
+        it = iter(frames)
+        first = next(it)
+        an = cls(ctx, first, anchors, anchor_radius, search_radius)
+        try:
+            return [(0, 0)] + [an.offset(f) for f in it]
+        finally:
+            an.close()
+
+    def close(self):
+        if self._h:
+            _lib.lib().chb_shake_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def crop_create(offsets, width, height):
     """Crop::create (src/shake.rs:136-176): per-frame crop origins and the common size, or None if all offsets are zero."""
     off = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 2)

@@ -192,6 +192,21 @@ int chb_sample_positions(uint64_t seed, int n, int cnt, int32_t *out_positions);
 void chb_threshold_new(int absolute, float min, float max, float *out_min, float *out_max, float *out_scale);
 /* Fade::new (src/options.rs:69-94): builds the LUT from (frame, value) pairs; returns the number of values or <0. */
 int chb_fade_build(const int32_t *frames, const float *values, int n_pairs, float *out_values, int out_cap, int32_t *out_offset);
+/* ---- camera-shake analysis (ShakeAnalyzer::analyze, src/shake.rs:190-305) ------------------------------------
+ * chb_shake_create takes the FIRST frame and keeps the (2r+1)^2 x C window around every anchor (fill_windows,
+ * src/shake.rs:307-336). chb_shake_offset replaces one iteration of the par_iter over the remaining files
+ * (src/shake.rs:248-283): sums of squared differences over the (2s+1)^2 search square for all anchors (calc_diffs,
+ * :338-386, i32 with wrap-around like the release build) and the FIRST minimum -> (dx, dy). Only the patches around the
+ * anchors cross PCIe. diffs (nullable) receives the table, row-major (oy, ox). Where the reference panics with "Image
+ * coordinate out of range" the call fails with CHB_ERR_INVALID and that message. Calls on one analyzer are serialised
+ * (callable from the rayon pool). The offsets feed chb_crop_create; frame 0's offset is (0, 0) by definition. */
+typedef struct chb_shake chb_shake;
+int chb_shake_create(chb_ctx *ctx, int width, int height, int channels, const int32_t *anchors_xy, int n_anchors,
+                     int anchor_radius, int search_radius, const uint8_t *first_frame, size_t row_pitch, chb_shake **out);
+int chb_shake_offset(chb_shake *analyzer, const uint8_t *frame, size_t row_pitch, int32_t *out_dx, int32_t *out_dy,
+                     int32_t *diffs);
+int chb_shake_destroy(chb_shake *analyzer);
+
 /* Crop::create (src/shake.rs:136-176). Returns 1 and fills out_xy (n x (x,y)), out_w, out_h; 0 if all offsets are zero. */
 int chb_crop_create(const int32_t *offsets_xy, int n, int width, int height, int32_t *out_xy, int32_t *out_w, int32_t *out_h);
 /* Window index math of create_video / create_video_simple (src/main.rs:230-286, :349-404). Returns the number of

@@ -8,6 +8,7 @@
 //   OutlierProcessor (new / process)                                                  src/chrono.rs:46-54, :73-81
 //   SimpleProcessor (new / process)                                                   src/simple.rs:18, :26-32
 //   GpuStack                                 replaces TimeSlicer::write_time_slices   src/slicer.rs:106
+//   ShakeParams, ShakeAnchor, ShakeAnalyzer                                          src/shake.rs:44-119, :185-305
 #pragma once
 #include <cstdint>
 #include <cstdlib>
@@ -293,6 +294,55 @@ private:
     float w_[4];
     Fade fade_;
     bool darker_;
+};
+
+// src/shake.rs:44-119: `--shake <anchor-radius>/<search-radius>` and `--shake-anchors x/y`
+struct ShakeParams {
+    uint32_t anchor_radius = 0, search_radius = 0;
+    static ShakeParams from_str(const std::string& s) {
+        auto parts = split(s, '/');
+        if (parts.size() != 2) throw ParseOptionError("Unexpected format in shake parameters, expected <rad>/<search-rad>: " + s);
+        ShakeParams p;
+        int a = parse_i32(parts[0], "Unexpected format in shake parameter: " + s), b = parse_i32(parts[1], "Unexpected format in shake parameter: " + s);
+        if (a < 0 || b < 0) throw ParseOptionError("Unexpected format in shake parameter: " + s);
+        p.anchor_radius = (uint32_t)a; p.search_radius = (uint32_t)b;
+        return p;
+    }
+};
+struct ShakeAnchor {
+    int32_t x = 0, y = 0;
+    static ShakeAnchor from_str(const std::string& s) {
+        auto parts = split(s, '/');
+        if (parts.size() != 2) throw ParseOptionError("Unexpected format in shake anchor, expected x/y: " + s);
+        ShakeAnchor a;
+        a.x = parse_i32(parts[0], "Unexpected format in shake anchor, expected x/y: " + s);
+        a.y = parse_i32(parts[1], "Unexpected format in shake anchor, expected x/y: " + s);
+        return a;
+    }
+};
+
+// ShakeAnalyzer::analyze (src/shake.rs:190-305): the first frame supplies the anchor windows; offset() is one iteration of
+// the reference's par_iter over the remaining frames (sums of squared differences on the GPU, first minimum).
+class ShakeAnalyzer {
+public:
+    ShakeAnalyzer(const Context& ctx, int width, int height, int channels, const std::vector<ShakeAnchor>& anchors, const ShakeParams& params,
+                  const uint8_t* first_frame, size_t row_pitch) {
+        std::vector<int32_t> xy;
+        for (const auto& a : anchors) { xy.push_back(a.x); xy.push_back(a.y); }
+        check(chb_shake_create(ctx.raw(), width, height, channels, xy.data(), (int)anchors.size(), (int)params.anchor_radius, (int)params.search_radius,
+                               first_frame, row_pitch, &h_));
+    }
+    ~ShakeAnalyzer() { chb_shake_destroy(h_); }
+    ShakeAnalyzer(const ShakeAnalyzer&) = delete;
+    ShakeAnalyzer& operator=(const ShakeAnalyzer&) = delete;
+    std::pair<int32_t, int32_t> offset(const uint8_t* frame, size_t row_pitch) const {
+        int32_t dx = 0, dy = 0;
+        check(chb_shake_offset(h_, frame, row_pitch, &dx, &dy, nullptr));
+        return {dx, dy};
+    }
+
+private:
+    chb_shake* h_ = nullptr;
 };
 
 }  // namespace chrono_b200

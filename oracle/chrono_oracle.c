@@ -691,6 +691,67 @@ int orc_crop_create(const int32_t *offsets, int n, int width, int height, int32_
     return 1;
 }
 
+/* ---------------------------------------------------------------- shake.rs ShakeAnalyzer */
+
+/* fill_windows (src/shake.rs:307-336): the (2r+1)^2 x C bytes around every anchor of the FIRST frame.
+ * Returns 0, or -1 when a coordinate leaves the image (the reference panics: "Image coordinate out of range"). */
+int orc_shake_fill_windows(const uint8_t *image, int width, int height, int channels, const int32_t *anchors_xy, int n_anchors,
+                           int anchor_radius, uint8_t *windows) {
+    const int size = 2 * anchor_radius + 1;
+    const size_t win_len = (size_t)size * size * channels;
+    for (int i = 0; i < n_anchors; i++) {
+        uint8_t *win = windows + (size_t)i * win_len;
+        const int cx = anchors_xy[2 * i], cy = anchors_xy[2 * i + 1];
+        for (int dy = 0; dy < size; dy++) {
+            const int yy = cy + dy - anchor_radius;
+            for (int dx = 0; dx < size; dx++) {
+                const int xx = cx + dx - anchor_radius;
+                if (xx < 0 || yy < 0 || xx >= width || yy >= height) return -1;
+                for (int ch = 0; ch < channels; ch++)
+                    win[((size_t)dy * size + dx) * channels + ch] = image[((size_t)yy * width + xx) * channels + ch];
+            }
+        }
+    }
+    return 0;
+}
+
+/* calc_diffs (src/shake.rs:338-386) + the first minimum (:275-279, Iterator::min_by_key keeps the first of equal minima).
+ * diffs: (2s+1)^2 sums of squared differences over all anchors, i32 with wrap-around (release build, overflow-checks off,
+ * Cargo.toml:13). Returns 0, or -1 when a coordinate leaves the image. */
+int orc_shake_offset(const uint8_t *image, int width, int height, int channels, const int32_t *anchors_xy, int n_anchors,
+                     int anchor_radius, int search_radius, const uint8_t *windows, int32_t *diffs, int32_t *out_dx, int32_t *out_dy) {
+    const int size = 2 * anchor_radius + 1, search_size = 2 * search_radius + 1;
+    const size_t win_len = (size_t)size * size * channels;
+    for (int i = 0; i < search_size * search_size; i++) diffs[i] = 0;
+    for (int i = 0; i < n_anchors; i++) {
+        const uint8_t *win = windows + (size_t)i * win_len;
+        const int cx = anchors_xy[2 * i], cy = anchors_xy[2 * i + 1];
+        for (int oy = 0; oy < search_size; oy++) {
+            for (int ox = 0; ox < search_size; ox++) {
+                uint32_t acc = (uint32_t)diffs[oy * search_size + ox];
+                for (int dy = 0; dy < size; dy++) {
+                    const int yy = cy + (oy - search_radius) + dy - anchor_radius;
+                    for (int dx = 0; dx < size; dx++) {
+                        const int xx = cx + (ox - search_radius) + dx - anchor_radius;
+                        if (xx < 0 || yy < 0 || xx >= width || yy >= height) return -1;
+                        for (int ch = 0; ch < channels; ch++) {
+                            const int d = (int)win[((size_t)dy * size + dx) * channels + ch] - (int)image[((size_t)yy * width + xx) * channels + ch];
+                            acc += (uint32_t)(d * d);
+                        }
+                    }
+                }
+                diffs[oy * search_size + ox] = (int32_t)acc;
+            }
+        }
+    }
+    int min_idx = 0;
+    for (int i = 1; i < search_size * search_size; i++)
+        if (diffs[i] < diffs[min_idx]) min_idx = i;
+    *out_dx = (min_idx % search_size) - search_radius;
+    *out_dy = (min_idx / search_size) - search_radius;
+    return 0;
+}
+
 /* ---------------------------------------------------------------- main.rs video windows */
 
 /* src/main.rs:230-286 (identical in :349-404). Rust `%` is a remainder with the sign of the dividend, like C. */

@@ -119,6 +119,13 @@ int orc_crop_create(const int32_t *offsets, int n, int width, int height, int32_
  * (step = in_step); an empty window (start >= end) means the reference skips the frame.
  * Returns the number of output frames, writes at most cap entries.
  */
+/* ShakeAnalyzer (src/shake.rs:190-386): anchor windows of the first frame, then per frame the sums of squared differences
+ * over the search square and the first minimum. Both return -1 when a coordinate leaves the image (the reference panics). */
+int orc_shake_fill_windows(const uint8_t *image, int width, int height, int channels, const int32_t *anchors_xy, int n_anchors,
+                           int anchor_radius, uint8_t *windows);
+int orc_shake_offset(const uint8_t *image, int width, int height, int channels, const int32_t *anchors_xy, int n_anchors,
+                     int anchor_radius, int search_radius, const uint8_t *windows, int32_t *diffs, int32_t *out_dx, int32_t *out_dy);
+
 int orc_video_windows(int image_count,
                       int in_has_start, int in_start, int in_has_end, int in_end, int in_step,
                       int out_has_start, int out_start, int out_has_end, int out_end, int out_step,

@@ -174,6 +174,32 @@ def simple(stack, darker, weights=(1, 1, 1, 1), fade_=None, indices=None, n_thre
     return out
 
 
+def shake_analyze(frames, anchors, anchor_radius, search_radius, want_diffs=False):
+    """ShakeAnalyzer::analyze (src/shake.rs:190-305) on decoded frames (N, H, W, C) uint8 -> offsets [(0, 0), (dx, dy), ...]
+    (and, optionally, the per-frame diff tables). Raises IndexError where the reference panics (coordinate out of range)."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    N, H, W, Cc = frames.shape
+    anc = np.ascontiguousarray(anchors, np.int32).reshape(-1, 2)
+    size, ss = 2 * anchor_radius + 1, 2 * search_radius + 1
+    wins = np.zeros(len(anc) * size * size * Cc, np.uint8)
+    l = lib()
+    l.orc_shake_fill_windows.restype = C.c_int
+    l.orc_shake_offset.restype = C.c_int
+    if l.orc_shake_fill_windows(C.c_void_p(frames[0].ctypes.data), W, H, Cc, C.c_void_p(anc.ctypes.data), len(anc), anchor_radius,
+                                C.c_void_p(wins.ctypes.data)) != 0:
+        raise IndexError("Image coordinate out of range")
+    out, tables = [(0, 0)], []
+    for i in range(1, N):
+        diffs = np.zeros(ss * ss, np.int32)
+        dx, dy = C.c_int32(), C.c_int32()
+        if l.orc_shake_offset(C.c_void_p(frames[i].ctypes.data), W, H, Cc, C.c_void_p(anc.ctypes.data), len(anc), anchor_radius, search_radius,
+                              C.c_void_p(wins.ctypes.data), C.c_void_p(diffs.ctypes.data), C.byref(dx), C.byref(dy)) != 0:
+            raise IndexError("Image coordinate out of range")
+        out.append((dx.value, dy.value))
+        tables.append(diffs)
+    return (out, tables) if want_diffs else out
+
+
 def crop_create(offsets, width, height):
     off = np.ascontiguousarray(offsets, np.int32).reshape(-1, 2)
     xy = np.zeros_like(off)

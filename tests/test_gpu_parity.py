@@ -459,6 +459,64 @@ def test_video_run_error_paths(ctx):
     fs.close()
 
 
+# ---------------------------------------------------------------------------------------------------- shake analysis
+def test_shake_analysis_matches_oracle_bit_for_bit(ctx):
+    from test_oracle import shaky_clip
+    rng = np.random.default_rng(2024)
+    for (n, H, W, C, shift, r, s, anchors) in [(6, 64, 96, 3, 4, 6, 5, [(30, 25), (60, 40)]), (4, 50, 70, 4, 2, 3, 3, [(12, 12)]),
+                                                 (5, 120, 160, 3, 7, 20, 9, [(40, 40), (110, 70), (80, 85)]), (3, 40, 40, 3, 0, 0, 0, [(5, 7)])]:
+        frames, true = shaky_clip(rng, n, H, W, C, shift, 8)
+        want, tables = orc.shake_analyze(frames, anchors, r, s, want_diffs=True)
+        an = cp.ShakeAnalyzer(ctx, frames[0], anchors, r, s)
+        for i in range(1, n):
+            got, diffs = an.offset(frames[i], want_diffs=True)
+            assert np.array_equal(diffs.ravel(), tables[i - 1]), (i, r, s)
+            assert got == want[i] == true[i]
+        an.close()
+        assert cp.ShakeAnalyzer.analyze(ctx, frames, [cp.ShakeAnchor.from_str(f"{x}/{y}") for x, y in anchors], r, s) == want
+
+
+def test_shake_ties_wrap_around_and_errors(ctx):
+    from chrono_photo_b200._lib import ChbError
+    flat = np.full((2, 40, 40, 3), 77, np.uint8)
+    assert cp.ShakeAnalyzer.analyze(ctx, flat, [(20, 20)], 3, 2) == [(0, 0), (-2, -2)]  # first minimum of a flat table
+    a = np.zeros((2, 140, 140, 3), np.uint8)
+    a[1] = 255
+    an = cp.ShakeAnalyzer(ctx, a[0], [(69, 69)] * 3, 64, 0)  # the sum overflows i32 and wraps like the reference's release build
+    got, diffs = an.offset(a[1], want_diffs=True)
+    _, tables = orc.shake_analyze(a, [(69, 69)] * 3, 64, 0, want_diffs=True)
+    assert got == (0, 0) and int(diffs[0, 0]) == int(tables[0][0]) != 3 * 129 * 129 * 3 * 255 * 255
+    an.close()
+    with pytest.raises(ChbError) as e:
+        cp.ShakeAnalyzer(ctx, flat[0], [(2, 20)], 3, 2)
+    assert "Image coordinate out of range" in str(e.value)
+    an = cp.ShakeAnalyzer(ctx, flat[0], [(4, 20)], 3, 2)
+    with pytest.raises(ChbError) as e:
+        an.offset(flat[1])
+    assert "Image coordinate out of range" in str(e.value)
+    an.close()
+
+
+def test_shake_analysis_feeds_crop_and_video(ctx):
+    # the whole config-5 chain on the GPU: analyse -> Crop::create -> upload with crop origins -> sliding-window run
+    from test_oracle import shaky_clip
+    rng = np.random.default_rng(5)
+    n, H, W = 30, 48, 64
+    scene_frames, true = shaky_clip(rng, n, H, W, 3, 3, 6)
+    noise = rng.integers(-3, 4, size=scene_frames.shape)
+    frames = np.clip(scene_frames.astype(np.int64) // 2 + 60 + noise, 0, 255).astype(np.uint8)  # low contrast + noise: still locks on
+    offs = cp.ShakeAnalyzer.analyze(ctx, frames, [(20, 20), (45, 30)], 8, 4)
+    assert offs == orc.shake_analyze(frames, [(20, 20), (45, 30)], 8, 4) == true
+    xy, w, h = cp.crop_create(offs, W, H)
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    for i in range(n):
+        fs.upload(i, frames[i], tuple(xy[i]))
+    fs.sync()
+    st = np.stack([frames[i, xy[i][1]:xy[i][1] + h, xy[i][0]:xy[i][0] + w] for i in range(n)])
+    _check_video_run(ctx, fs, st, 0, 9, n - 8, (True, 0.05, 0.2), "first", "extreme")
+    fs.close()
+
+
 def test_concurrent_callers_like_the_rayon_video_pool(ctx):
     # create_video calls one processor per output frame from a rayon pool (src/main.rs:260-261); decode threads upload
     # distinct frames concurrently. The library must give every caller its own correct result.

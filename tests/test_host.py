@@ -121,3 +121,15 @@ def test_sample_positions_are_sorted_distinct():
     p = cp.sample_positions(9, 200, 40)
     assert len(set(p.tolist())) == 40 and (np.diff(p) > 0).all() and p.min() >= 0 and p.max() < 200
     assert np.array_equal(p, cp.sample_positions(9, 200, 40))
+
+
+def test_shake_option_parsing_mirrors_the_reference():
+    # src/shake.rs:58-119
+    p = cp.ShakeParams.from_str("20/10")
+    assert (p.anchor_radius, p.search_radius) == (20, 10)
+    assert cp.ShakeAnchor.from_str("120/-3").anchor == (120, -3)
+    for bad, cls, msg in [("20", cp.ShakeParams, "expected <rad>/<search-rad>"), ("a/3", cp.ShakeParams, "Unexpected format in shake parameter"),
+                          ("1/2/3", cp.ShakeAnchor, "expected x/y"), ("x/2", cp.ShakeAnchor, "expected x/y")]:
+        with pytest.raises(cp.ParseOptionError) as e:
+            cls.from_str(bad)
+        assert msg in str(e.value)

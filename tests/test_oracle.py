@@ -205,3 +205,67 @@ def test_video_windows_quirks():
         while st < 0:
             st += 2
         assert ws[f] == max(st % 2, f - 4)
+
+
+# ---- shake analysis (src/shake.rs:190-386) -----------------------------------------------------------------------
+def shaky_clip(rng, n, H, W, C, max_shift, margin):
+    """A textured scene seen through a camera that shifts by a known integer offset per frame (frame 0 unshifted)."""
+    scene = rng.integers(0, 256, size=(H + 2 * margin, W + 2 * margin, C), dtype=np.uint8)
+    offs = rng.integers(-max_shift, max_shift + 1, size=(n, 2))
+    offs[0] = 0
+    frames = np.stack([scene[margin - oy:margin - oy + H, margin - ox:margin - ox + W] for ox, oy in offs])
+    return frames, [tuple(int(v) for v in o) for o in offs]
+
+
+def np_shake_offsets(frames, anchors, r, s):
+    """Independent numpy restatement of calc_diffs + first minimum."""
+    out, tables = [(0, 0)], []
+    f0 = frames[0].astype(np.int64)
+    for fr in frames[1:]:
+        fr = fr.astype(np.int64)
+        diffs = np.zeros((2 * s + 1, 2 * s + 1), np.int64)
+        for cx, cy in anchors:
+            win = f0[cy - r:cy + r + 1, cx - r:cx + r + 1]
+            for oy in range(-s, s + 1):
+                for ox in range(-s, s + 1):
+                    pat = fr[cy + oy - r:cy + oy + r + 1, cx + ox - r:cx + ox + r + 1]
+                    diffs[oy + s, ox + s] += ((win - pat) ** 2).sum()
+        d32 = ((diffs + 2 ** 31) % 2 ** 32 - 2 ** 31).astype(np.int32)  # i32 wrap-around
+        idx = int(np.argmin(d32.ravel()))  # argmin returns the first minimum
+        out.append((idx % (2 * s + 1) - s, idx // (2 * s + 1) - s))
+        tables.append(d32.ravel())
+    return out, tables
+
+
+def test_shake_offsets_recover_known_shifts_and_match_numpy():
+    rng = np.random.default_rng(321)
+    frames, true = shaky_clip(rng, 7, 60, 80, 3, 4, 6)
+    anchors = [(30, 25), (55, 40)]
+    got, tables = orc.shake_analyze(frames, anchors, 6, 5, want_diffs=True)
+    ref, ref_tables = np_shake_offsets(frames, anchors, 6, 5)
+    assert got == ref and all(np.array_equal(a, b) for a, b in zip(tables, ref_tables))
+    # a frame shifted by (ox, oy) shows the anchor's content at anchor + (ox, oy): the analysis returns exactly that
+    assert got == true
+    # Crop::create then realigns the frames (src/shake.rs:136-176)
+    xy, w, h = orc.crop_create(got, 80, 60)
+    aligned = np.stack([frames[i, xy[i][1]:xy[i][1] + h, xy[i][0]:xy[i][0] + w] for i in range(len(frames))])
+    assert all(np.array_equal(aligned[0], a) for a in aligned[1:])
+
+
+def test_shake_first_minimum_wins_and_range_panics():
+    flat = np.full((3, 40, 40, 3), 77, np.uint8)  # every offset has the same (zero) difference: the first one wins
+    assert orc.shake_analyze(flat, [(20, 20)], 3, 2) == [(0, 0), (-2, -2), (-2, -2)]
+    with pytest.raises(IndexError):
+        orc.shake_analyze(flat, [(2, 20)], 3, 2)        # window leaves the image: the reference panics
+    with pytest.raises(IndexError):
+        orc.shake_analyze(flat, [(4, 20)], 3, 2)        # search square leaves the image
+
+
+def test_shake_diffs_wrap_like_i32():
+    # 3 anchors x 129^2 x 3 bytes of maximal difference overflow i32; the release build of the reference wraps
+    a = np.zeros((2, 140, 140, 3), np.uint8)
+    a[1] = 255
+    anchors = [(69, 69)] * 3
+    got, tables = orc.shake_analyze(a, anchors, 64, 0, want_diffs=True)
+    exact = 3 * 129 * 129 * 3 * 255 * 255
+    assert exact > 2 ** 31 and int(tables[0][0]) == ((exact + 2 ** 31) % 2 ** 32) - 2 ** 31 and got == [(0, 0), (0, 0)]
