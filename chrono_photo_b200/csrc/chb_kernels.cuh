@@ -72,6 +72,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// per-lane asynchronous 16-byte copies (cp.async, SASS LDGSTS): the G > 1 variants prefetch every lane's own units
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
     for (int spin = 0; !ok; spin++) {
@@ -743,9 +749,9 @@ constexpr int kHardBytes = kWarpsPerCta * kQueueCap * (int)sizeof(long long);
 constexpr int kBarBytes = 128;
 constexpr int kAccBytes = kWarpsPerCta * 32 * 12 * 4;
 // dynamic shared memory of one CTA: exact-path queues, hard-pixel queues, one mbarrier per warp, per-thread result slots,
-// one staged pixel-band per warp (G == 1)
+// one staged pixel-band per warp (G == 1: the tile's contiguous slab; G > 1: every lane's own units, [slot][lane])
 __host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) {
-    return kQueueBytes + kHardBytes + kBarBytes + kAccBytes + (g == 1 ? kWarpsPerCta * wpl * 512 : 0);
+    return kQueueBytes + kHardBytes + kBarBytes + kAccBytes + kWarpsPerCta * wpl * 512;  // g == 1: one slab per warp; g > 1: wpl units per lane
 }
 
 template <int C>
@@ -1004,8 +1010,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     constexpr int PPW = 32 / G;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
     // G == 1: a tile's band is one contiguous slab, staged by ONE TMA bulk copy per pixel-band. With G > 1 a slab is
-    // n_groups rows of 512/G bytes; staging those with one small bulk copy per row measured slower than direct 128-bit
-    // loads (10.4 vs 8.7 ms on the 1000-frame UHD stack), so those variants load straight into registers.
+    // n_groups rows of 512/G bytes (one small bulk copy per row measured slower than direct loads: 10.4 vs 8.7 ms on the
+    // 1000-frame UHD stack); there every lane prefetches its OWN 16-byte units of the next pixel-band with cp.async into a
+    // lane-private strip of shared memory while the current band is processed.
     constexpr bool kStage = (G == 1);
     constexpr int kRowBytes = 512 / G;  // bytes of one (band, group) row that belong to this warp's 32/G pixels
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1045,9 +1052,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
         }
     };
 
+    // G > 1: this lane's units of one pixel-band, slot i at strip + i * 512 (conflict-free 128-bit reads)
+    const uint32_t strip_lane = smem_u32(stage) + lane * 16;
+    auto prefetch_band = [&](int task, int c) {
+        const int tile = task / G;
+        const int p = (task % G) * PPW + pl;
+        const uint8_t* cb = a.stack + (long long)tile * tile_bytes(C, a.NG) + ((long long)(c * a.NG + a.g0 + j) * kTilePixels + p) * kUnitBytes;
+#pragma unroll
+        for (int i = 0; i < WPL; i++)
+            if ((!GENERIC && i < WPL - 1) || i * G + j < a.n_groups) cp_async16(strip_lane + i * 512, cb + i * kSlotStride);
+        cp_async_commit();
+    };
+
     uint32_t A[W4];  // the current pixel-band
     int task = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (kStage && task < n_tasks) stage_band(task, 0);
+    if (task < n_tasks) {
+        if (kStage) stage_band(task, 0);
+        else prefetch_band(task, 0);
+    }
     while (task < n_tasks) {
         const int tile = task / G;
         const int p = (task % G) * PPW + pl;
@@ -1074,18 +1096,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
                 const int nt = last ? task + n_warps : task;
                 if (nt < n_tasks) stage_band(nt, last ? 0 : c + 1);
             } else {
-                const uint8_t* cb = a.stack + (long long)tile * tile_bytes(C, a.NG) + ((long long)(c * a.NG + a.g0 + j) * kTilePixels + p) * kUnitBytes;
+                // ---- the lane's units were prefetched one pixel-band ago: strip -> registers, then start the next prefetch
+                cp_async_wait_all();
 #pragma unroll
                 for (int i = 0; i < WPL; i++) {
-                    uint4 v;
-                    if (!GENERIC && i < WPL - 1) {
-                        v = ldg_stream(cb + i * kSlotStride);
-                    } else {
-                        v = make_uint4(0, 0, 0, 0);
-                        if (i * G + j < a.n_groups) v = ldg_stream(cb + i * kSlotStride);
-                    }
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if ((!GENERIC && i < WPL - 1) || i * G + j < a.n_groups) v = lds128(strip_lane + i * 512);
                     A[4 * i + 0] = v.x; A[4 * i + 1] = v.y; A[4 * i + 2] = v.z; A[4 * i + 3] = v.w;
                 }
+                const bool last = (c == C - 1);
+                const int nt = last ? task + n_warps : task;
+                if (nt < n_tasks) prefetch_band(nt, last ? 0 : c + 1);
             }
             process_band<C, WPL, G, MODE, true>(a, A, c, j, pix, owner, cap, pad, acc);
         }
