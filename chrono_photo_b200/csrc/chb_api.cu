@@ -84,6 +84,9 @@ struct Band {
     int v_cap_windows = 0;
     unsigned long long* d_vwarn = nullptr;
     int vwarn_cap = 0;
+    QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters
+    unsigned int* d_qcount = nullptr;
+    unsigned int queue_cap = 0;
     VideoQueueEntry* d_vqueue = nullptr;  // exact-path queue of a chunk + its counter
     unsigned int* d_vqcount = nullptr;
     cudaEvent_t v_done[2] = {nullptr, nullptr};    // kernel writing slot s finished
@@ -186,7 +189,7 @@ static void free_band(Band& b) {
         if (b.v_done[s]) cudaEventDestroy(b.v_done[s]);
         if (b.v_copied[s]) cudaEventDestroy(b.v_copied[s]);
     }
-    cudaFree(b.d_vwarn); cudaFree(b.d_vqueue); cudaFree(b.d_vqcount);
+    cudaFree(b.d_vwarn); cudaFree(b.d_vqueue); cudaFree(b.d_vqcount); cudaFree(b.d_queue); cudaFree(b.d_qcount);
 }
 
 extern "C" int chb_stack_destroy(chb_stack* st) {
@@ -601,7 +604,17 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
         }
         CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
+        if (!b.d_queue) {  // a quarter of the band's pixels (at most 4 M entries); the rest would be finished inside the main kernel
+            b.queue_cap = (unsigned int)std::min<long long>(4LL << 20, std::max<long long>(1 << 16, b.n_pixels / 4));
+            CU(cudaMalloc(&b.d_queue, sizeof(QueueEntry) * (size_t)b.queue_cap));
+            CU(cudaMalloc(&b.d_qcount, 2 * sizeof(unsigned int)));
+        }
+        CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(unsigned int), s));
+        CU(cudaMemsetAsync(b.d_qcount + 1, 0xff, sizeof(unsigned int), s));
         OutlierArgs ab = a;
+        ab.gq = b.d_queue; ab.gq_count = b.d_qcount; ab.gq_cap = b.queue_cap;
+        if (const char* qc = getenv("CHB_QUEUE_CAP"))  // test aid: a small capacity exercises the in-place fallback
+            ab.gq_cap = (unsigned int)std::min<long long>(b.queue_cap, std::max<long long>(0, atoll(qc)));
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
         ab.wmask = b.d_wmask; ab.smask = sub ? b.d_smask : nullptr; ab.win_frames = b.d_win;
@@ -636,7 +649,9 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         const int blocks = grid_for(n_tasks * 32, kWarpsPerCta * 32, d.sm_count, std::max(1, occ));
         CU(cudaEventRecord(b.ev0, s));
         kern<<<blocks, kWarpsPerCta * 32, smem, s>>>(ab);
-        g_launches++;
+        if (st->C == 3) outlier_exact_kernel<3><<<d.sm_count * 4, 256, 0, s>>>(ab);
+        else outlier_exact_kernel<4><<<d.sm_count * 4, 256, 0, s>>>(ab);
+        g_launches += 2;
         CU(cudaGetLastError());
         CU(cudaEventRecord(b.ev1, s));
         CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));

@@ -118,6 +118,9 @@ struct OutlierArgs {
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
     unsigned long long* counters;  // [0] warnings (all-outlier pixels), [1] pixels on the exact path, [2] pixels on the iterative (hard) path
+    struct QueueEntry* gq;         // global exact-path queue of the launch (drained by outlier_exact_kernel), or null
+    unsigned int* gq_count;        // [0] entries requested, [1] end of the entries that were written (first refused request)
+    unsigned int gq_cap;
     float* dbg_median; float* dbg_q1; float* dbg_q3; int* dbg_nout;
 };
 
@@ -954,22 +957,36 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
     const bool dirty = owner && !clean;
     const unsigned db = __ballot_sync(0xffffffffu, dirty);
     if (db) {
+        // Uncertified pixels go to the launch's global queue, finished by outlier_exact_kernel right after this kernel: the
+        // exact path (half of this kernel's code) then never enters the instruction stream of the streaming loop. If the
+        // queue is full (or absent) the warp falls back to its shared-memory queue and drains it in place.
         const int nd = __popc(db);
-        if (qcount + nd > kQueueCap) {  // make room: drain full batches
+        unsigned int gbase = 0;
+        bool to_global = false;
+        if (a.gq) {
+            if (lane == 0) gbase = atomicAdd(a.gq_count, (unsigned int)nd);
+            gbase = __shfl_sync(0xffffffffu, gbase, 0);
+            to_global = gbase + (unsigned int)nd <= a.gq_cap;
+            if (!to_global && lane == 0) atomicMin(a.gq_count + 1, gbase);
+        }
+        if (!to_global && qcount + nd > kQueueCap) {  // make room: drain full batches
             __syncwarp();
             while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
             __syncwarp();
         }
         if (dirty) {
-            QueueEntry& e = queue[qcount + __popc(db & ((1u << lane) - 1u))];
+            const int rank = __popc(db & ((1u << lane) - 1u));
+            QueueEntry& e = to_global ? a.gq[gbase + rank] : queue[qcount + rank];
             e.pix = pix;
 #pragma unroll
             for (int c = 0; c < 4; c++) { e.median[c] = acc.median(c); e.iqr_inv[c] = acc.iqr_inv(c); e.sum[c] = acc.sum(c); }
         }
-        qcount += nd;
-        __syncwarp();
-        while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
-        __syncwarp();
+        if (!to_global) {
+            qcount += nd;
+            __syncwarp();
+            while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
+            __syncwarp();
+        }
     }
 }
 
@@ -1133,6 +1150,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     if (hcount > 0) drain_hard<C, WPL, G, MODE>(a, hq, hcount, lane, cap, pad, queue, qcount, acc_slot);
     __syncwarp();
     if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
+}
+
+// Second launch of a compositing call: the queued pixels, 32 per warp.
+template <int C>
+__global__ void __launch_bounds__(256) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
+    const unsigned int total = min(a.gq_count[0], a.gq_count[1]);  // requests that did not fit were finished in place
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < total; base += n_warps * 32u)
+        drain_queue<C>(a, a.gq + base, (int)min(32u, total - base), lane);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 chrono-video
