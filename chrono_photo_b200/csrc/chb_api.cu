@@ -84,7 +84,8 @@ struct Band {
     int v_cap_windows = 0;
     unsigned long long* d_vwarn = nullptr;
     int vwarn_cap = 0;
-    QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters
+    QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters ([0..1] exact, [2..3] iterative tier)
+    long long* d_hqueue = nullptr;        // iterative-tier queue (pixel indices)
     unsigned int* d_qcount = nullptr;
     unsigned int queue_cap = 0;
     VideoQueueEntry* d_vqueue = nullptr;  // exact-path queue of a chunk + its counter
@@ -189,7 +190,7 @@ static void free_band(Band& b) {
         if (b.v_done[s]) cudaEventDestroy(b.v_done[s]);
         if (b.v_copied[s]) cudaEventDestroy(b.v_copied[s]);
     }
-    cudaFree(b.d_vwarn); cudaFree(b.d_vqueue); cudaFree(b.d_vqcount); cudaFree(b.d_queue); cudaFree(b.d_qcount);
+    cudaFree(b.d_vwarn); cudaFree(b.d_vqueue); cudaFree(b.d_vqcount); cudaFree(b.d_queue); cudaFree(b.d_hqueue); cudaFree(b.d_qcount);
 }
 
 extern "C" int chb_stack_destroy(chb_stack* st) {
@@ -446,6 +447,24 @@ struct Variant { int wpl, g; };
 static const Variant kVariants[] = {{1, 1}, {2, 1}, {4, 1}, {8, 1}, {13, 1}, {7, 2}, {8, 2}, {8, 4}, {16, 4}, {8, 8}, {8, 16}, {8, 32}};
 static constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
+template <int C, int GENERIC>
+static OutlierKernel hard_kernel_for(int v) {
+    switch (v) {
+        case 0: return outlier_hard_kernel<C, 1, 1, GENERIC>;
+        case 1: return outlier_hard_kernel<C, 2, 1, GENERIC>;
+        case 2: return outlier_hard_kernel<C, 4, 1, GENERIC>;
+        case 3: return outlier_hard_kernel<C, 8, 1, GENERIC>;
+        case 4: return outlier_hard_kernel<C, 13, 1, GENERIC>;
+        case 5: return outlier_hard_kernel<C, 7, 2, GENERIC>;
+        case 6: return outlier_hard_kernel<C, 8, 2, GENERIC>;
+        case 7: return outlier_hard_kernel<C, 8, 4, GENERIC>;
+        case 8: return outlier_hard_kernel<C, 16, 4, GENERIC>;
+        case 9: return outlier_hard_kernel<C, 8, 8, GENERIC>;
+        case 10: return outlier_hard_kernel<C, 8, 16, GENERIC>;
+        default: return outlier_hard_kernel<C, 8, 32, GENERIC>;
+    }
+}
+
 template <int C, int GENERIC>  // GENERIC here is the kernel MODE: 0 generic, 1 absolute, 2 relative thresholds
 static OutlierKernel kernel_for(int v) {
     switch (v) {
@@ -578,6 +597,9 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     OutlierKernel kern;
     if (st->C == 3) kern = kmode == 0 ? kernel_for<3, 0>(vidx) : (kmode == 1 ? kernel_for<3, 1>(vidx) : kernel_for<3, 2>(vidx));
     else kern = kmode == 0 ? kernel_for<4, 0>(vidx) : (kmode == 1 ? kernel_for<4, 1>(vidx) : kernel_for<4, 2>(vidx));
+    OutlierKernel hard_kern;
+    if (st->C == 3) hard_kern = kmode == 0 ? hard_kernel_for<3, 0>(vidx) : (kmode == 1 ? hard_kernel_for<3, 1>(vidx) : hard_kernel_for<3, 2>(vidx));
+    else hard_kern = kmode == 0 ? hard_kernel_for<4, 0>(vidx) : (kmode == 1 ? hard_kernel_for<4, 1>(vidx) : hard_kernel_for<4, 2>(vidx));
 
     // fingerprint of the device-side tables of this call
     std::vector<uint8_t> blob;
@@ -607,14 +629,18 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         if (!b.d_queue) {  // a quarter of the band's pixels (at most 4 M entries); the rest would be finished inside the main kernel
             b.queue_cap = (unsigned int)std::min<long long>(4LL << 20, std::max<long long>(1 << 16, b.n_pixels / 4));
             CU(cudaMalloc(&b.d_queue, sizeof(QueueEntry) * (size_t)b.queue_cap));
-            CU(cudaMalloc(&b.d_qcount, 2 * sizeof(unsigned int)));
+            CU(cudaMalloc(&b.d_hqueue, sizeof(long long) * (size_t)b.queue_cap));
+            CU(cudaMalloc(&b.d_qcount, 4 * sizeof(unsigned int)));
         }
-        CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(unsigned int), s));
-        CU(cudaMemsetAsync(b.d_qcount + 1, 0xff, sizeof(unsigned int), s));
+        {
+            static const unsigned int kInit[4] = {0u, 0xffffffffu, 0u, 0xffffffffu};
+            CU(cudaMemcpyAsync(b.d_qcount, kInit, sizeof kInit, cudaMemcpyHostToDevice, s));
+        }
         OutlierArgs ab = a;
         ab.gq = b.d_queue; ab.gq_count = b.d_qcount; ab.gq_cap = b.queue_cap;
-        if (const char* qc = getenv("CHB_QUEUE_CAP"))  // test aid: a small capacity exercises the in-place fallback
-            ab.gq_cap = (unsigned int)std::min<long long>(b.queue_cap, std::max<long long>(0, atoll(qc)));
+        ab.ghq = b.d_hqueue; ab.ghq_count = b.d_qcount + 2; ab.ghq_cap = b.queue_cap;
+        if (const char* qc = getenv("CHB_QUEUE_CAP"))  // test aid: a small capacity exercises the in-place fallbacks
+            ab.gq_cap = ab.ghq_cap = (unsigned int)std::min<long long>(b.queue_cap, std::max<long long>(0, atoll(qc)));
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
         ab.wmask = b.d_wmask; ab.smask = sub ? b.d_smask : nullptr; ab.win_frames = b.d_win;
@@ -649,9 +675,11 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         const int blocks = grid_for(n_tasks * 32, kWarpsPerCta * 32, d.sm_count, std::max(1, occ));
         CU(cudaEventRecord(b.ev0, s));
         kern<<<blocks, kWarpsPerCta * 32, smem, s>>>(ab);
+        CU(cudaFuncSetAttribute(hard_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        hard_kern<<<blocks, kWarpsPerCta * 32, smem, s>>>(ab);
         if (st->C == 3) outlier_exact_kernel<3><<<d.sm_count * 4, 256, 0, s>>>(ab);
         else outlier_exact_kernel<4><<<d.sm_count * 4, 256, 0, s>>>(ab);
-        g_launches += 2;
+        g_launches += 3;
         CU(cudaGetLastError());
         CU(cudaEventRecord(b.ev1, s));
         CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));

@@ -121,6 +121,9 @@ struct OutlierArgs {
     struct QueueEntry* gq;         // global exact-path queue of the launch (drained by outlier_exact_kernel), or null
     unsigned int* gq_count;        // [0] entries requested, [1] end of the entries that were written (first refused request)
     unsigned int gq_cap;
+    long long* ghq;                // global queue of the pixels for the iterative tier (outlier_hard_kernel), or null
+    unsigned int* ghq_count;       // [0] requested, [1] end of the written entries
+    unsigned int ghq_cap;
     float* dbg_median; float* dbg_q1; float* dbg_q3; int* dbg_nout;
 };
 
@@ -1133,15 +1136,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
         const bool hard = owner && to_hard;
         const unsigned hb = __ballot_sync(0xffffffffu, hard);
         if (hb) {
-            if (hard) hq[hcount + __popc(hb & ((1u << lane) - 1u))] = pix;
-            hcount += __popc(hb);
-            if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(hb));
-            __syncwarp();
-            while (hcount >= PPW) {
-                drain_hard<C, WPL, G, MODE>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount, acc_slot);
-                hcount -= PPW;
+            // they go to the launch's global queue (outlier_hard_kernel runs the solver on them right after this kernel, so
+            // its code stays out of this loop); only a full queue makes the warp solve them in place
+            const int nh = __popc(hb);
+            if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)nh);
+            unsigned int gbase = 0;
+            bool to_global = false;
+            if (a.ghq) {
+                if (lane == 0) gbase = atomicAdd(a.ghq_count, (unsigned int)nh);
+                gbase = __shfl_sync(0xffffffffu, gbase, 0);
+                to_global = gbase + (unsigned int)nh <= a.ghq_cap;
+                if (!to_global && lane == 0) atomicMin(a.ghq_count + 1, gbase);
             }
-            __syncwarp();
+            if (hard) {
+                const int rank = __popc(hb & ((1u << lane) - 1u));
+                if (to_global) a.ghq[gbase + rank] = pix;
+                else hq[hcount + rank] = pix;
+            }
+            if (!to_global) {
+                hcount += nh;
+                __syncwarp();
+                while (hcount >= PPW) {
+                    drain_hard<C, WPL, G, MODE>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount, acc_slot);
+                    hcount -= PPW;
+                }
+                __syncwarp();
+            }
         }
         finish_pixel<C>(a, acc, pix, p, owner && !to_hard, lane, queue, qcount);
         task += n_warps;
@@ -1152,7 +1172,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
 }
 
-// Second launch of a compositing call: the queued pixels, 32 per warp.
+// Second launch of a compositing call: the pixels queued for the iterative tier, 32/G per warp pass; what their certificate
+// cannot clear moves on to the exact-path queue.
+template <int C, int WPL, int G, int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_hard_kernel(const __grid_constant__ OutlierArgs a) {
+    constexpr int PPW = 32 / G;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    const int cap = 4 * WPL * 4 * G, pad = cap - a.n_sub;
+    QueueEntry* const queue = reinterpret_cast<QueueEntry*>(smem_raw) + warp_in_cta * kQueueCap;
+    const uint32_t acc_slot = smem_u32(smem_raw + kQueueBytes + kHardBytes + kBarBytes) + threadIdx.x * 4;
+    const unsigned int total = min(a.ghq_count[0], a.ghq_count[1]);  // requests that did not fit were solved in place
+    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+    int qcount = 0;
+    for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PPW; base < total; base += n_warps * PPW)
+        drain_hard<C, WPL, G, MODE>(a, a.ghq + base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, queue, qcount, acc_slot);
+    __syncwarp();
+    if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
+}
+
+// Last launch of a compositing call: the queued pixels, 32 per warp.
 template <int C>
 __global__ void __launch_bounds__(256) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
     const unsigned int total = min(a.gq_count[0], a.gq_count[1]);  // requests that did not fit were finished in place
