@@ -87,7 +87,6 @@ struct Band {
     QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters ([0..1] exact, [2..3] iterative tier)
     long long* d_hqueue = nullptr;        // iterative-tier queue (pixel indices)
     unsigned int* d_qcount = nullptr;
-    unsigned int queue_cap = 0;
     VideoQueueEntry* d_vqueue = nullptr;  // exact-path queue of a chunk + its counter
     unsigned int* d_vqcount = nullptr;
     cudaEvent_t v_done[2] = {nullptr, nullptr};    // kernel writing slot s finished
@@ -626,21 +625,15 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
         }
         CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
-        if (!b.d_queue) {  // a quarter of the band's pixels (at most 4 M entries); the rest would be finished inside the main kernel
-            b.queue_cap = (unsigned int)std::min<long long>(4LL << 20, std::max<long long>(1 << 16, b.n_pixels / 4));
-            CU(cudaMalloc(&b.d_queue, sizeof(QueueEntry) * (size_t)b.queue_cap));
-            CU(cudaMalloc(&b.d_hqueue, sizeof(long long) * (size_t)b.queue_cap));
-            CU(cudaMalloc(&b.d_qcount, 4 * sizeof(unsigned int)));
+        if (!b.d_queue) {  // one slot per pixel: the queues of the iterative tier and of the exact path cannot overflow
+            CU(cudaMalloc(&b.d_queue, sizeof(QueueEntry) * (size_t)b.n_pixels));
+            CU(cudaMalloc(&b.d_hqueue, sizeof(long long) * (size_t)b.n_pixels));
+            CU(cudaMalloc(&b.d_qcount, 2 * sizeof(unsigned int)));
         }
-        {
-            static const unsigned int kInit[4] = {0u, 0xffffffffu, 0u, 0xffffffffu};
-            CU(cudaMemcpyAsync(b.d_qcount, kInit, sizeof kInit, cudaMemcpyHostToDevice, s));
-        }
+        CU(cudaMemsetAsync(b.d_qcount, 0, 2 * sizeof(unsigned int), s));
         OutlierArgs ab = a;
-        ab.gq = b.d_queue; ab.gq_count = b.d_qcount; ab.gq_cap = b.queue_cap;
-        ab.ghq = b.d_hqueue; ab.ghq_count = b.d_qcount + 2; ab.ghq_cap = b.queue_cap;
-        if (const char* qc = getenv("CHB_QUEUE_CAP"))  // test aid: a small capacity exercises the in-place fallbacks
-            ab.gq_cap = ab.ghq_cap = (unsigned int)std::min<long long>(b.queue_cap, std::max<long long>(0, atoll(qc)));
+        ab.gq = b.d_queue; ab.gq_count = b.d_qcount;
+        ab.ghq = b.d_hqueue; ab.ghq_count = b.d_qcount + 1;
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
         ab.wmask = b.d_wmask; ab.smask = sub ? b.d_smask : nullptr; ab.win_frames = b.d_win;

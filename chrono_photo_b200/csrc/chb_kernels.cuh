@@ -118,12 +118,10 @@ struct OutlierArgs {
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
     unsigned long long* counters;  // [0] warnings (all-outlier pixels), [1] pixels on the exact path, [2] pixels on the iterative (hard) path
-    struct QueueEntry* gq;         // global exact-path queue of the launch (drained by outlier_exact_kernel), or null
-    unsigned int* gq_count;        // [0] entries requested, [1] end of the entries that were written (first refused request)
-    unsigned int gq_cap;
-    long long* ghq;                // global queue of the pixels for the iterative tier (outlier_hard_kernel), or null
-    unsigned int* ghq_count;       // [0] requested, [1] end of the written entries
-    unsigned int ghq_cap;
+    struct QueueEntry* gq;         // exact-path queue of the launch, one slot per pixel of the band (outlier_exact_kernel drains it)
+    unsigned int* gq_count;
+    long long* ghq;                // queue of the pixels for the iterative tier (outlier_hard_kernel), one slot per pixel
+    unsigned int* ghq_count;
     float* dbg_median; float* dbg_q1; float* dbg_q3; int* dbg_nout;
 };
 
@@ -750,14 +748,11 @@ struct QueueEntry {
     float iqr_inv[4];
     uint32_t sum[4];
 };
-constexpr int kQueueBytes = kWarpsPerCta * kQueueCap * (int)sizeof(QueueEntry);
-constexpr int kHardBytes = kWarpsPerCta * kQueueCap * (int)sizeof(long long);
 constexpr int kBarBytes = 128;
 constexpr int kAccBytes = kWarpsPerCta * 32 * 12 * 4;
-// dynamic shared memory of one CTA: exact-path queues, hard-pixel queues, one mbarrier per warp, per-thread result slots,
-// one staged pixel-band per warp (G == 1: the tile's contiguous slab; G > 1: every lane's own units, [slot][lane])
+// dynamic shared memory of one CTA: one mbarrier per warp, per-thread result slots, one staged pixel-band per warp (G == 1: the tile's contiguous slab; G > 1: every lane's own units, [slot][lane])
 __host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) {
-    return kQueueBytes + kHardBytes + kBarBytes + kAccBytes + kWarpsPerCta * wpl * 512;  // g == 1: one slab per warp; g > 1: wpl units per lane
+    return kBarBytes + kAccBytes + kWarpsPerCta * wpl * 512;  // g == 1: one slab per warp; g > 1: wpl units per lane
 }
 
 template <int C>
@@ -931,10 +926,9 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
     }
 }
 
-// Certified pixels are written from registers; the others are appended to the warp's exact-path queue.
+// Certified pixels are written from registers; the others are appended to the launch's exact-path queue.
 template <int C>
-__device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAcc& acc, long long pix, int p_in_tile, bool owner, int lane,
-                                             QueueEntry* queue, int& qcount) {
+__device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAcc& acc, long long pix, int p_in_tile, bool owner, int lane) {
     const bool clean = acc.bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
     if (owner && clean) {
         uint8_t pixel[4] = {0, 0, 0, 0};
@@ -957,46 +951,26 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
         store_pixel<C>(a, pix, pixel, 0);
         if (a.dbg_nout) a.dbg_nout[pix] = 0;
     }
+    // Uncertified pixels go to the launch's global queue (one slot per pixel of the band, so it cannot overflow) and are
+    // finished by outlier_exact_kernel right after: the exact path never enters this kernel's instruction stream.
     const bool dirty = owner && !clean;
     const unsigned db = __ballot_sync(0xffffffffu, dirty);
     if (db) {
-        // Uncertified pixels go to the launch's global queue, finished by outlier_exact_kernel right after this kernel: the
-        // exact path (half of this kernel's code) then never enters the instruction stream of the streaming loop. If the
-        // queue is full (or absent) the warp falls back to its shared-memory queue and drains it in place.
-        const int nd = __popc(db);
         unsigned int gbase = 0;
-        bool to_global = false;
-        if (a.gq) {
-            if (lane == 0) gbase = atomicAdd(a.gq_count, (unsigned int)nd);
-            gbase = __shfl_sync(0xffffffffu, gbase, 0);
-            to_global = gbase + (unsigned int)nd <= a.gq_cap;
-            if (!to_global && lane == 0) atomicMin(a.gq_count + 1, gbase);
-        }
-        if (!to_global && qcount + nd > kQueueCap) {  // make room: drain full batches
-            __syncwarp();
-            while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
-            __syncwarp();
-        }
+        if (lane == 0) gbase = atomicAdd(a.gq_count, (unsigned int)__popc(db));
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
         if (dirty) {
-            const int rank = __popc(db & ((1u << lane) - 1u));
-            QueueEntry& e = to_global ? a.gq[gbase + rank] : queue[qcount + rank];
+            QueueEntry& e = a.gq[gbase + __popc(db & ((1u << lane) - 1u))];
             e.pix = pix;
 #pragma unroll
             for (int c = 0; c < 4; c++) { e.median[c] = acc.median(c); e.iqr_inv[c] = acc.iqr_inv(c); e.sum[c] = acc.sum(c); }
-        }
-        if (!to_global) {
-            qcount += nd;
-            __syncwarp();
-            while (qcount >= 32) { drain_queue<C>(a, queue + (qcount - 32), 32, lane); qcount -= 32; }
-            __syncwarp();
         }
     }
 }
 
 // Hard pixels, 32/G at a time: each pixel group reloads its own bands (L2) and runs the iterative solver.
 template <int C, int WPL, int G, int MODE>
-__device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* hq, int count, int lane, int cap, int pad, QueueEntry* queue, int& qcount,
-                                         uint32_t acc_slot) {
+__device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* hq, int count, int lane, int cap, int pad, uint32_t acc_slot) {
     constexpr int W4 = 4 * WPL;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
     const int j = lane / (32 / G), pl = lane % (32 / G);
@@ -1020,7 +994,7 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* h
         }
         process_band<C, WPL, G, MODE, false>(a, A, c, j, pix, active && j == 0, cap, pad, acc);
     }
-    finish_pixel<C>(a, acc, pix, p, active && j == 0, lane, queue, qcount);
+    finish_pixel<C>(a, acc, pix, p, active && j == 0, lane);
 }
 
 template <int C, int WPL, int G, int MODE>
@@ -1042,13 +1016,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     const int n_tasks = (int)(a.n_tiles * G);  // the host keeps n_tiles * G below 2^31
     const int cap = W4 * 4 * G;     // bytes per pixel-band across the G lanes
     const int pad = cap - a.n_sub;  // zero bytes that take part in the selection
-    QueueEntry* const queue = reinterpret_cast<QueueEntry*>(smem_raw) + warp_in_cta * kQueueCap;
-    long long* const hq = reinterpret_cast<long long*>(smem_raw + kQueueBytes) + warp_in_cta * kQueueCap;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + kQueueBytes + kHardBytes) + warp_in_cta;
-    const uint32_t acc_slot = smem_u32(smem_raw + kQueueBytes + kHardBytes + kBarBytes) + threadIdx.x * 4;
-    uint8_t* const stage = smem_raw + kQueueBytes + kHardBytes + kBarBytes + kAccBytes + warp_in_cta * (WPL * 512);
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw) + warp_in_cta;
+    const uint32_t acc_slot = smem_u32(smem_raw + kBarBytes) + threadIdx.x * 4;
+    uint8_t* const stage = smem_raw + kBarBytes + kAccBytes + warp_in_cta * (WPL * 512);
     const uint32_t stage_lane = smem_u32(stage) + j * kRowBytes + pl * 16;  // this lane's 16 bytes of row (slot * G + j)
-    int qcount = 0, hcount = 0;
     const int staged_groups = a.n_groups < WPL * G ? a.n_groups : WPL * G;
     uint32_t parity = 0;
     if (kStage) {
@@ -1136,40 +1107,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
         const bool hard = owner && to_hard;
         const unsigned hb = __ballot_sync(0xffffffffu, hard);
         if (hb) {
-            // they go to the launch's global queue (outlier_hard_kernel runs the solver on them right after this kernel, so
-            // its code stays out of this loop); only a full queue makes the warp solve them in place
+            // they go to the launch's global queue (one slot per pixel of the band): outlier_hard_kernel runs the solver on
+            // them right after this kernel, so its code stays out of this loop
             const int nh = __popc(hb);
-            if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)nh);
             unsigned int gbase = 0;
-            bool to_global = false;
-            if (a.ghq) {
-                if (lane == 0) gbase = atomicAdd(a.ghq_count, (unsigned int)nh);
-                gbase = __shfl_sync(0xffffffffu, gbase, 0);
-                to_global = gbase + (unsigned int)nh <= a.ghq_cap;
-                if (!to_global && lane == 0) atomicMin(a.ghq_count + 1, gbase);
+            if (lane == 0) {
+                atomicAdd(a.counters + 2, (unsigned long long)nh);
+                gbase = atomicAdd(a.ghq_count, (unsigned int)nh);
             }
-            if (hard) {
-                const int rank = __popc(hb & ((1u << lane) - 1u));
-                if (to_global) a.ghq[gbase + rank] = pix;
-                else hq[hcount + rank] = pix;
-            }
-            if (!to_global) {
-                hcount += nh;
-                __syncwarp();
-                while (hcount >= PPW) {
-                    drain_hard<C, WPL, G, MODE>(a, hq + (hcount - PPW), PPW, lane, cap, pad, queue, qcount, acc_slot);
-                    hcount -= PPW;
-                }
-                __syncwarp();
-            }
+            gbase = __shfl_sync(0xffffffffu, gbase, 0);
+            if (hard) a.ghq[gbase + __popc(hb & ((1u << lane) - 1u))] = pix;
         }
-        finish_pixel<C>(a, acc, pix, p, owner && !to_hard, lane, queue, qcount);
+        finish_pixel<C>(a, acc, pix, p, owner && !to_hard, lane);
         task += n_warps;
     }
-    __syncwarp();
-    if (hcount > 0) drain_hard<C, WPL, G, MODE>(a, hq, hcount, lane, cap, pad, queue, qcount, acc_slot);
-    __syncwarp();
-    if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
 }
 
 // Second launch of a compositing call: the pixels queued for the iterative tier, 32/G per warp pass; what their certificate
@@ -1178,23 +1129,19 @@ template <int C, int WPL, int G, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_hard_kernel(const __grid_constant__ OutlierArgs a) {
     constexpr int PPW = 32 / G;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int cap = 4 * WPL * 4 * G, pad = cap - a.n_sub;
-    QueueEntry* const queue = reinterpret_cast<QueueEntry*>(smem_raw) + warp_in_cta * kQueueCap;
-    const uint32_t acc_slot = smem_u32(smem_raw + kQueueBytes + kHardBytes + kBarBytes) + threadIdx.x * 4;
-    const unsigned int total = min(a.ghq_count[0], a.ghq_count[1]);  // requests that did not fit were solved in place
+    const uint32_t acc_slot = smem_u32(smem_raw + kBarBytes) + threadIdx.x * 4;
+    const unsigned int total = a.ghq_count[0];
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
-    int qcount = 0;
     for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PPW; base < total; base += n_warps * PPW)
-        drain_hard<C, WPL, G, MODE>(a, a.ghq + base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, queue, qcount, acc_slot);
-    __syncwarp();
-    if (qcount > 0) drain_queue<C>(a, queue, qcount, lane);
+        drain_hard<C, WPL, G, MODE>(a, a.ghq + base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, acc_slot);
 }
 
 // Last launch of a compositing call: the queued pixels, 32 per warp.
 template <int C>
 __global__ void __launch_bounds__(256) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
-    const unsigned int total = min(a.gq_count[0], a.gq_count[1]);  // requests that did not fit were finished in place
+    const unsigned int total = a.gq_count[0];
     const int lane = threadIdx.x & 31;
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < total; base += n_warps * 32u)
