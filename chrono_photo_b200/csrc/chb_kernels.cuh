@@ -740,6 +740,12 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center,
 #ifndef CHB_MINB
 #define CHB_MINB 2
 #endif
+#ifndef CHB_HARD_MINB
+#define CHB_HARD_MINB 2
+#endif
+#ifndef CHB_EXACT_MINB
+#define CHB_EXACT_MINB 4
+#endif
 constexpr int kWarpsPerCta = CHB_WARPS;
 constexpr int kQueueCap = 64;  // per warp
 struct QueueEntry {
@@ -1126,7 +1132,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
 // Second launch of a compositing call: the pixels queued for the iterative tier, 32/G per warp pass; what their certificate
 // cannot clear moves on to the exact-path queue.
 template <int C, int WPL, int G, int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_hard_kernel(const __grid_constant__ OutlierArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard_kernel(const __grid_constant__ OutlierArgs a) {
     constexpr int PPW = 32 / G;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -1140,7 +1146,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_hard_kern
 
 // Last launch of a compositing call: the queued pixels, 32 per warp.
 template <int C>
-__global__ void __launch_bounds__(256) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
+__global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
     const unsigned int total = a.gq_count[0];
     const int lane = threadIdx.x & 31;
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
