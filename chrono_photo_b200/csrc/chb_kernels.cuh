@@ -1144,6 +1144,128 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard
         drain_hard<C, WPL, G, MODE>(a, a.ghq + base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, acc_slot);
 }
 
+// Iterative tier for long whole-stack series (hundreds of frames): instead of the solver's repeated passes over the pixel's
+// registers, one warp per queued pixel builds a 256-bin histogram of a band in shared memory (one shared-memory atomic per
+// sample) and reads every order statistic the band needs -- median pair, quartile pairs, smallest and largest sample --
+// off one warp-wide prefix sum (lane l owns bins 8l .. 8l+7). The certificate term uses the exact max |x - centre|.
+template <int C>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const __grid_constant__ OutlierArgs a) {
+    __shared__ __align__(16) uint32_t hist_all[kWarpsPerCta][256];
+    __shared__ uint32_t acc_words[kAccWords * kWarpsPerCta * 32];
+    const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    uint32_t* const hist = hist_all[warp_in_cta];
+    for (int b = lane; b < 256; b += 32) hist[b] = 0;
+    __syncwarp();
+    const unsigned int total = a.ghq_count[0];
+    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool rel = !a.absolute;
+    for (unsigned int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < total; idx += n_warps) {
+        const long long pix = a.ghq[idx];
+        const long long tile = pix >> 5;
+        const int p = (int)(pix & 31);
+        PixelAcc acc;
+        acc.slot = smem_u32(acc_words) + threadIdx.x * 4;
+        acc.reset();
+#pragma unroll 1
+        for (int c = 0; c < C; c++) {
+            const float w = a.w[c];
+            const uint8_t* ub = a.stack + tile * tile_bytes(C, a.NG) + (((long long)c * a.NG + a.g0) * kTilePixels + p) * kUnitBytes;
+            const bool need = (a.bg == 2 || w != 0.0f);
+            uint32_t first = 0;
+            for (int g = lane; g < a.n_groups; g += 32) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(ub + (long long)g * (kTilePixels * kUnitBytes)));
+                if (g == 0) first = v.x & 0xffu;  // window position 0 (whole-stack launch: frame 0)
+                if (need) {
+                    const int left = a.n - g * kGroupFrames;  // frames of this group that exist (the rest are zero padding)
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (4 * q + k < left) atomicAdd(&hist[(wv[q] >> (8 * k)) & 0xffu], 1u);
+                    }
+                }
+            }
+            first = __shfl_sync(0xffffffffu, first, 0);
+            acc.first_px |= first << (8 * c);
+            __syncwarp();
+            if (!need) continue;
+            // ---- this lane's eight bins, then the warp-wide prefix sum
+            uint32_t h[8];
+            {
+                const uint4 h0 = *reinterpret_cast<const uint4*>(hist + 8 * lane), h1 = *reinterpret_cast<const uint4*>(hist + 8 * lane + 4);
+                h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+                *reinterpret_cast<uint4*>(hist + 8 * lane) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(hist + 8 * lane + 4) = make_uint4(0, 0, 0, 0);
+            }
+            uint32_t lane_tot = 0, lane_sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { lane_tot += h[k]; lane_sum += (uint32_t)(8 * lane + k) * h[k]; }
+            uint32_t incl = lane_tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t excl = incl - lane_tot;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lane_sum += __shfl_xor_sync(0xffffffffu, lane_sum, o);
+            acc.set_sum(c, lane_sum);
+            __syncwarp();
+            if (w == 0.0f) continue;
+            auto stat = [&](int r) {  // the sample of 0-based rank r: the first bin whose cumulative count exceeds r
+                const unsigned m = __ballot_sync(0xffffffffu, incl > (uint32_t)r);
+                const int src = __ffs(m) - 1;
+                uint32_t cum = excl;
+                int val = -1;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    cum += h[k];
+                    if (val < 0 && cum > (uint32_t)r) val = 8 * lane + k;
+                }
+                return __shfl_sync(0xffffffffu, val, src);
+            };
+            const int mlo = stat(a.rk[2]);
+            const int mhi = (a.rk[3] == a.rk[2]) ? mlo : stat(a.rk[3]);
+            const float med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
+            const int center = (mlo + mhi) >> 1;
+            const float halfw = med - (float)center;
+            float iqi = 0.0f;
+            if (rel) {  // quartiles (src/chrono.rs:559-579) and inverse IQR (:246-252)
+                const int q1a = stat(a.rk[0]), q3a = stat(a.rk[4]);
+                const int q1b = (a.rk[0] == a.rk[1]) ? q1a : stat(a.rk[1]);
+                const int q3b = (a.rk[4] == a.rk[5]) ? q3a : stat(a.rk[5]);
+                const float q1 = (a.rk[0] == a.rk[1]) ? (float)q1a : (1.0f - a.q1_frac) * (float)q1a + a.q1_frac * (float)q1b;
+                const float q3 = (a.rk[4] == a.rk[5]) ? (float)q3a : (1.0f - a.q3_frac) * (float)q3a + a.q3_frac * (float)q3b;
+                float iq = q3 - q1;
+                if (iq == 0.0f) iq = 1.0f;
+                iqi = 1.0f / iq;
+            }
+            acc.set_median(c, med);
+            acc.set_iqr_inv(c, iqi);
+            if (!(w < 0.0f)) {  // exact max |x - centre| from the smallest and the largest sample
+                const unsigned nz = __ballot_sync(0xffffffffu, lane_tot > 0);
+                int my_lo = 8 * lane + 7, my_hi = 8 * lane;
+#pragma unroll
+                for (int k = 7; k >= 0; k--)
+                    if (h[k] > 0) my_lo = 8 * lane + k;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (h[k] > 0) my_hi = 8 * lane + k;
+                const int minv = __shfl_sync(0xffffffffu, my_lo, __ffs(nz) - 1);
+                const int maxv = __shfl_sync(0xffffffffu, my_hi, 31 - __clz(nz));
+                const int odev = max(center - minv, maxv - center);
+                const float aw = a.absolute ? w : w * iqi;
+                const float t = aw * ((float)odev + halfw);
+                acc.bound += t * t;
+            }
+        }
+        __syncwarp();
+        finish_pixel<C>(a, acc, pix, p, lane == 0, lane);
+        __syncwarp();
+    }
+}
+
 // Last launch of a compositing call: the queued pixels, 32 per warp.
 template <int C>
 __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {

@@ -355,6 +355,23 @@ def test_config5_chrono_video_with_shake_crop(ctx):
     fs.close()
 
 
+def test_long_series_histogram_tier(ctx, monkeypatch):
+    # whole-stack series of >= 256 frames send the iterative tier through the shared-memory histogram kernel; shorter ones
+    # (and CHB_HIST=0) through the solver. Both must equal the oracle: iid bytes (every pixel), objects, flat bands, RGBA.
+    rng = np.random.default_rng(21)
+    uni = rng.integers(0, 256, size=(300, 6, 64, 3), dtype=np.uint8)
+    objs = make_stack(rng, 520, 8, 40, 3, n_obj=80, noise=9)
+    flat = np.full((256, 4, 32, 3), 255, np.uint8)
+    flat[::7, :, :5] = 0
+    rgba = make_stack(rng, 257, 5, 33, 4, n_obj=40, noise=12)
+    for force in ("1", "0"):
+        monkeypatch.setenv("CHB_HIST", force)
+        for st in (uni, objs, flat, rgba):
+            check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
+            check_outlier(ctx, st, (False, 3.0, 5.0), "average", "forward", weights=(1, 0.5, 0, 1))
+            check_outlier(ctx, st, (False, 1.0, 2.0), "median", "average", weights=(1, -0.5, 1, 0))
+
+
 def test_every_pixel_through_the_tier_queues(ctx):
     # pixels for the iterative tier and for the exact path travel through per-launch global queues (one slot per pixel) drained
     # by the follow-up kernels; iid bytes send EVERY pixel through both queues
