@@ -321,12 +321,17 @@ def main():
     sampler.start()
     ms_step, launches = timed_steps(stack, proc)
     clocks = sampler.stop()
-    launch_ms = [proc.process_device(stack) for _ in range(min(5, args.steps))]  # per-launch device time (CUDA events on the launching stream)
+    launch_ms, main_ms = [], []
+    for _ in range(min(5, args.steps)):  # per-call device time (CUDA events on the launching stream)
+        launch_ms.append(proc.process_device(stack))
+        main_ms.append(float(_lib.lib().chb_last_main_kernel_ms()) if is_outlier else launch_ms[-1])
     kernel_ms = max_over_ranks(sum(launch_ms) / len(launch_ms))
+    main_kernel_ms = max_over_ranks(sum(main_ms) / len(main_ms))
     total_pf = float(n) * H * W
     value = total_pf / (ms_step / 1e3)
 
-    # ---- roofline of the dominant kernel (algorithmic bytes of this rank's shard / its average launch duration)
+    # ---- roofline (algorithmic bytes of this rank's shard). The headline fraction is taken over the WHOLE call -- the streaming
+    # kernel plus the two tier kernels that finish the queued pixels -- and the dominant (streaming) kernel is reported beside it.
     P_shard = rows * W
     alg_bytes = P_shard * 3 * (n + (2 if is_outlier else 1))  # read the stack once + composite (+ mask) write
     peak, peak_src = peaks()
@@ -334,8 +339,13 @@ def main():
     kernel_name = "outlier_kernel" if is_outlier else "simple_int_kernel"
     traffic = traffic_from_profiles(kernel_name + ":" + wl) if n_gpus == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "peak_source": peak_src,
+                "kernel": (kernel_name + " + outlier_hard_kernel|outlier_hist_kernel + outlier_exact_kernel (one call)") if is_outlier else kernel_name,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "peak_source": peak_src,
                 "slow_path_pixels_per_launch": int(_lib.lib().chb_last_slow_pixels()) if is_outlier else 0}
+    if is_outlier:
+        dom = alg_bytes / (main_kernel_ms / 1e3) / 1e9
+        roofline["dominant_kernel"] = {"kernel": kernel_name, "avg_launch_ms": main_kernel_ms, "achieved": dom, "frac": dom / peak,
+                                       "note": "streaming kernel alone (CUDA events around it inside the library): reads the whole stack, writes the certified pixels"}
 
     # ---- the workload's own image cut into N bands (strong scaling), reported beside the weak-scaling headline
     strong = None

@@ -66,6 +66,7 @@ SYMBOLS = {
     "chb_launch_count_reset": (None, []),
     "chb_last_slow_pixels": (C.c_uint64, []),
     "chb_last_hard_pixels": (C.c_uint64, []),
+    "chb_last_main_kernel_ms": (C.c_float, []),
     "chb_sample_positions": (_i, [C.c_uint64, _i, _i, _i32p]),
     "chb_threshold_new": (None, [_i, C.c_float, C.c_float, _f32p, _f32p, _f32p]),
     "chb_fade_build": (_i, [_i32p, _f32p, _i, _f32p, _i, _i32p]),

@@ -19,6 +19,7 @@ using namespace chb;
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 static thread_local uint64_t g_last_slow = 0, g_last_hard = 0;
+static thread_local float g_last_main_ms = 0.0f;
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const char* fmt, ...) {
@@ -42,6 +43,7 @@ extern "C" uint64_t chb_launch_count(void) { return g_launches.load(); }
 extern "C" void chb_launch_count_reset(void) { g_launches.store(0); }
 extern "C" uint64_t chb_last_slow_pixels(void) { return g_last_slow; }
 extern "C" uint64_t chb_last_hard_pixels(void) { return g_last_hard; }
+extern "C" float chb_last_main_kernel_ms(void) { return g_last_main_ms; }
 
 // ------------------------------------------------------------------------------------------------ objects
 struct Dev {
@@ -77,7 +79,7 @@ struct Band {
     unsigned long long* d_counters = nullptr;
     float *d_dbg_median = nullptr, *d_dbg_q1 = nullptr, *d_dbg_q3 = nullptr;
     int* d_dbg_nout = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;  // ev_mid: after the streaming kernel, before the tier kernels
     // chrono-video: two slots of window planes (composites, masks), per-window warning counters
     uint8_t* d_vout[2] = {nullptr, nullptr};
     uint8_t* d_vmask[2] = {nullptr, nullptr};
@@ -184,6 +186,7 @@ static void free_band(Band& b) {
     cudaFree(b.d_dbg_median); cudaFree(b.d_dbg_q1); cudaFree(b.d_dbg_q3); cudaFree(b.d_dbg_nout);
     if (b.ev0) cudaEventDestroy(b.ev0);
     if (b.ev1) cudaEventDestroy(b.ev1);
+    if (b.ev_mid) cudaEventDestroy(b.ev_mid);
     for (int s = 0; s < 2; s++) {
         cudaFree(b.d_vout[s]); cudaFree(b.d_vmask[s]);
         if (b.v_done[s]) cudaEventDestroy(b.v_done[s]);
@@ -668,6 +671,8 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         const int blocks = grid_for(n_tasks * 32, kWarpsPerCta * 32, d.sm_count, std::max(1, occ));
         CU(cudaEventRecord(b.ev0, s));
         kern<<<blocks, kWarpsPerCta * 32, smem, s>>>(ab);
+        if (!b.ev_mid) CU(cudaEventCreate(&b.ev_mid));
+        CU(cudaEventRecord(b.ev_mid, s));
         // iterative tier: long whole-stack series with relative thresholds (six ranks per band) use the histogram kernel -- one
         // shared-memory atomic per sample instead of the solver's repeated passes (measured on 1000 x UHD: 1.0 ms against
         // 1.7 ms; with absolute thresholds, two ranks, the solver's 0.6 ms wins). CHB_HIST=0 / 1 forces the choice (tests).
@@ -697,7 +702,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
 
 // Waits for the launches of every band and gathers timing, counters and debug planes.
 static int collect_outlier(chb_stack* st, const chb_debug_planes* dbg, float* kernel_ms, bool want_mask) {
-    float ms_max = 0.0f;
+    float ms_max = 0.0f, main_max = 0.0f;
     uint64_t warnings = 0, slow = 0, hard = 0;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
@@ -706,6 +711,11 @@ static int collect_outlier(chb_stack* st, const chb_debug_planes* dbg, float* ke
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
         ms_max = std::max(ms_max, ms);
+        if (b.ev_mid) {
+            float mm = 0.0f;
+            if (cudaEventElapsedTime(&mm, b.ev0, b.ev_mid) == cudaSuccess) main_max = std::max(main_max, mm);
+            else cudaGetLastError();
+        }
         warnings += st->h_counters[4 * b.dev_slot];
         slow += st->h_counters[4 * b.dev_slot + 1];
         hard += st->h_counters[4 * b.dev_slot + 2];
@@ -722,6 +732,7 @@ static int collect_outlier(chb_stack* st, const chb_debug_planes* dbg, float* ke
     st->last_warnings = warnings;
     g_last_slow = slow;
     g_last_hard = hard;
+    g_last_main_ms = main_max;
     return CHB_OK;
 }
 

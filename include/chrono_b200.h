@@ -181,7 +181,10 @@ int chb_outlier_video_device(chb_stack *stack, const chb_outlier_params *params,
 uint64_t chb_launch_count(void);
 void chb_launch_count_reset(void);
 uint64_t chb_last_slow_pixels(void);
-uint64_t chb_last_hard_pixels(void); /* pixels whose medians needed the iterative solver */
+uint64_t chb_last_hard_pixels(void);
+/* Device time (ms, max over devices) of the streaming kernel alone in the calling thread's last outlier call; the call's
+ * kernel_ms also covers the two tier kernels that follow it. */
+float chb_last_main_kernel_ms(void); /* pixels whose medians needed the iterative solver */
 
 /* The --sample subset the library draws for (seed, window length n, cnt): cnt ascending positions in [0, n).
  * Deterministic replacement of rand::seq::sample_indices (src/chrono.rs:157), exported so a checker can use the same set. */
