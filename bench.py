@@ -344,7 +344,8 @@ def main():
                 "slow_path_pixels_per_launch": int(_lib.lib().chb_last_slow_pixels()) if is_outlier else 0}
     if is_outlier:
         dom = alg_bytes / (main_kernel_ms / 1e3) / 1e9
-        roofline["dominant_kernel"] = {"kernel": kernel_name, "avg_launch_ms": main_kernel_ms, "achieved": dom, "frac": dom / peak,
+        roofline["traffic_kernel"] = kernel_name  # the ncu capture (profiles/roofline_traffic.json) is of the streaming kernel's launch
+        roofline["dominant_kernel"] = {"kernel": kernel_name, "avg_launch_ms": main_kernel_ms, "achieved": dom, "frac": dom / peak, "traffic": traffic,
                                        "note": "streaming kernel alone (CUDA events around it inside the library): reads the whole stack, writes the certified pixels"}
 
     # ---- the workload's own image cut into N bands (strong scaling), reported beside the weak-scaling headline
