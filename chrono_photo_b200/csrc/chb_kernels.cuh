@@ -592,8 +592,23 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         float pix_new[4], blend_inv = 1.0f;
 #pragma unroll
         for (int i = 0; i < 4; i++) pix_new[i] = (float)pixel[i];
+        // An outlier blended at full weight (blend >= 1) copies its sample, whatever the accumulator held, and its factor
+        // (1 - 1) zeroes blend_inv for good: everything the list holds before its LAST full-weight entry is dead. Without a
+        // fade (blend = blend_value, never above 1 and never NaN) a short walk from the end of the list looks for that entry
+        // and the chain starts there -- for an opaque object that is the list's last entry. Not found within 16 frames: the
+        // whole list is walked as written.
+        int t0 = 0;
+        if (a.fade.is_none) {
+            const int span = last_idx - first_idx;
+            for (int t = span; t >= 0 && t > span - 16; t--) {
+                const int s = (a.om == 4) ? first_idx + t : last_idx - t;
+                rd.fetch(frame_at(s), sample);
+                const float d = dist_sq_px(dc, sample);
+                if (d >= thr_sq && blend_value(a, sqrtf(d)) >= 1.0f) { t0 = t; break; }
+            }
+        }
         // only the span [first_idx, last_idx] holds outliers; in a contiguous window whole words without a candidate are skipped
-        for (int ss = first_idx; ss <= last_idx; ss++) {
+        for (int ss = first_idx + t0; ss <= last_idx; ss++) {
             const int s = (a.om == 4) ? ss : last_idx - (ss - first_idx);
             const int f = frame_at(s);
             if (contig_f0 >= 0) {
@@ -1178,11 +1193,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
                 if (need) {
                     const int left = a.n - g * kGroupFrames;  // frames of this group that exist (the rest are zero padding)
                     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                    if (left >= kGroupFrames) {  // a full group: sixteen samples, no per-sample test
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
+                        for (int q = 0; q < 4; q++) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if (4 * q + k < left) atomicAdd(&hist[(wv[q] >> (8 * k)) & 0xffu], 1u);
+                            for (int k = 0; k < 4; k++) atomicAdd(&hist[(wv[q] >> (8 * k)) & 0xffu], 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if (4 * q + k < left) atomicAdd(&hist[(wv[q] >> (8 * k)) & 0xffu], 1u);
+                        }
                     }
                 }
             }
@@ -1213,16 +1236,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
             acc.set_sum(c, lane_sum);
             __syncwarp();
             if (w == 0.0f) continue;
+            uint32_t cum[8];  // cumulative counts at this lane's bins
+            {
+                uint32_t run = excl;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { run += h[k]; cum[k] = run; }
+            }
             auto stat = [&](int r) {  // the sample of 0-based rank r: the first bin whose cumulative count exceeds r
                 const unsigned m = __ballot_sync(0xffffffffu, incl > (uint32_t)r);
                 const int src = __ffs(m) - 1;
-                uint32_t cum = excl;
-                int val = -1;
+                int val = 8 * lane;  // in the owning lane: its first bin + the number of its bins still at or below r
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    cum += h[k];
-                    if (val < 0 && cum > (uint32_t)r) val = 8 * lane + k;
-                }
+                for (int k = 0; k < 8; k++) val += (cum[k] <= (uint32_t)r);
                 return __shfl_sync(0xffffffffu, val, src);
             };
             const int mlo = stat(a.rk[2]);

@@ -383,6 +383,29 @@ def test_every_pixel_through_the_tier_queues(ctx):
         check_outlier(ctx, st, (False, 3.0, 5.0), "median", "forward")
 
 
+def test_forward_backward_chain_skips_only_dead_entries(ctx):
+    # forward / backward blending without a fade starts its chain at the LAST full-weight outlier of the list (everything
+    # before it is overwritten); the search looks at the last 16 list entries only. Series built to hit every branch: opaque
+    # objects at either end of the list, long tails (> 16 frames) of partial blends after / before them, partial blends only,
+    # and a fade (no shortcut). abs/0.05/0.2: distances of 12.75..51 (8..29 levels in each of three bands) blend partially, above that fully.
+    rng = np.random.default_rng(77)
+    n, h, w = 192, 6, 64
+    st = (100 + rng.integers(-2, 3, size=(n, h, w, 3))).astype(np.uint8)
+    st[10:20, 0] = 220                                             # opaque run only
+    st[10:20, 1] = 220; st[20:60, 1] = 115                         # opaque run, then a 40-frame partial tail (forward: not found)
+    st[50:90, 2] = 117; st[40:50, 2] = 10                          # opaque run before a partial tail of 40 (backward: found at once)
+    st[5:70:2, 3] = 114                                            # partial blends only
+    st[30:34, 4] = 230; st[34:44, 4] = 116; st[60, 4] = 240        # opaque, 10 partial, opaque again as the last entry
+    st[12, 5, :32] = 180; st[70, 5, 16:] = 20                      # one or two isolated opaque outliers
+    for om in ("forward", "backward"):
+        for bg in ("first", "median"):
+            check_outlier(ctx, st, (True, 0.05, 0.2), bg, om)
+            check_outlier(ctx, st, (False, 3.0, 9.0), bg, om)
+        check_outlier(ctx, st, (True, 0.05, 0.2), "first", om, fade=(0, True, [(0, 0.0), (191, 1.5)]))
+        check_outlier(ctx, st, (True, 0.05, 0.2), "first", om, indices=list(range(7, 181)))
+        check_outlier(ctx, st, (True, 0.05, 0.2), "first", om, indices=list(range(3, 190, 2)))
+
+
 # ---------------------------------------------------------------------------------------------------- chrono-video runs
 def _check_video_run(ctx, fs, st, first, wl, count, spec, bg, om, weights=(1, 1, 1, 1), fade=None, seed=5):
     t_gpu, t_orc = thr_pair(spec)
