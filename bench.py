@@ -254,6 +254,7 @@ def main():
     multi_proc = world > 1
     if multi_proc:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         devices, shard_rank, shard_world = [local_rank], rank, world
