@@ -88,6 +88,7 @@ struct Band {
     int vwarn_cap = 0;
     QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters ([0..1] exact, [2..3] iterative tier)
     long long* d_hqueue = nullptr;        // iterative-tier queue (pixel indices)
+    uint32_t* d_hflags = nullptr;         // per-tile flag words the iterative-tier queue is built from
     unsigned int* d_qcount = nullptr;
     VideoQueueEntry* d_vqueue = nullptr;  // exact-path queue of a chunk + its counter
     unsigned int* d_vqcount = nullptr;
@@ -631,12 +632,15 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         if (!b.d_queue) {  // one slot per pixel: the queues of the iterative tier and of the exact path cannot overflow
             CU(cudaMalloc(&b.d_queue, sizeof(QueueEntry) * (size_t)b.n_pixels));
             CU(cudaMalloc(&b.d_hqueue, sizeof(long long) * (size_t)b.n_pixels));
-            CU(cudaMalloc(&b.d_qcount, 2 * sizeof(unsigned int)));
+            // one allocation, one memset per call: the two queue counters (16 words reserved), then the per-tile flag words
+            CU(cudaMalloc(&b.d_qcount, sizeof(uint32_t) * (16 + (size_t)b.n_tiles)));
+            b.d_hflags = b.d_qcount + 16;
         }
-        CU(cudaMemsetAsync(b.d_qcount, 0, 2 * sizeof(unsigned int), s));
+        CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(uint32_t) * (16 + (size_t)b.n_tiles), s));
         OutlierArgs ab = a;
         ab.gq = b.d_queue; ab.gq_count = b.d_qcount;
         ab.ghq = b.d_hqueue; ab.ghq_count = b.d_qcount + 1;
+        ab.hflags = b.d_hflags;
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
         ab.wmask = b.d_wmask; ab.smask = sub ? b.d_smask : nullptr; ab.win_frames = b.d_win;
@@ -676,6 +680,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         // iterative tier: long whole-stack series with relative thresholds (six ranks per band) use the histogram kernel -- one
         // shared-memory atomic per sample instead of the solver's repeated passes (measured on 1000 x UHD: 1.0 ms against
         // 1.7 ms; with absolute thresholds, two ranks, the solver's 0.6 ms wins). CHB_HIST=0 / 1 forces the choice (tests).
+        compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(b.d_hflags, b.n_tiles, b.d_hqueue, b.d_qcount + 1);
         bool use_hist = kmode == 2 && n >= 256;
         if (const char* hv = getenv("CHB_HIST")) use_hist = kmode != 0 && n >= 256 && atoi(hv) != 0;
         if (use_hist) {
@@ -687,7 +692,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         }
         if (st->C == 3) outlier_exact_kernel<3><<<d.sm_count * 4, 256, 0, s>>>(ab);
         else outlier_exact_kernel<4><<<d.sm_count * 4, 256, 0, s>>>(ab);
-        g_launches += 3;
+        g_launches += 4;
         CU(cudaGetLastError());
         CU(cudaEventRecord(b.ev1, s));
         CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));

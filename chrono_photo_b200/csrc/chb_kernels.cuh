@@ -118,10 +118,15 @@ struct OutlierArgs {
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
     unsigned long long* counters;  // [0] warnings (all-outlier pixels), [1] pixels on the exact path, [2] pixels on the iterative (hard) path
-    struct QueueEntry* gq;         // exact-path queue of the launch, one slot per pixel of the band (outlier_exact_kernel drains it)
+    // exact-path queue of the launch, one slot per pixel of the band (outlier_exact_kernel drains it). Slot i < ghq_count mirrors
+    // entry i of the iterative tier's queue (pix = -1: that pixel was certified after all), so the exact path sees neighbouring
+    // pixels -- whose objects dwell on them during the same frames -- side by side; pixels the streaming kernel queues
+    // directly fill the array from its far end (gq_count of them).
+    struct QueueEntry* gq;
     unsigned int* gq_count;
-    long long* ghq;                // queue of the pixels for the iterative tier (outlier_hard_kernel), one slot per pixel
+    long long* ghq;                // pixels for the iterative tier in tile order (compact_hard_kernel builds it from hflags)
     unsigned int* ghq_count;
+    uint32_t* hflags;              // [n_tiles] bit p: pixel p of the tile goes to the iterative tier (zeroed by the host)
     float* dbg_median; float* dbg_q1; float* dbg_q3; int* dbg_nout;
 };
 
@@ -787,9 +792,15 @@ __device__ __forceinline__ void store_pixel(const OutlierArgs& a, long long pix,
 }
 
 template <int C>
-__device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry* q, int count, int lane) {
-    const bool active = lane < count;
-    const QueueEntry e = q[active ? lane : 0];
+__device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry* slot, bool in_range, int lane) {
+    QueueEntry e = *slot;
+    const bool active = in_range && e.pix >= 0;
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (act == 0) return;
+    {   // lanes without a pixel run along on a copy of the first active lane's entry; their results are discarded
+        const unsigned long long first = __shfl_sync(0xffffffffu, (unsigned long long)slot, __ffs(act) - 1);
+        if (!active) e = *reinterpret_cast<const QueueEntry*>(first);
+    }
     const long long tile = e.pix >> 5;
     const PixelSrc src{a.stack + tile * tile_bytes(C, a.NG), a.NG, C, (int)(e.pix & 31)};
     uint8_t pixel[4] = {0, 0, 0, 0};
@@ -802,7 +813,7 @@ __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry*
     const unsigned wb = __ballot_sync(0xffffffffu, active && warn);
     if (lane == 0) {
         if (wb) atomicAdd(a.counters, (unsigned long long)__popc(wb));
-        atomicAdd(a.counters + 1, (unsigned long long)count);
+        atomicAdd(a.counters + 1, (unsigned long long)__popc(act));
     }
 }
 
@@ -949,7 +960,8 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
 
 // Certified pixels are written from registers; the others are appended to the launch's exact-path queue.
 template <int C>
-__device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAcc& acc, long long pix, int p_in_tile, bool owner, int lane) {
+__device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAcc& acc, long long pix, int p_in_tile, bool owner, int lane,
+                                             long long slot = -1) {
     const bool clean = acc.bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
     if (owner && clean) {
         uint8_t pixel[4] = {0, 0, 0, 0};
@@ -975,13 +987,24 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
     // Uncertified pixels go to the launch's global queue (one slot per pixel of the band, so it cannot overflow) and are
     // finished by outlier_exact_kernel right after: the exact path never enters this kernel's instruction stream.
     const bool dirty = owner && !clean;
+    if (slot >= 0) {  // iterative tier: the pixel's own slot (its position in that tier's queue), certified or not
+        if (owner) {
+            QueueEntry& e = a.gq[slot];
+            e.pix = dirty ? pix : -1;
+            if (dirty) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) { e.median[c] = acc.median(c); e.iqr_inv[c] = acc.iqr_inv(c); e.sum[c] = acc.sum(c); }
+            }
+        }
+        return;
+    }
     const unsigned db = __ballot_sync(0xffffffffu, dirty);
-    if (db) {
+    if (db) {  // streaming kernel: appended from the far end of the array
         unsigned int gbase = 0;
         if (lane == 0) gbase = atomicAdd(a.gq_count, (unsigned int)__popc(db));
         gbase = __shfl_sync(0xffffffffu, gbase, 0);
         if (dirty) {
-            QueueEntry& e = a.gq[gbase + __popc(db & ((1u << lane) - 1u))];
+            QueueEntry& e = a.gq[a.n_pixels - 1 - (long long)(gbase + __popc(db & ((1u << lane) - 1u)))];
             e.pix = pix;
 #pragma unroll
             for (int c = 0; c < 4; c++) { e.median[c] = acc.median(c); e.iqr_inv[c] = acc.iqr_inv(c); e.sum[c] = acc.sum(c); }
@@ -991,7 +1014,8 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
 
 // Hard pixels, 32/G at a time: each pixel group reloads its own bands (L2) and runs the iterative solver.
 template <int C, int WPL, int G, int MODE>
-__device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* hq, int count, int lane, int cap, int pad, uint32_t acc_slot) {
+__device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase, int count, int lane, int cap, int pad, uint32_t acc_slot) {
+    const long long* hq = a.ghq + hbase;
     constexpr int W4 = 4 * WPL;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
     const int j = lane / (32 / G), pl = lane % (32 / G);
@@ -1015,7 +1039,7 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, const long long* h
         }
         process_band<C, WPL, G, MODE, false>(a, A, c, j, pix, active && j == 0, cap, pad, acc);
     }
-    finish_pixel<C>(a, acc, pix, p, active && j == 0, lane);
+    finish_pixel<C>(a, acc, pix, p, active && j == 0, lane, (long long)hbase + pl);
 }
 
 template <int C, int WPL, int G, int MODE>
@@ -1128,16 +1152,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
         const bool hard = owner && to_hard;
         const unsigned hb = __ballot_sync(0xffffffffu, hard);
         if (hb) {
-            // they go to the launch's global queue (one slot per pixel of the band): outlier_hard_kernel runs the solver on
-            // them right after this kernel, so its code stays out of this loop
-            const int nh = __popc(hb);
-            unsigned int gbase = 0;
+            // they are flagged in the tile's word; compact_hard_kernel turns the flags into the iterative tier's queue in tile
+            // order and outlier_hard_kernel / outlier_hist_kernel run on it right after, so their code stays out of this loop
+            // (owner lanes are lanes 0 .. PPW-1: lane pl holds pixel (task % G) * PPW + pl of the tile)
             if (lane == 0) {
-                atomicAdd(a.counters + 2, (unsigned long long)nh);
-                gbase = atomicAdd(a.ghq_count, (unsigned int)nh);
+                atomicAdd(a.counters + 2, (unsigned long long)__popc(hb));
+                atomicOr(a.hflags + tile, hb << ((task % G) * PPW));
             }
-            gbase = __shfl_sync(0xffffffffu, gbase, 0);
-            if (hard) a.ghq[gbase + __popc(hb & ((1u << lane) - 1u))] = pix;
         }
         finish_pixel<C>(a, acc, pix, p, owner && !to_hard, lane);
         task += n_warps;
@@ -1156,7 +1177,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard
     const unsigned int total = a.ghq_count[0];
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PPW; base < total; base += n_warps * PPW)
-        drain_hard<C, WPL, G, MODE>(a, a.ghq + base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, acc_slot);
+        drain_hard<C, WPL, G, MODE>(a, base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, acc_slot);
 }
 
 // Iterative tier for long whole-stack series (hundreds of frames): instead of the solver's repeated passes over the pixel's
@@ -1286,7 +1307,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
             }
         }
         __syncwarp();
-        finish_pixel<C>(a, acc, pix, p, lane == 0, lane);
+        finish_pixel<C>(a, acc, pix, p, lane == 0, lane, (long long)idx);
         __syncwarp();
     }
 }
@@ -1294,11 +1315,66 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
 // Last launch of a compositing call: the queued pixels, 32 per warp.
 template <int C>
 __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
-    const unsigned int total = a.gq_count[0];
+    const unsigned int mirrored = a.ghq_count[0], total = mirrored + a.gq_count[0];
     const int lane = threadIdx.x & 31;
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < total; base += n_warps * 32u)
-        drain_queue<C>(a, a.gq + base, (int)min(32u, total - base), lane);
+    for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < total; base += n_warps * 32u) {
+        const unsigned int v = base + lane;
+        const bool in_range = v < total;
+        const long long slot = !in_range ? 0 : (v < mirrored ? (long long)v : a.n_pixels - 1 - (long long)(v - mirrored));
+        drain_queue<C>(a, a.gq + slot, in_range, lane);
+    }
+}
+
+// Between the streaming kernel and the iterative tier: the per-tile flag words become that tier's queue. A block takes 1024
+// consecutive tiles and writes their flagged pixels in tile order (blocks land in the order of their atomicAdd), so entries
+// that are neighbours in the queue are neighbours in the image.
+__global__ void __launch_bounds__(256) compact_hard_kernel(const uint32_t* __restrict__ flags, long long n_tiles, long long* __restrict__ ghq,
+                                                           unsigned int* __restrict__ ghq_count) {
+    constexpr int kTilesPerThread = 4;
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t block_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long n_chunks = (n_tiles + 256 * kTilesPerThread - 1) / (256 * kTilesPerThread);
+    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const long long t0 = (chunk * 256 + threadIdx.x) * kTilesPerThread;
+        uint32_t f[kTilesPerThread];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < kTilesPerThread; k++) {
+            f[k] = (t0 + k < n_tiles) ? flags[t0 + k] : 0u;
+            cnt += (uint32_t)__popc(f[k]);
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            if (w < wid) woff += warp_tot[w];
+            tot += warp_tot[w];
+        }
+        if (threadIdx.x == 0) block_base = tot ? atomicAdd(ghq_count, tot) : 0u;
+        __syncthreads();
+        if (cnt) {
+            uint32_t off = block_base + woff + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < kTilesPerThread; k++) {
+                uint32_t m = f[k];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    ghq[off++] = (t0 + k) * kTilePixels + b;
+                    m &= m - 1;
+                }
+            }
+        }
+        __syncthreads();  // warp_tot / block_base are reused by the next chunk
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K3 chrono-video
