@@ -332,7 +332,7 @@ def main():
     value = total_pf / (ms_step / 1e3)
 
     # ---- roofline (algorithmic bytes of this rank's shard). The headline fraction is taken over the WHOLE call -- the streaming
-    # kernel plus the two tier kernels that finish the queued pixels -- and the dominant (streaming) kernel is reported beside it.
+    # kernel plus the queue compaction and the two tier kernels that finish the queued pixels -- and the dominant (streaming) kernel is reported beside it.
     P_shard = rows * W
     alg_bytes = P_shard * 3 * (n + (2 if is_outlier else 1))  # read the stack once + composite (+ mask) write
     peak, peak_src = peaks()
@@ -340,7 +340,7 @@ def main():
     kernel_name = "outlier_kernel" if is_outlier else "simple_int_kernel"
     traffic = traffic_from_profiles(kernel_name + ":" + wl) if n_gpus == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": (kernel_name + " + outlier_hard_kernel|outlier_hist_kernel + outlier_exact_kernel (one call)") if is_outlier else kernel_name,
+                "kernel": (kernel_name + " + compact_hard_kernel + outlier_hard_kernel|outlier_hist_kernel + outlier_exact_kernel (one call)") if is_outlier else kernel_name,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": kernel_ms, "peak_source": peak_src,
                 "slow_path_pixels_per_launch": int(_lib.lib().chb_last_slow_pixels()) if is_outlier else 0}
     if is_outlier:

@@ -1211,25 +1211,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
             for (int g = lane; g < a.n_groups; g += 32) {
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(ub + (long long)g * (kTilePixels * kUnitBytes)));
                 if (g == 0) first = v.x & 0xffu;  // window position 0 (whole-stack launch: frame 0)
-                if (need) {
-                    const int left = a.n - g * kGroupFrames;  // frames of this group that exist (the rest are zero padding)
+                if (need) {  // all sixteen bytes: the frames a last group lacks are zero bytes, taken out of bin 0 below
                     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-                    if (left >= kGroupFrames) {  // a full group: sixteen samples, no per-sample test
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
+                    for (int q = 0; q < 4; q++) {
 #pragma unroll
-                            for (int k = 0; k < 4; k++) atomicAdd(&hist[(wv[q] >> (8 * k)) & 0xffu], 1u);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-#pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                if (4 * q + k < left) atomicAdd(&hist[(wv[q] >> (8 * k)) & 0xffu], 1u);
-                        }
+                        for (int k = 0; k < 4; k++) atomicAdd(&hist[(wv[q] >> (8 * k)) & 0xffu], 1u);
                     }
                 }
             }
+            __syncwarp();
+            if (need && lane == 0) hist[0] -= (uint32_t)(a.n_groups * kGroupFrames - a.n);
             first = __shfl_sync(0xffffffffu, first, 0);
             acc.first_px |= first << (8 * c);
             __syncwarp();
