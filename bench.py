@@ -30,6 +30,11 @@ WORKLOADS = {
     "c2-lighter": ("lighter", 200, 4000, 6000, 2, "--mode lighter, 200 x 6000x4000 RGB8"),
     "c4-outlier-rel-forward": ("outlier-rel", 1000, 2160, 3840, 2, "--mode outlier -t rel/3.0/5.0 -l forward -b first, 1000 x 3840x2160 RGB8"),
     "c1-minimal": ("outlier-c1", 25, 768, 1024, 1, "cmd_examples/minimal: defaults abs/0.05/0.2, extreme, 25 x 1024x768 RGB8 (background first)"),
+    # adversarial / noisier series: not bench lines of BASELINE.json, measured for the worst case in profiles/
+    "a1-iid-uniform": ("outlier", 200, 2048, 2048, 3, "worst case: iid uniform bytes (every pixel through the iterative tier and the per-frame path), "
+                       "--mode outlier -t abs/0.05/0.2 -l extreme -b first, 200 x 2048x2048 RGB8"),
+    "a4-gauss-noise": ("outlier", 200, 4000, 6000, 4, "gradient + Gaussian-like noise (sigma ~ 4.6, range +-14) + discs, "
+                       "--mode outlier -t abs/0.05/0.2 -l extreme -b first, 200 x 6000x4000 RGB8"),
     "c5-video": ("video", 1800, 1064, 1904, 2, "chrono-video: --video-in 0/25/1 over 1800 x 1080p frames cropped to 1904x1064 by shake offsets in [-8,8]^2, "
                  "outlier abs/0.05/0.2 extreme; one launch per output frame (1824 windows)"),
 }

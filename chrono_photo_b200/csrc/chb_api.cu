@@ -683,15 +683,25 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(b.d_hflags, b.n_tiles, b.d_hqueue, b.d_qcount + 1);
         bool use_hist = kmode == 2 && n >= 256;
         if (const char* hv = getenv("CHB_HIST")) use_hist = kmode != 0 && n >= 256 && atoi(hv) != 0;
+        // the two tier kernels are programmatic dependent launches: their CTAs become resident while the previous kernel's
+        // last CTAs drain and wait (griddepcontrol.wait) for its results, which hides two launch latencies per call
+        static const bool use_pdl = !(getenv("CHB_PDL") && atoi(getenv("CHB_PDL")) == 0);
+        auto launch_dep = [&](OutlierKernel k, int grid, int block, size_t sh) -> cudaError_t {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = sh; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+            return cudaLaunchKernelEx(&cfg, k, ab);
+        };
         if (use_hist) {
-            if (st->C == 3) outlier_hist_kernel<3><<<d.sm_count * 8, kWarpsPerCta * 32, 0, s>>>(ab);
-            else outlier_hist_kernel<4><<<d.sm_count * 8, kWarpsPerCta * 32, 0, s>>>(ab);
+            CU(launch_dep(st->C == 3 ? outlier_hist_kernel<3> : outlier_hist_kernel<4>, d.sm_count * 8, kWarpsPerCta * 32, 0));
         } else {
             CU(cudaFuncSetAttribute(hard_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            hard_kern<<<blocks, kWarpsPerCta * 32, smem, s>>>(ab);
+            CU(launch_dep(hard_kern, blocks, kWarpsPerCta * 32, smem));
         }
-        if (st->C == 3) outlier_exact_kernel<3><<<d.sm_count * 4, 256, 0, s>>>(ab);
-        else outlier_exact_kernel<4><<<d.sm_count * 4, 256, 0, s>>>(ab);
+        CU(launch_dep(st->C == 3 ? outlier_exact_kernel<3> : outlier_exact_kernel<4>, d.sm_count * 4, 256, 0));
         g_launches += 4;
         CU(cudaGetLastError());
         CU(cudaEventRecord(b.ev1, s));

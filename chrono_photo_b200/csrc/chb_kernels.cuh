@@ -25,6 +25,10 @@ __device__ __forceinline__ uint32_t absdiff4(uint32_t a, uint32_t b) {
     return d;
 }
 __device__ __forceinline__ uint32_t rep4(int v) { return (uint32_t)v * 0x01010101u; }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may become resident
+// while its predecessor in the stream drains; it must not touch the predecessor's results before this wait (a no-op without
+// the attribute).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -1170,6 +1174,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
 template <int C, int WPL, int G, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard_kernel(const __grid_constant__ OutlierArgs a) {
     constexpr int PPW = 32 / G;
+    grid_dependency_wait();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int cap = 4 * WPL * 4 * G, pad = cap - a.n_sub;
@@ -1186,6 +1191,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard
 // off one warp-wide prefix sum (lane l owns bins 8l .. 8l+7). The certificate term uses the exact max |x - centre|.
 template <int C>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const __grid_constant__ OutlierArgs a) {
+    grid_dependency_wait();
     __shared__ __align__(16) uint32_t hist_all[kWarpsPerCta][256];
     __shared__ uint32_t acc_words[kAccWords * kWarpsPerCta * 32];
     const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
@@ -1307,6 +1313,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
 // Last launch of a compositing call: the queued pixels, 32 per warp.
 template <int C>
 __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
+    grid_dependency_wait();
     const unsigned int mirrored = a.ghq_count[0], total = mirrored + a.gq_count[0];
     const int lane = threadIdx.x & 31;
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
