@@ -444,6 +444,15 @@ extern "C" int chb_sample_positions(uint64_t seed, int n, int cnt, int32_t* out)
 }
 
 // ------------------------------------------------------------------------------------------------ K1 dispatch
+
+// Absolute thresholds with every weight 0 or 1: 4 * dist_sq is an exact integer below 2^20 and the outlier test becomes
+// 4 * dist_sq >= ceil(4 * thr_sq) (see IntDist in chb_kernels.cuh).
+static void set_int_dist(OutlierArgs& a) {
+    bool ok = a.absolute && a.thr_sq == a.thr_sq && a.thr_sq >= 0.0f && a.thr_sq < 1.0e6f;
+    for (int i = 0; i < a.C; i++) ok = ok && (a.w[i] == 0.0f || a.w[i] == 1.0f);
+    a.int_dist = ok ? 1 : 0;
+    a.thr4 = ok ? (int)ceilf(4.0f * a.thr_sq) : 0;
+}
 typedef void (*OutlierKernel)(const OutlierArgs);
 struct Variant { int wpl, g; };
 // capacity (frames) = 16 * wpl * g
@@ -563,6 +572,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     a.thr_min = prm->thr_min; a.thr_max = prm->thr_max; a.thr_scale = prm->thr_scale;
     a.thr_sq = prm->thr_min * prm->thr_min;  // src/chrono.rs:220
     for (int i = 0; i < 4; i++) a.w[i] = prm->weights[i];
+    set_int_dist(a);
     a.bg = prm->background; a.om = prm->outlier;
     rc = fade_to_dev(prm->fade, a.fade, "chb_outlier");
     if (rc) return rc;
@@ -863,6 +873,7 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
     a.thr_min = prm->thr_min; a.thr_max = prm->thr_max; a.thr_scale = prm->thr_scale;
     a.thr_sq = prm->thr_min * prm->thr_min;  // src/chrono.rs:220
     for (int i = 0; i < 4; i++) a.w[i] = prm->weights[i];
+    set_int_dist(a);
     a.bg = prm->background; a.om = prm->outlier;
     int rc = fade_to_dev(prm->fade, a.fade, "chb_outlier_video");
     if (rc) return rc;

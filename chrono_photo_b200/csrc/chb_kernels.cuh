@@ -111,6 +111,8 @@ struct OutlierArgs {
     float q1_frac, q3_frac;  // interpolation weights of quantile() (src/chrono.rs:568-579)
     float inv_n_sub;
     int absolute;
+    int int_dist;            // 1: absolute thresholds and every weight 0 or 1: 4 * dist_sq is an exact integer (IntDist)
+    int thr4;                // ceil(4 * thr_sq): dist_sq >= thr_sq <=> 4 * dist_sq >= thr4
     float thr_min, thr_max, thr_scale, thr_sq;
     float w[4];
     int bg, om;
@@ -422,6 +424,46 @@ __device__ __forceinline__ float dist_sq_px(const DistCtx& d, const uint8_t (&px
     return dist_sq;
 }
 
+// Integer form of the distance for absolute thresholds with weights in {0, 1} (the CLI default): median = (lo + hi) / 2 with
+// lo = floor(median), hi = ceil(median) (no sample lies strictly between them), so |2 * median - 2 * x| = |x - lo| + |x - hi|
+// and 4 * dist_sq = sum over bands of (L + H)^2 = L.L + 2 L.H + H.H -- three IDP.4A on the per-frame byte vectors L, H
+// (VABSDIFF4 per band and word, transposed with PRMT). Every f32 operation of the reference (src/chrono.rs:265-278) is exact
+// on these values (multiples of 0.25 below 2^18), so the integers reproduce it bit for bit.
+struct IntDist {
+    uint32_t lo[4], hi[4];
+    bool use[4];
+};
+__device__ __forceinline__ void make_int_dist(const OutlierArgs& a, const float (&median)[4], IntDist& d) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        d.use[i] = (i < a.C) && (a.w[i] != 0.0f);
+        const int lo = (int)median[i];  // medians are >= 0: truncation is floor
+        d.lo[i] = rep4(lo);
+        d.hi[i] = rep4(lo + (median[i] != (float)lo ? 1 : 0));
+    }
+}
+// 4 * dist_sq of the four frames of a word (frame k in out[k])
+__device__ __forceinline__ void int_dist4(const IntDist& d, const uint32_t (&xw)[4], uint32_t (&out)[4]) {
+    uint32_t L[4], H[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        L[i] = d.use[i] ? absdiff4(xw[i], d.lo[i]) : 0u;
+        H[i] = d.use[i] ? absdiff4(xw[i], d.hi[i]) : 0u;
+    }
+    // 4 x 4 byte transposes: band-major words -> one word per frame
+    const uint32_t l01a = __byte_perm(L[0], L[1], 0x5140), l01b = __byte_perm(L[0], L[1], 0x7362);
+    const uint32_t l23a = __byte_perm(L[2], L[3], 0x5140), l23b = __byte_perm(L[2], L[3], 0x7362);
+    const uint32_t h01a = __byte_perm(H[0], H[1], 0x5140), h01b = __byte_perm(H[0], H[1], 0x7362);
+    const uint32_t h23a = __byte_perm(H[2], H[3], 0x5140), h23b = __byte_perm(H[2], H[3], 0x7362);
+    const uint32_t Lf[4] = {__byte_perm(l01a, l23a, 0x5410), __byte_perm(l01a, l23a, 0x7632), __byte_perm(l01b, l23b, 0x5410), __byte_perm(l01b, l23b, 0x7632)};
+    const uint32_t Hf[4] = {__byte_perm(h01a, h23a, 0x5410), __byte_perm(h01a, h23a, 0x7632), __byte_perm(h01b, h23b, 0x5410), __byte_perm(h01b, h23b, 0x7632)};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t sq = __dp4a(Hf[k], Hf[k], __dp4a(Lf[k], Lf[k], 0u));
+        out[k] = sq + 2u * __dp4a(Lf[k], Hf[k], 0u);
+    }
+}
+
 __device__ __forceinline__ float blend_value(const OutlierArgs& a, float dist) {  // src/options.rs:223-231
     if (dist <= a.thr_min) return 0.0f;
     if (dist >= a.thr_max) return 1.0f;
@@ -470,6 +512,8 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
     make_dist_ctx(a, median, iqr_inv, dc);
     WordScan ws;
     make_word_scan(a, median, iqr_inv, ws);
+    IntDist idc;
+    make_int_dist(a, median, idc);
     ColumnReader rd(src);
     // pass 1 (src/chrono.rs:261-288 plus the sums the policies need)
     int k = 0, first_idx = 0, last_idx = 0, max_index = 0, first_non = -1;
@@ -502,6 +546,19 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
                 const uint32_t ex = may_exceed(ws, xw);
                 if (ex == 0) {
                     if (first_non < 0) first_non = s;
+                } else if (a.int_dist) {  // the word's four distances as integers
+                    uint32_t d4[4];
+                    int_dist4(idc, xw, d4);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        if ((int)d4[kk] >= a.thr4) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) px[i] = (uint8_t)((xw[i] >> (8 * kk)) & 0xffu);
+                            visit(s + kk, 0.25f * (float)d4[kk]);
+                        } else if (first_non < 0) {
+                            first_non = s + kk;
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) {
