@@ -181,6 +181,7 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
     int g = __float2int_rn((float)ssum * inv_cnt);  // mean as the first guess for the median
     g = g < 0 ? 0 : (g > 254 ? 254 : g);
     int cv_mlo = cap, dq = 0;
+    bool rejumped = false;  // the first rank's guess has been moved to the mean of the samples on the answer's side
     r.mlo = r.mhi = r.q1a = r.q1b = r.q3a = r.q3b = 0;
     while (__any_sync(0xffffffffu, t < nt)) {
         const bool act = t < nt;
@@ -228,6 +229,25 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
             nmode = 1; nsteps = 0;
             res = up0 ? (nb == 255) : (nb == 0);
             v = nb; cv = ncnth;
+            if (!res && t == 0 && !rejumped) {
+                // A pixel reaches this solver because its mean is no guess for its median: an object rests on it for a good part
+                // of the series. The samples on the median's side of g are mostly background, and F(g), F(g+1) and the sum give
+                // their mean for free (sum of (x - g - 1) over x > g is (F(g+1) + sum - cap (g+1)) / 2; likewise below g, without
+                // the pad zeros): jump there once before walking.
+                rejumped = true;
+                int g2;
+                if (up0) {
+                    const int above = cap - nj;  // > 0: the rank lies above g
+                    const int A = ((int)f2 + (int)ssum - cap * (g + 1)) >> 1;
+                    g2 = g + 1 + __float2int_rn(__fdividef((float)A, (float)above));
+                } else {
+                    const int below = nj - pad;  // > 0: real samples <= g
+                    const int B = (((int)f1 - (int)ssum + cap * g) >> 1) - pad * g;
+                    g2 = g - __float2int_rn(__fdividef((float)B, (float)max(below, 1)));
+                }
+                g2 = g2 < 0 ? 0 : (g2 > 254 ? 254 : g2);
+                if (g2 > g + 3 || g2 < g - 3) { g = g2; nmode = 0; }  // close guesses just walk
+            }
         } else if (m1) {
             res = rb | rb1;
             v = rb ? b : b + d;
