@@ -1,4 +1,5 @@
-"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every tier of K1, both K2 kernels."""
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every tier of K1 (streaming, queue compaction,
+solver and histogram tiers, per-frame path), a chrono-video run, both K2 kernels."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -16,6 +17,8 @@ for n, c in ((25, 3), (200, 3), (70, 4), (300, 3)):
             cp.OutlierProcessor(thr, bg, om, seed=3).process(fs)
             cp.OutlierProcessor(thr, bg, om, seed=3).process(fs, list(range(1, n - 1, 2)))
     cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2, sample_count=max(3, n // 3)).process(fs)
+    if n >= 70:  # chrono-video run (video_kernel + video_exact_kernel): 20 windows of 9 frames
+        cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2).process_video_run(fs, 3, 9, 20)
     cp.SimpleProcessor(darker=True).process(fs)
     cp.SimpleProcessor((1, 0.5, 0.25, 0), cp.Fade(0, False, [(0, 1.0), (9, 0.0)]), False).process(fs, list(range(0, n, 3)))
     fs.close()
