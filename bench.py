@@ -259,9 +259,20 @@ def main():
     multi_proc = world > 1
     if multi_proc:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries the one JSON line only: NCCL prints its version banner (NCCL_DEBUG=VERSION on the GPU boxes) with a plain
+        # printf when the communicator is created, so file descriptor 1 points at stderr until the first collective is through
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         devices, shard_rank, shard_world = [local_rank], rank, world
     else:
         devices, shard_rank, shard_world = list(range(args.gpus)), 0, 1  # one process drives all GPUs through one context
