@@ -114,6 +114,64 @@ def test_outlier_window_fade_weights_sample_matches_numpy_restatement():
             assert np.array_equal(img, img2) and np.array_equal(msk, msk2) and warn == warn2
 
 
+@pytest.mark.parametrize("seed", range(96))
+def test_random_option_fuzz_oracle_against_numpy_restatement(seed):
+    # The C oracle is the pin of GPU parity; its own pin beyond the reference's few known answers is this independent
+    # restatement written from the Rust source. Seeded walk through the option space on small stacks (the restatement is a
+    # pure-Python loop): frame counts incl. 1-2, RGB / RGBA, four data regimes, both threshold kinds, every policy pair,
+    # zero / fractional / negative weights, fades of both kinds and modes, contiguous and stepped windows, --sample.
+    rng = np.random.default_rng(50_000 + seed)
+    n = int(rng.choice([1, 2, 3, 4, 5, 8, 13, 16, 17, 24]))
+    c = int(rng.choice([3, 4]))
+    h, w = int(rng.integers(2, 5)), int(rng.integers(2, 6))
+    regime = int(rng.integers(0, 4))
+    if regime == 0:
+        st = make_stack(rng, n, h, w, c, noise=int(rng.integers(0, 12)), n_obj=int(rng.integers(0, 6)))
+    elif regime == 1:
+        st = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    elif regime == 2:
+        st = rng.choice(np.array([0, 255, 3, 252], np.uint8), size=(n, h, w, c))
+    else:
+        base = rng.integers(0, 256, size=(1, h, w, c))
+        st = np.clip(base + np.rint(rng.normal(0, rng.uniform(0.5, 9), size=(n, h, w, c))), 0, 255).astype(np.uint8)
+    idx = None
+    if n >= 4 and rng.integers(0, 2):
+        a0 = int(rng.integers(0, n // 2))
+        idx = list(range(a0, int(rng.integers(a0 + 1, n + 1)), int(rng.choice([1, 1, 2, 3]))))
+    nwin = len(idx) if idx is not None else n
+    absolute = bool(rng.integers(0, 2)) or nwin < 3  # quantile() needs three samples (src/chrono.rs:569-570)
+    if absolute:
+        mn = float(rng.choice([0.0, 0.01, 0.05, 0.1, 0.3]))
+        thr = orc.threshold(True, mn, mn + float(rng.choice([0.0, 0.05, 0.15, 0.5])))
+    else:
+        mn = float(rng.choice([0.5, 1.0, 3.0, 6.0]))
+        thr = orc.threshold(False, mn, mn + float(rng.choice([0.0, 1.0, 2.0])))
+    weights = tuple(float(x) for x in rng.choice([1.0, 1.0, 1.0, 0.0, 0.5, 2.0, -1.0], size=4))
+    if not any(weights[:c]):
+        weights = (1.0,) + weights[1:]
+    fo = fn = None
+    if rng.integers(0, 3) == 0:
+        mode, fabs = int(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        f0 = int(rng.integers(-3, 4))
+        pts = [(f0, float(rng.uniform(-0.5, 1.5))), (f0 + int(rng.integers(1, 6)), float(rng.uniform(-0.5, 1.5)))]
+        if rng.integers(0, 2):
+            pts.append((pts[-1][0] + int(rng.integers(1, 5)), float(rng.uniform(0.0, 1.0))))
+        fo, fn = orc.fade(mode, fabs, pts), npr.Fade.build(mode, fabs, pts)
+    spos = None
+    if nwin >= 4 and rng.integers(0, 4) == 0:
+        k = int(rng.integers(3 if not absolute else 1, nwin))
+        spos = sorted(int(v) for v in rng.choice(nwin, size=k, replace=False))
+    bg, om = int(rng.integers(0, 4)), int(rng.integers(0, 6))
+    seed_rng = int(rng.integers(0, 1000))
+    img, msk, warn = orc.outlier(st, thr, bg, om, weights=weights, fade_=fo, indices=idx, sample_pos=spos, seed=seed_rng, pixel_offset=11)
+    img2, msk2, warn2 = npr.outlier(st, absolute, thr.min, thr.max, thr.scale, bg, om, weights=weights, fade=fn, indices=idx,
+                                    sample_pos=spos, seed=seed_rng, pixel_offset=11)
+    tag = f"n={n} c={c} regime={regime} abs={absolute} bg={bg} om={om} w={weights} idx={idx} spos={spos}"
+    assert np.array_equal(msk, msk2), "mask " + tag
+    assert np.array_equal(img, img2), "composite " + tag
+    assert warn == warn2, "warnings " + tag
+
+
 def test_all_outlier_warning_path():
     # threshold 0: every frame is an outlier (dist_sq >= 0), first_excluded returns (0, warning) src/chrono.rs:510-516
     rng = np.random.default_rng(11)
