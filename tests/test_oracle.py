@@ -221,6 +221,34 @@ def test_simple_matches_numpy_restatement():
                               npr.simple(st, darker, weights=(1, 0.5, 0.25, 0), fade=fn, indices=[1, 2, 5, 6, 9]))
 
 
+@pytest.mark.parametrize("seed", range(32))
+def test_simple_fuzz_oracle_against_numpy_restatement(seed):
+    # darker / lighter: ties (few distinct values), RGB / RGBA incl. the alpha band in the weighted sum, fractional / zero /
+    # negative weights, fades (running order-dependent blend), windows
+    rng = np.random.default_rng(70_000 + seed)
+    n, c = int(rng.choice([1, 2, 3, 7, 16, 17, 30])), int(rng.choice([3, 4]))
+    h, w = int(rng.integers(1, 5)), int(rng.integers(1, 7))
+    if rng.integers(0, 2):
+        st = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    else:
+        st = rng.choice(np.array([0, 1, 2, 128, 254, 255], np.uint8), size=(n, h, w, c))
+    weights = tuple(float(x) for x in rng.choice([1.0, 1.0, 0.0, 0.5, 0.25, 2.0, -1.0], size=4))
+    idx = None
+    if n >= 3 and rng.integers(0, 2):
+        a0 = int(rng.integers(0, n - 1))
+        idx = list(range(a0, int(rng.integers(a0 + 1, n + 1)), int(rng.choice([1, 2, 3]))))
+    fo = fn = None
+    if rng.integers(0, 2):
+        mode, fabs = int(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        f0 = int(rng.integers(-2, 3))
+        pts = [(f0, float(rng.uniform(-0.5, 1.5))), (f0 + int(rng.integers(1, 8)), float(rng.uniform(-0.5, 1.5)))]
+        fo, fn = orc.fade(mode, fabs, pts), npr.Fade.build(mode, fabs, pts)
+    for darker in (True, False):
+        got = orc.simple(st, darker, weights=weights, fade_=fo, indices=idx)
+        want = npr.simple(st, darker, weights=weights, fade=fn, indices=idx)
+        assert np.array_equal(got, want), f"darker={darker} n={n} c={c} w={weights} idx={idx} fade={fo is not None}"
+
+
 def test_simple_first_frame_wins_ties():
     st = np.zeros((3, 1, 2, 3), np.uint8)
     st[0, 0, 0] = (10, 20, 30)
