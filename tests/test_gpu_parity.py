@@ -129,6 +129,29 @@ def test_frame_counts_cover_every_kernel_variant(ctx, n):
         check_outlier(ctx, st, (False, 3.0, 5.0), "first", "forward")
 
 
+@pytest.mark.parametrize("n", [2049, 4096])
+def test_longest_series_one_launch_holds(ctx, n):
+    # the register-resident variants end at (8 units, 32 lanes per pixel) = 4096 frames per window span; 2049 is the first
+    # frame count that needs it, 4096 fills it
+    rng = np.random.default_rng(n)
+    st = make_stack(rng, n, 3, 9, 3, noise=6, n_obj=4)
+    check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
+    check_outlier(ctx, st, (False, 3.0, 5.0), "median", "backward")
+
+
+def test_more_than_4096_frames_in_one_window_is_reported(ctx):
+    st = np.zeros((4097, 2, 4, 3), np.uint8)
+    fs = upload(ctx, st)
+    with pytest.raises(Exception) as ei:
+        cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG["first"], OM["extreme"]).process(fs)
+    assert "4096" in str(ei.value) or "holds at most" in str(ei.value)
+    # a window of the same stack that fits is fine, and so are darker / lighter (they stream, no capacity limit)
+    img, _ = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG["first"], OM["extreme"]).process(fs, list(range(100, 400)))
+    assert not img.any()
+    assert not cp.SimpleProcessor(darker=True).process(fs).any()
+    fs.close()
+
+
 def test_rel_needs_three_samples(ctx):
     st = np.zeros((2, 4, 4, 3), np.uint8)
     fs = upload(ctx, st)
