@@ -58,6 +58,8 @@ SYMBOLS = {
     "chb_outlier_device": (_i, [_vp, C.POINTER(OutlierParams), _i32p, _i, _i, _f32p]),
     "chb_simple_device": (_i, [_vp, C.POINTER(SimpleParams), _i32p, _i, _f32p]),
     "chb_fetch_last": (_i, [_vp, _vp, _vp, _u64p]),
+    "chb_fetch_last_device": (_i, [_vp, _i, _vp, _vp]),
+    "chb_set_tuning": (_i, [C.c_char_p, _i]),
     "chb_outlier_enqueue": (_i, [_vp, C.POINTER(OutlierParams), _i32p, _i, _i]),
     "chb_stack_wait": (_i, [_vp, _f32p, _u64p]),
     "chb_outlier_video": (_i, [_vp, C.POINTER(OutlierParams), _i, _i, _i, _vp, _vp, _u64p]),

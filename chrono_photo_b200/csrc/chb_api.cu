@@ -37,6 +37,33 @@ static int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(CHB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// ---- tuning / test knobs: read from the environment ONCE when the library is loaded (no getenv on the launch path); tests and
+// tuning scripts change them through chb_set_tuning. -1 = automatic.
+struct Tuning {
+    std::atomic<int> force_variant{-1};    // CHB_FORCE_VARIANT: K1 variant table index (a larger-capacity variant than needed)
+    std::atomic<int> hist{-1};             // CHB_HIST: 0 / 1 forces the solver / the histogram kernel on the iterative tier
+    std::atomic<int> pdl{1};               // CHB_PDL: tier kernels as programmatic dependent launches
+    std::atomic<int> video_queue_cap{-1};  // CHB_VIDEO_QUEUE_CAP: capacity of the video exact-path queue (tests the in-place fallback)
+    std::atomic<int> inline_min{12};       // CHB_INLINE_MIN: uncertified pixels per tile from which the tile is finished inside K1 (0 = never)
+    Tuning() {
+        auto env = [](const char* k, std::atomic<int>& v) { if (const char* e = getenv(k)) v.store(atoi(e)); };
+        env("CHB_FORCE_VARIANT", force_variant); env("CHB_HIST", hist); env("CHB_PDL", pdl);
+        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min);
+    }
+};
+static Tuning g_tune;
+extern "C" int chb_set_tuning(const char* key, int value) {
+    if (!key) return fail(CHB_ERR_INVALID, "chb_set_tuning: null key");
+    const std::string k(key);
+    if (k == "force_variant") g_tune.force_variant.store(value);
+    else if (k == "hist") g_tune.hist.store(value);
+    else if (k == "pdl") g_tune.pdl.store(value);
+    else if (k == "video_queue_cap") g_tune.video_queue_cap.store(value);
+    else if (k == "inline_min") g_tune.inline_min.store(value);
+    else return fail(CHB_ERR_INVALID, "chb_set_tuning: unknown key '%s'", key);
+    return CHB_OK;
+}
+
 extern "C" const char* chb_last_error(void) { return g_err.c_str(); }
 extern "C" int chb_version(void) { return CHB_VERSION; }
 extern "C" uint64_t chb_launch_count(void) { return g_launches.load(); }
@@ -280,6 +307,18 @@ static int grid_for(long long work_items, int threads, int sm_count, int waves) 
     long long blocks = (work_items + threads - 1) / threads;
     long long cap = (long long)sm_count * waves;
     return (int)std::max<long long>(1, std::min(blocks, cap));
+}
+
+// Orders a compute stream after every ingest step enqueued so far on this band (H2D copies on d.copy, re-layout on d.pack), so a
+// compositing launch issued right after a run of uploads never reads a partly packed stack -- with or without chb_stack_sync.
+// (Waiting on an event that was never recorded is a no-op.)
+static cudaError_t wait_ingest(Band& b, cudaStream_t s) {
+    for (int k = 0; k < 2; k++) {
+        if (!b.packed[k]) continue;
+        cudaError_t e = cudaStreamWaitEvent(s, b.packed[k], 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // Ingest of one frame into every band. `pinned`: the source can be DMA'd directly.
@@ -545,8 +584,8 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     int vidx = -1;
     for (int v = 0; v < kNumVariants; v++)
         if (kVariants[v].wpl * kVariants[v].g >= win.n_groups) { vidx = v; break; }
-    if (const char* force = getenv("CHB_FORCE_VARIANT")) {  // tuning aid: pick a larger-capacity variant by table index
-        int v = atoi(force);
+    {   // tuning aid: pick a larger-capacity variant by table index
+        const int v = g_tune.force_variant.load();
         if (v >= 0 && v < kNumVariants && kVariants[v].wpl * kVariants[v].g >= win.n_groups) vidx = v;
     }
     if (vidx < 0)
@@ -580,6 +619,10 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     a.contig_f0 = (win.frames.back() - win.frames.front() + 1 == n) ? win.frames.front() : -1;
     a.exact_quartiles = (dbg && (dbg->q1 || dbg->q3)) ? 1 : 0;
     a.seed = prm->seed;
+    // dense per-frame pass with per-group outlier masks: integer distance, contiguous window of at most kMaskGroups groups
+    a.mask_path = (a.int_dist && a.contig_f0 >= 0 && win.n_groups <= kMaskGroups) ? 1 : 0;
+    // ... run inside the streaming kernel (lane = pixel: the G == 1 variants) for tiles with at least this many uncertified pixels
+    a.inline_min = (a.mask_path && var.g == 1) ? g_tune.inline_min.load() : 0;
 
     // host tables
     byte_masks(win.frames, win.g0, cap_groups, st->h_wmask);
@@ -626,12 +669,13 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         if (!prm->fade.is_none) put(st->h_fade, sizeof(float) * (size_t)prm->fade.n_values);
     }
     const bool tables_cached = (blob == st->last_tables);
-    if (!tables_cached) st->last_tables = blob;
+    if (!tables_cached) st->last_tables.clear();  // set again once every band's copies and launches were enqueued
     const size_t P = (size_t)st->W * st->H;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
         cudaStream_t s = d.compute;
+        CU(wait_ingest(b, s));
         if (!tables_cached) {  // window / sample / fade tables: uploaded only when they differ from the previous call's
             CU(cudaMemcpyAsync(b.d_wmask, st->h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
             if (sub) CU(cudaMemcpyAsync(b.d_smask, st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
@@ -692,10 +736,10 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         // 1.7 ms; with absolute thresholds, two ranks, the solver's 0.6 ms wins). CHB_HIST=0 / 1 forces the choice (tests).
         compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(b.d_hflags, b.n_tiles, b.d_hqueue, b.d_qcount + 1);
         bool use_hist = kmode == 2 && n >= 256;
-        if (const char* hv = getenv("CHB_HIST")) use_hist = kmode != 0 && n >= 256 && atoi(hv) != 0;
+        if (g_tune.hist.load() >= 0) use_hist = kmode != 0 && n >= 256 && g_tune.hist.load() != 0;
         // the two tier kernels are programmatic dependent launches: their CTAs become resident while the previous kernel's
         // last CTAs drain and wait (griddepcontrol.wait) for its results, which hides two launch latencies per call
-        static const bool use_pdl = !(getenv("CHB_PDL") && atoi(getenv("CHB_PDL")) == 0);
+        const bool use_pdl = g_tune.pdl.load() != 0;
         auto launch_dep = [&](OutlierKernel k, int grid, int block, size_t sh) -> cudaError_t {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = sh; cfg.stream = s;
@@ -718,6 +762,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
     }
     (void)P;
+    if (!tables_cached) st->last_tables = blob;
     if (enqueue_only && tables_cached) {  // nothing on the host is reused before the launch has read it: return without waiting
         st->last_has_mask = want_mask;
         return CHB_OK;
@@ -811,6 +856,18 @@ extern "C" int chb_stack_wait(chb_stack* st, float* last_kernel_ms, uint64_t* n_
     int rc = collect_outlier(st, nullptr, last_kernel_ms, st->last_has_mask);
     if (rc) return rc;
     if (n_warnings) *n_warnings = st->last_warnings;
+    return CHB_OK;
+}
+extern "C" int chb_fetch_last_device(chb_stack* st, int dev_slot, void* d_image, void* d_mask) {
+    if (!st || !d_image) return fail(CHB_ERR_INVALID, "chb_fetch_last_device: null argument");
+    if (dev_slot < 0 || dev_slot >= (int)st->bands.size()) return fail(CHB_ERR_INVALID, "chb_fetch_last_device: bad device slot");
+    std::lock_guard<std::mutex> lk(st->call_mu);
+    if (d_mask && !st->last_has_mask) return fail(CHB_ERR_STATE, "chb_fetch_last_device: the last call did not produce a mask");
+    Band& b = st->bands[dev_slot];
+    Dev& d = st->ctx->devs[b.dev_slot];
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpyAsync(d_image, b.d_out, b.frame_bytes, cudaMemcpyDeviceToDevice, d.compute));
+    if (d_mask) CU(cudaMemcpyAsync(d_mask, b.d_mask, b.frame_bytes, cudaMemcpyDeviceToDevice, d.compute));
     return CHB_OK;
 }
 extern "C" int chb_fetch_last(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
@@ -927,6 +984,7 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             b.vwarn_cap = n_windows;
         }
         cudaStream_t s = d.compute;
+        CU(wait_ingest(b, s));
         if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
         CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
         CU(cudaMemsetAsync(b.d_vwarn, 0, sizeof(unsigned long long) * (size_t)n_windows, s));
@@ -959,8 +1017,8 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             vb.out_masks = want_mask ? b.d_vmask[slot] : nullptr;
             vb.win_warnings = b.d_vwarn + w_lo;
             vb.gq = b.d_vqueue; vb.gq_count = b.d_vqcount; vb.gq_cap = kVideoQueueEntries;
-            if (const char* qc = getenv("CHB_VIDEO_QUEUE_CAP"))  // test aid: a small capacity exercises the in-place fallback
-                vb.gq_cap = (unsigned int)std::min<long long>(kVideoQueueEntries, std::max<long long>(0, atoll(qc)));
+            if (g_tune.video_queue_cap.load() >= 0)  // test aid: a small capacity exercises the in-place fallback
+                vb.gq_cap = (unsigned int)std::min<long long>(kVideoQueueEntries, g_tune.video_queue_cap.load());
             CU(cudaMemsetAsync(b.d_vqcount, 0, sizeof(unsigned int), s));
             CU(cudaMemsetAsync(b.d_vqcount + 1, 0xff, sizeof(unsigned int), s));
             const long long n_tasks = b.n_tiles * vb.n_blocks;
@@ -1078,6 +1136,7 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
         cudaStream_t s = d.compute;
+        CU(wait_ingest(b, s));
         SimpleArgs ab = a;
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;

@@ -10,6 +10,8 @@
 // hence no tensor-core use. Compiled with -fmad=false: Rust never contracts a*b+c, and blended bytes must round alike.
 #pragma once
 #include "chb_common.cuh"
+#include <climits>
+#include <type_traits>
 
 namespace chb {
 
@@ -120,6 +122,8 @@ struct OutlierArgs {
     int frame_offset;
     int exact_quartiles;     // 1: the fast tier computes exact quartiles (debug planes requested) instead of an IQR bound
     int contig_f0;           // >= 0: the window is the contiguous frame range starting here (position s = frame contig_f0 + s)
+    int mask_path;           // 1: integer distance, contiguous window of at most kMaskGroups groups: dense_masks_int + finish_masks
+    int inline_min;          // > 0 (G == 1 kernels): a tile with at least this many uncertified pixels is finished inside the streaming kernel
     unsigned long long seed, pixel_offset;
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
@@ -518,8 +522,383 @@ __device__ __forceinline__ void blend_into_f32_u8(float (&pa)[4], const uint8_t 
     }
 }
 
+// ---- dense per-frame pass (src/chrono.rs:261-288) for the integer distance: EVERY frame of a contiguous window is
+// classified, four frames per instruction group and without a data-dependent branch, at about a dozen instructions per
+// pixel-frame -- the path for pixels (noise at the threshold, iid bytes) where most 4-frame words hold a candidate, so
+// that a pre-test only adds work. A lane walks its pixel's 16-frame units group by group (three or four 128-bit loads,
+// the next group's in flight while the current one is evaluated). Per 4-frame word: the band-major words are transposed
+// to one word per frame (8 PRMT), L = |x - lo|, H = |x - hi| bytewise (2 VABSDIFF4 per frame) and
+// 4 dist_sq = L.L + H.H + 2 L.H (3 IDP.4A). Per frame: one compare sets the frame's bit in the group's 16-bit outlier mask
+// and a key 16 * (4 dist_sq) + (15 - j) tracks the group's first maximum. Per group: the masks give the outlier count, the
+// first non-outlier and the first / last outlier; the group's key is folded into (4 dist_sq << 12 | 4095 - position), whose
+// maximum over the window is the reference's first strict maximum. Outlier sums (--outlier average, --background average)
+// are taken under a branch in frame order (AVG).
+struct DensePass {
+    int k, first_idx, last_idx, first_non;
+    uint32_t maxkey;
+    float out_sum[4], mean_dist;
+};
+template <int C, bool AVG>
+__device__ __forceinline__ void dense_pass_int(const OutlierArgs& a, const uint8_t* colbase, long long band_stride, int f0, int n,
+                                               const float (&median)[4], DensePass& r) {
+    uint32_t lof = 0, hif = 0;  // frame-major constants: byte c = floor / ceil of band c's median (0 for a band of weight 0)
+    bool use[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        use[c] = (c < C) && (a.w[c] != 0.0f);
+        const int lo = (int)median[c];
+        const int hi = lo + (median[c] != (float)lo ? 1 : 0);
+        if (use[c]) { lof |= (uint32_t)lo << (8 * c); hif |= (uint32_t)hi << (8 * c); }
+    }
+    const int thr4 = a.thr4;
+    const uint32_t negthr = (uint32_t)(-thr4);
+    r.k = 0; r.first_idx = 0x7fffffff; r.last_idx = -1; r.first_non = 0x7fffffff; r.maxkey = 0; r.mean_dist = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) r.out_sum[c] = 0.0f;
+    const int gA = f0 >> 4, gB = (f0 + n - 1) >> 4;
+    uint4 cur[4], nxt[4];
+    auto load = [&](uint4 (&u)[4], int g) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            u[c] = (use[c] || (AVG && c < C)) ? __ldg(reinterpret_cast<const uint4*>(colbase + c * band_stride + (long long)g * (kTilePixels * kUnitBytes))) : make_uint4(0, 0, 0, 0);
+    };
+    // AVG sums the samples of every band, weight 0 or not: such a band is loaded and masked out of the distance
+    const uint32_t usemask = (use[0] ? 0xffu : 0u) | (use[1] ? 0xff00u : 0u) | (use[2] ? 0xff0000u : 0u) | (use[3] ? 0xff000000u : 0u);
+    load(cur, gA);
+#pragma unroll 1
+    for (int g = gA; g <= gB; g++) {
+        if (g < gB) load(nxt, g + 1);
+        const int sg = 16 * g - f0;  // window position of the group's frame 0
+        const bool full = (sg >= 0) && (sg + 16 <= n);
+        uint32_t om16 = 0;
+        int gkey = INT_MIN;  // max over the group's frames of 16 * (4 dist_sq - thr4) + (15 - j)
+        // FULL: every frame of the group lies in the window (all groups but the first and the last of a window); the bits of
+        // om16 are then collected by a funnel shift of the sign of (thr4 - 1 - d4), frame j at bit 15 - j, and reversed below
+        auto group_body = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t xw[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) xw[c] = q == 0 ? cur[c].x : (q == 1 ? cur[c].y : (q == 2 ? cur[c].z : cur[c].w));
+                const uint32_t t0 = __byte_perm(xw[0], xw[1], 0x5140), t1 = __byte_perm(xw[0], xw[1], 0x7362);
+                const uint32_t t2 = __byte_perm(xw[2], xw[3], 0x5140), t3 = __byte_perm(xw[2], xw[3], 0x7362);
+                const uint32_t pf[4] = {__byte_perm(t0, t2, 0x5410), __byte_perm(t0, t2, 0x7632), __byte_perm(t1, t3, 0x5410), __byte_perm(t1, t3, 0x7632)};
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const int j = 4 * q + kk;
+                    const uint32_t pfm = AVG ? (pf[kk] & usemask) : pf[kk];
+                    const uint32_t L = absdiff4(pfm, lof), H = absdiff4(pfm, hif);
+                    const uint32_t lh = __dp4a(L, H, 0u);
+                    // dm = 4 dist_sq - thr4 (the subtraction rides in the first accumulator): negative <=> not an outlier
+                    const int dm = (int)(__dp4a(H, H, __dp4a(L, L, negthr)) + lh + lh);
+                    if (FULL || (sg + j >= 0 && sg + j < n)) {  // uniform
+                        if (FULL && !AVG) {
+                            om16 = __funnelshift_l((uint32_t)dm, om16, 1);  // collects the NON-outlier bits, frame j at bit 15 - j
+                        } else {
+                            const bool isout = dm >= 0;
+                            om16 |= isout ? (1u << j) : 0u;
+                            if (AVG && isout) {  // frame order: the reference's f32 sum of sqrt(dist_sq) is order-dependent
+#pragma unroll
+                                for (int c = 0; c < 4; c++) r.out_sum[c] += (float)((pf[kk] >> (8 * c)) & 0xffu);
+                                r.mean_dist += sqrtf(0.25f * (float)(dm + thr4));
+                            }
+                        }
+                        gkey = max(gkey, dm * 16 + (15 - j));
+                    }
+                }
+            }
+            if (FULL && !AVG) om16 = (~__brev(om16)) >> 16;
+        };
+        if (full) group_body(std::true_type{});
+        else group_body(std::false_type{});
+        // ---- fold the group
+        uint32_t valid = 0xffffu;
+        if (!full) {
+            const int lo_j = sg < 0 ? -sg : 0, hi_j = (n - sg < 16) ? n - sg : 16;  // valid frames j in [lo_j, hi_j)
+            valid = ((1u << hi_j) - 1u) & ~((1u << lo_j) - 1u);
+        }
+        const uint32_t non = ~om16 & valid;
+        r.k += __popc(om16);
+        if (om16) {
+            r.first_idx = min(r.first_idx, sg + __ffs(om16) - 1);
+            r.last_idx = sg + 31 - __clz(om16);
+        }
+        if (non) r.first_non = min(r.first_non, sg + __ffs(non) - 1);
+        {
+            const int s = sg + 15 - (gkey & 15);
+            const uint32_t cand = ((uint32_t)((gkey >> 4) + thr4) << 12) | (uint32_t)(4095 - s);
+            // (a partial group without a valid frame cannot occur: gA and gB both hold window frames)
+            r.maxkey = max(r.maxkey, cand);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) cur[c] = nxt[c];
+    }
+}
+
+// ---- dense pass with per-group outlier masks (windows of at most kMaskGroups frame groups) -------------------------
+// Same classification as dense_pass_int, but the 16-bit outlier mask of every group is parked in a shared-memory slot of
+// the thread: the masks ARE the reference's outlier list (src/chrono.rs:280-287), so every background / outlier policy can
+// be finished by walking set bits (finish_masks) -- no second pass over the frames, whatever the policy. Two groups are
+// kept in registers, the reload of a buffer is issued as soon as the buffer has been evaluated.
+constexpr int kMaskGroups = 16;  // 256 frames: the G == 1 variants of K1 hold at most 13 groups
+struct MaskSlots {
+    uint32_t base;    // shared-memory address of this thread's first halfword
+    uint32_t stride;  // bytes between the halfwords of consecutive groups
+    __device__ __forceinline__ void put(int gi, uint32_t m) const { asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + gi * stride), "h"((unsigned short)m) : "memory"); }
+    __device__ __forceinline__ uint32_t get(int gi) const {
+        unsigned short v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + gi * stride));
+        return (uint32_t)v;
+    }
+};
+struct IntMedians {  // frame-major constants of the integer distance: byte c = floor / ceil of band c's median (0: weight 0)
+    uint32_t lof, hif;
+};
+template <int C>
+__device__ __forceinline__ IntMedians make_int_medians(const OutlierArgs& a, const float (&median)[4]) {
+    IntMedians m{0u, 0u};
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (a.w[c] != 0.0f) {
+            const int lo = (int)median[c];  // medians are >= 0: truncation is floor
+            const int hi = lo + (median[c] != (float)lo ? 1 : 0);
+            m.lof |= (uint32_t)lo << (8 * c);
+            m.hif |= (uint32_t)hi << (8 * c);
+        }
+    }
+    return m;
+}
+// 4 * dist_sq of one frame given as a frame-major word (byte c = band c; bands of weight 0 must be zero in x)
+__device__ __forceinline__ uint32_t int_dist_frame(const IntMedians& m, uint32_t x) {
+    const uint32_t L = absdiff4(x, m.lof), H = absdiff4(x, m.hif);
+    const uint32_t lh = __dp4a(L, H, 0u);
+    return __dp4a(H, H, __dp4a(L, L, 0u)) + lh + lh;
+}
+template <int C>
+__device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint8_t* colbase, long long band_stride, int f0, int n,
+                                                const IntMedians& im, const MaskSlots& ms, int& k_out, uint32_t& maxkey_out) {
+    const int thr4 = a.thr4;
+    const uint32_t negthr = (uint32_t)(-thr4);
+    const uint32_t lof = im.lof, hif = im.hif;
+    bool use[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) use[c] = (c < C) && (a.w[c] != 0.0f);
+    const int gA = f0 >> 4, gB = (f0 + n - 1) >> 4;
+    int k = 0;
+    uint32_t maxkey = 0;
+    auto load = [&](uint4 (&u)[4], int g) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            u[c] = use[c] ? __ldg(reinterpret_cast<const uint4*>(colbase + c * band_stride + (long long)g * (kTilePixels * kUnitBytes))) : make_uint4(0, 0, 0, 0);
+    };
+    auto group = [&](const uint4 (&u)[4], int g) {
+        const int sg = 16 * g - f0;  // window position of the group's frame 0
+        const bool full = (sg >= 0) && (sg + 16 <= n);
+        uint32_t om16 = 0;
+        int gkey = INT_MIN;  // max over the group's frames of 16 * (4 dist_sq - thr4) + (15 - j)
+        auto body = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t xw[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) xw[c] = q == 0 ? u[c].x : (q == 1 ? u[c].y : (q == 2 ? u[c].z : u[c].w));
+                const uint32_t t0 = __byte_perm(xw[0], xw[1], 0x5140), t1 = __byte_perm(xw[0], xw[1], 0x7362);
+                const uint32_t t2 = __byte_perm(xw[2], xw[3], 0x5140), t3 = __byte_perm(xw[2], xw[3], 0x7362);
+                const uint32_t pf[4] = {__byte_perm(t0, t2, 0x5410), __byte_perm(t0, t2, 0x7632), __byte_perm(t1, t3, 0x5410), __byte_perm(t1, t3, 0x7632)};
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const int j = 4 * q + kk;
+                    const uint32_t L = absdiff4(pf[kk], lof), H = absdiff4(pf[kk], hif);
+                    const uint32_t lh = __dp4a(L, H, 0u);
+                    // dm = 4 dist_sq - thr4 (the subtraction rides in the first accumulator): negative <=> not an outlier
+                    const int dm = (int)(__dp4a(H, H, __dp4a(L, L, negthr)) + lh + lh);
+                    if (FULL) {
+                        om16 = __funnelshift_l((uint32_t)dm, om16, 1);  // collects the NON-outlier bits, frame j at bit 15 - j
+                        gkey = max(gkey, dm * 16 + (15 - j));
+                    } else if (sg + j >= 0 && sg + j < n) {  // uniform: first / last group of a window
+                        om16 |= dm >= 0 ? (1u << j) : 0u;
+                        gkey = max(gkey, dm * 16 + (15 - j));
+                    }
+                }
+            }
+            if (FULL) om16 = (~__brev(om16)) >> 16;
+        };
+        if (full) body(std::true_type{});
+        else body(std::false_type{});
+        ms.put(g - gA, om16);
+        k += __popc(om16);
+        const int s = sg + 15 - (gkey & 15);
+        maxkey = max(maxkey, ((uint32_t)((gkey >> 4) + thr4) << 12) | (uint32_t)(4095 - s));
+    };
+    // one copy of the group body in the instruction stream (the streaming kernel's warps interleave this loop with the band
+    // code: the footprint decides whether both stay in the instruction cache): the next group's loads are issued into a
+    // second register set before the current group is evaluated, then moved over
+    uint4 cur[4], nxt[4];
+    load(cur, gA);
+#pragma unroll 1
+    for (int g = gA; g <= gB; g++) {
+        if (g < gB) load(nxt, g + 1);
+        group(cur, g);
+#pragma unroll
+        for (int c = 0; c < 4; c++) cur[c] = nxt[c];
+    }
+    k_out = k;
+    maxkey_out = maxkey;
+}
+
+// Everything calc_pixel does after the classification loop (src/chrono.rs:290-494), from the per-group outlier masks:
+// set bits are the outlier list in frame order. Returns the mask byte; `pixel` receives the composite.
+template <int C>
+__device__ __forceinline__ uint8_t finish_masks(const OutlierArgs& a, const uint8_t* colbase, long long band_stride, unsigned long long pixel_id,
+                                                const float (&median)[4], const uint32_t (&band_sum)[4], const IntMedians& im, const MaskSlots& ms,
+                                                int f0, int n, int frame_offset, int k, uint32_t maxkey, uint8_t (&pixel)[4], int& warn) {
+    const int gA = f0 >> 4, n_g = ((f0 + n - 1) >> 4) - gA + 1;
+    const int bit0 = f0 & 15;  // window position s sits at bit (s + bit0) & 15 of group (s + bit0) >> 4
+    const uint32_t usemask = (a.w[0] != 0.0f ? 0xffu : 0u) | (a.w[1] != 0.0f ? 0xff00u : 0u) | (a.w[2] != 0.0f ? 0xff0000u : 0u) |
+                             ((C > 3 && a.w[3] != 0.0f) ? 0xff000000u : 0u);
+    auto sample = [&](int s) -> uint32_t {  // the pixel of window position s, band c in byte c
+        const int f = f0 + s;
+        const uint8_t* p = colbase + (long long)(f >> 4) * (kTilePixels * kUnitBytes) + (f & 15);
+        uint32_t v = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) v |= (uint32_t)__ldg(p + c * band_stride) << (8 * c);
+        return v;
+    };
+    auto unpack = [&](uint32_t v, uint8_t (&px)[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) px[c] = (uint8_t)((v >> (8 * c)) & 0xffu);
+    };
+    auto dist_of = [&](uint32_t v) { return 0.25f * (float)int_dist_frame(im, v & usemask); };  // dist_sq, exact in f32
+    warn = 0;
+    const bool has_outliers = k > 0;
+    float out_sum[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mean_dist = 0.0f;
+    const bool need_avg = has_outliers && (a.om == 3 || a.bg == 2);
+    if (need_avg) {  // outlier sums in frame order (the f32 sum of sqrt(dist_sq) is order-dependent)
+        for (int gi = 0; gi < n_g; gi++) {
+            uint32_t m = ms.get(gi);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t v = sample(16 * gi + b - bit0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) out_sum[c] += (float)((v >> (8 * c)) & 0xffu);
+                mean_dist += sqrtf(dist_of(v));
+            }
+        }
+    }
+    // background (src/chrono.rs:294-375)
+    if (a.bg == 2) {
+        const float ratio = (float)n / (float)(n - k);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const float mean = (float)band_sum[c] / (float)n;
+            pixel[c] = has_outliers ? sat_u8(roundf(mean * ratio - out_sum[c] / (float)n)) : sat_u8(roundf(mean));
+        }
+    } else if (a.bg == 3) {
+#pragma unroll
+        for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(median[c]));
+    } else {
+        int idx = 0;
+        if (a.bg == 0) {  // first_excluded (src/chrono.rs:505-530)
+            if (has_outliers) {
+                if (k == n) warn = 1;
+                else {
+                    for (int gi = 0; gi < n_g; gi++) {
+                        // valid bits of group gi: positions 16 gi + b - bit0 in [0, n)
+                        const int lo_b = gi == 0 ? bit0 : 0, hi_b = min(16, n + bit0 - 16 * gi);
+                        const uint32_t valid = ((1u << hi_b) - 1u) & ~((1u << lo_b) - 1u);
+                        const uint32_t non = ~ms.get(gi) & valid;
+                        if (non) { idx = 16 * gi + __ffs(non) - 1 - bit0; break; }
+                    }
+                }
+            }
+        } else {  // sample_excluded (src/chrono.rs:532-555), closed form of the position swaps (see exact_pixel)
+            if (!has_outliers) idx = (int)rng_range(a.seed, pixel_id, 0, (uint32_t)n);
+            else if (k == n) { idx = (int)rng_range(a.seed, pixel_id, 0, (uint32_t)n); warn = 1; }
+            else {
+                const int r = (int)rng_range(a.seed, pixel_id, 0, (uint32_t)(n - k));
+                const int rb = r + bit0, rg = rb >> 4;
+                idx = r;
+                if ((ms.get(rg) >> (rb & 15)) & 1u) {
+                    int order = __popc(ms.get(rg) & ((1u << (rb & 15)) - 1u));  // outliers before r
+                    for (int gi = 0; gi < rg; gi++) order += __popc(ms.get(gi));
+                    idx = n - 1 - order;
+                }
+            }
+        }
+        unpack(sample(idx), pixel);
+    }
+    if (!has_outliers) return 0;
+
+    auto first_bit = [&]() {
+        for (int gi = 0; gi < n_g; gi++) {
+            const uint32_t m = ms.get(gi);
+            if (m) return 16 * gi + __ffs(m) - 1 - bit0;
+        }
+        return 0;
+    };
+    auto last_bit = [&]() {
+        for (int gi = n_g - 1; gi >= 0; gi--) {
+            const uint32_t m = ms.get(gi);
+            if (m) return 16 * gi + 31 - __clz(m) - bit0;
+        }
+        return 0;
+    };
+    uint8_t smp[4] = {0, 0, 0, 0};
+    if (k > 1 && (a.om == 4 || a.om == 5)) {  // forward / backward (src/chrono.rs:391-427): the list in (reverse) frame order
+        float pix_new[4], blend_inv = 1.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) pix_new[c] = (float)pixel[c];
+        for (int t = 0; t < n_g; t++) {
+            const int gi = a.om == 4 ? t : n_g - 1 - t;
+            uint32_t m = ms.get(gi);
+            while (m) {
+                const int b = a.om == 4 ? __ffs(m) - 1 : 31 - __clz(m);
+                m &= ~(1u << b);
+                const int s = 16 * gi + b - bit0;
+                const uint32_t v = sample(s);
+                unpack(v, smp);
+                const float blend = fade_for(a.fade, s, n, frame_offset) * blend_value(a, sqrtf(dist_of(v)));
+                blend_into_f32_u8(pix_new, smp, C, blend);
+                blend_inv *= 1.0f - blend;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(pix_new[c]));
+        return sat_u8(roundf((1.0f - blend_inv) * 255.0f));
+    }
+    int sidx;
+    float dist;
+    if (k > 1 && a.om == 3) {  // average (src/chrono.rs:430-468)
+#pragma unroll
+        for (int c = 0; c < C; c++) smp[c] = sat_u8(roundf(out_sum[c] / (float)k));
+        sidx = 0;
+        dist = mean_dist / (float)k;
+    } else {  // a single outlier (:379-388), or first / last / extreme (:470-483)
+        float dsq;
+        if (k == 1 || a.om == 2 || a.om >= 3) {  // the only outlier is the maximum
+            sidx = 4095 - (int)(maxkey & 4095u);
+            dsq = 0.25f * (float)(maxkey >> 12);
+            unpack(sample(sidx), smp);
+        } else {
+            sidx = a.om == 0 ? first_bit() : last_bit();
+            const uint32_t v = sample(sidx);
+            unpack(v, smp);
+            dsq = dist_of(v);
+        }
+        dist = sqrtf(dsq);
+    }
+    const float blend = fade_for(a.fade, sidx, n, frame_offset) * blend_value(a, dist);  // src/chrono.rs:485-488
+    blend_into_u8(pixel, smp, C, blend);
+    return sat_u8(roundf(blend * 255.0f));
+}
+
 // Returns the mask byte; writes the composite pixel; n_out = number of outliers; warn = all-outlier warning.
 // `active` lanes hold a pixel; inactive lanes run along (uniform loops) and their results are discarded.
+// DENSE (single-window launches of K1): contiguous windows with the integer distance take dense_pass_int for pass 1.
+template <int CT = 0, bool DENSE = false>
 __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const PixelSrc& src, unsigned long long pixel_id,
                                                const float (&median)[4], const float (&iqr_inv)[4], const uint32_t (&band_sum)[4],
                                                uint8_t (&pixel)[4], int& n_out, int& warn, int contig_f0, int frame_offset) {
@@ -556,7 +935,44 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
             first_non = s;
         }
     };
-    if (contig_f0 >= 0) {  // contiguous window: position s is frame contig_f0 + s; aligned words are pre-tested four frames at a time
+    if (DENSE && a.int_dist && contig_f0 >= 0) {
+        // every frame classified by the branch-free integer pass; the per-policy values are read off its summary
+        DensePass dp;
+        const uint8_t* colbase = src.tile + (long long)src.p * kUnitBytes;
+        const long long bstride = (long long)src.NG * kTilePixels * kUnitBytes;
+        if (need_avg) dense_pass_int<CT, true>(a, colbase, bstride, contig_f0, n, median, dp);
+        else dense_pass_int<CT, false>(a, colbase, bstride, contig_f0, n, median, dp);
+        k = dp.k;
+        if (k > 0) {
+            max_index = 4095 - (int)(dp.maxkey & 4095u);
+            max_dist_sq = 0.25f * (float)(dp.maxkey >> 12);
+            first_idx = dp.first_idx; last_idx = dp.last_idx;
+            auto d4_at = [&](int s) {  // 4 * dist_sq of one frame (src/chrono.rs:265-278 on integers, see IntDist)
+                rd.fetch(contig_f0 + s, px);
+                uint32_t d4 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < C && a.w[i] != 0.0f) {
+                        const int lo = (int)median[i], hi = lo + (median[i] != (float)lo ? 1 : 0);
+                        const int t = abs((int)px[i] - lo) + abs((int)px[i] - hi);
+                        d4 += (uint32_t)(t * t);
+                    }
+                }
+                return 0.25f * (float)d4;
+            };
+            if (k == 1) { first_d = max_dist_sq; last_d = max_dist_sq; }  // the only outlier is the maximum
+            else {
+                if (a.om == 0) first_d = d4_at(first_idx);
+                if (a.om == 1) last_d = d4_at(last_idx);
+            }
+            if (need_avg) {
+                mean_dist = dp.mean_dist;
+#pragma unroll
+                for (int i = 0; i < 4; i++) out_sum[i] = dp.out_sum[i];
+            }
+        }
+        first_non = dp.first_non == 0x7fffffff ? -1 : dp.first_non;
+    } else if (contig_f0 >= 0) {  // contiguous window: position s is frame contig_f0 + s; aligned words are pre-tested four frames at a time
         int s = 0;
         while (s < n) {
             const int f = contig_f0 + s;
@@ -857,9 +1273,10 @@ struct QueueEntry {
 };
 constexpr int kBarBytes = 128;
 constexpr int kAccBytes = kWarpsPerCta * 32 * 12 * 4;
+constexpr int kMaskBytes = kWarpsPerCta * 32 * kMaskGroups * 2;  // per-thread outlier masks of the in-kernel dense pass
 // dynamic shared memory of one CTA: one mbarrier per warp, per-thread result slots, one staged pixel-band per warp (G == 1: the tile's contiguous slab; G > 1: every lane's own units, [slot][lane])
 __host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) {
-    return kBarBytes + kAccBytes + kWarpsPerCta * wpl * 512;  // g == 1: one slab per warp; g > 1: wpl units per lane
+    return kBarBytes + kAccBytes + kWarpsPerCta * wpl * 512 + kMaskBytes;  // g == 1: one slab per warp; g > 1: wpl units per lane; then the mask slots
 }
 
 template <int C>
@@ -872,26 +1289,57 @@ __device__ __forceinline__ void store_pixel(const OutlierArgs& a, long long pix,
     }
 }
 
+// Dense per-frame pass + finish for the 32 pixels (one per lane) whose unit columns start at colbase; lanes that are not
+// `active` run along and their results are discarded. Returns the ballot of active lanes with an all-outlier warning.
 template <int C>
-__device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry* slot, bool in_range, int lane) {
-    QueueEntry e = *slot;
-    const bool active = in_range && e.pix >= 0;
+__device__ __forceinline__ unsigned dense_pixels(const OutlierArgs& a, const uint8_t* colbase, long long pix, bool active, const float (&median)[4],
+                                                 const uint32_t (&band_sum)[4], const MaskSlots& ms) {
+    const long long bstride = (long long)a.NG * kTilePixels * kUnitBytes;
+    const IntMedians im = make_int_medians<C>(a, median);
+    int k = 0, warn = 0;
+    uint32_t maxkey = 0;
+    dense_masks_int<C>(a, colbase, bstride, a.contig_f0, a.n, im, ms, k, maxkey);
+    uint8_t pixel[4] = {0, 0, 0, 0};
+    const uint8_t mask = finish_masks<C>(a, colbase, bstride, a.pixel_offset + (unsigned long long)pix, median, band_sum, im, ms, a.contig_f0, a.n,
+                                         a.frame_offset, k, maxkey, pixel, warn);
+    if (active) {
+        store_pixel<C>(a, pix, pixel, mask);
+        if (a.dbg_nout) a.dbg_nout[pix] = k;
+    }
+    return __ballot_sync(0xffffffffu, active && warn);
+}
+
+template <int C>
+__device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry* slot, bool in_range, int lane, const MaskSlots& ms) {
+    long long pix = in_range ? slot->pix : -1;
+    const bool active = pix >= 0;
     const unsigned act = __ballot_sync(0xffffffffu, active);
     if (act == 0) return;
-    {   // lanes without a pixel run along on a copy of the first active lane's entry; their results are discarded
+    {   // lanes without a pixel run along on the first active lane's entry; their results are discarded
         const unsigned long long first = __shfl_sync(0xffffffffu, (unsigned long long)slot, __ffs(act) - 1);
-        if (!active) e = *reinterpret_cast<const QueueEntry*>(first);
+        if (!active) { slot = reinterpret_cast<const QueueEntry*>(first); pix = slot->pix; }
     }
-    const long long tile = e.pix >> 5;
-    const PixelSrc src{a.stack + tile * tile_bytes(C, a.NG), a.NG, C, (int)(e.pix & 31)};
-    uint8_t pixel[4] = {0, 0, 0, 0};
-    int n_out = 0, warn = 0;
-    const uint8_t mask = exact_pixel(a, src, a.pixel_offset + (unsigned long long)e.pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn, a.contig_f0, a.frame_offset);
-    if (active) {
-        store_pixel<C>(a, e.pix, pixel, mask);
-        if (a.dbg_nout) a.dbg_nout[e.pix] = n_out;
+    const long long tile = pix >> 5;
+    const uint8_t* tile_base = a.stack + tile * tile_bytes(C, a.NG);
+    unsigned wb;
+    if (a.mask_path) {
+        float median[4];
+        uint32_t sum[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { median[c] = slot->median[c]; sum[c] = slot->sum[c]; }
+        wb = dense_pixels<C>(a, tile_base + (pix & 31) * kUnitBytes, pix, active, median, sum, ms);
+    } else {
+        const QueueEntry e = *slot;
+        const PixelSrc src{tile_base, a.NG, C, (int)(pix & 31)};
+        uint8_t pixel[4] = {0, 0, 0, 0};
+        int n_out = 0, warn = 0;
+        const uint8_t mask = exact_pixel<C, true>(a, src, a.pixel_offset + (unsigned long long)pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn, a.contig_f0, a.frame_offset);
+        if (active) {
+            store_pixel<C>(a, pix, pixel, mask);
+            if (a.dbg_nout) a.dbg_nout[pix] = n_out;
+        }
+        wb = __ballot_sync(0xffffffffu, active && warn);
     }
-    const unsigned wb = __ballot_sync(0xffffffffu, active && warn);
     if (lane == 0) {
         if (wb) atomicAdd(a.counters, (unsigned long long)__popc(wb));
         atomicAdd(a.counters + 1, (unsigned long long)__popc(act));
@@ -1095,7 +1543,7 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
 
 // Hard pixels, 32/G at a time: each pixel group reloads its own bands (L2) and runs the iterative solver.
 template <int C, int WPL, int G, int MODE>
-__device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase, int count, int lane, int cap, int pad, uint32_t acc_slot) {
+__device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase, int count, int lane, int cap, int pad, uint32_t acc_slot, const MaskSlots& ms) {
     const long long* hq = a.ghq + hbase;
     constexpr int W4 = 4 * WPL;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
@@ -1120,7 +1568,40 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase
         }
         process_band<C, WPL, G, MODE, false>(a, A, c, j, pix, active && j == 0, cap, pad, acc);
     }
-    finish_pixel<C>(a, acc, pix, p, active && j == 0, lane, (long long)hbase + pl);
+    // a warp-full of mostly uncertified pixels (iid bytes, heavy noise) is classified frame by frame right here instead of going
+    // through the exact-path queue; its queue slots are marked empty
+    bool finished_here = false;
+    if (G == 1 && MODE != 2 && a.inline_min > 0) {
+        const bool dirty = active && !(acc.bound * 1.0001f < a.thr_sq);
+        const unsigned db = __ballot_sync(0xffffffffu, dirty);
+        if (__popc(db) >= a.inline_min) {
+            float median[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            uint32_t sum[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int c = 0; c < C; c++) { median[c] = acc.median(c); sum[c] = acc.sum(c); }
+            const uint8_t* colbase = a.stack + tile * tile_bytes(C, a.NG) + p * kUnitBytes;
+            const unsigned wb = dense_pixels<C>(a, colbase, pix, dirty, median, sum, ms);
+            if (lane == 0) {
+                if (wb) atomicAdd(a.counters, (unsigned long long)__popc(wb));
+                atomicAdd(a.counters + 1, (unsigned long long)__popc(db));
+            }
+            if (dirty) a.gq[(long long)hbase + pl].pix = -1;
+            finished_here = dirty;
+        }
+    }
+    finish_pixel<C>(a, acc, pix, p, active && j == 0 && !finished_here, lane, (long long)hbase + pl);
+}
+
+// One tile finished inside the streaming kernel: lane = pixel of the tile, medians and sums from the thread's result slots.
+template <int C>
+__device__ __noinline__ void inline_dense_tile(const OutlierArgs& a, int tile, int lane, long long pix, bool dirty, const PixelAcc& acc, const MaskSlots& ms) {
+    float median[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t sum[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int c = 0; c < C; c++) { median[c] = acc.median(c); sum[c] = acc.sum(c); }
+    const uint8_t* colbase = a.stack + (long long)tile * tile_bytes(C, a.NG) + lane * kUnitBytes;
+    const unsigned wb = dense_pixels<C>(a, colbase, pix, dirty, median, sum, ms);
+    if (lane == 0 && wb) atomicAdd(a.counters, (unsigned long long)__popc(wb));
 }
 
 template <int C, int WPL, int G, int MODE>
@@ -1147,6 +1628,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     uint8_t* const stage = smem_raw + kBarBytes + kAccBytes + warp_in_cta * (WPL * 512);
     const uint32_t stage_lane = smem_u32(stage) + j * kRowBytes + pl * 16;  // this lane's 16 bytes of row (slot * G + j)
     const int staged_groups = a.n_groups < WPL * G ? a.n_groups : WPL * G;
+    const MaskSlots mask_slots{smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512)) + threadIdx.x * 2, kWarpsPerCta * 32u * 2u};
     uint32_t parity = 0;
     if (kStage) {
         if (lane == 0) mbar_init(bar, 1);
@@ -1241,7 +1723,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
                 atomicOr(a.hflags + tile, hb << ((task % G) * PPW));
             }
         }
-        finish_pixel<C>(a, acc, pix, p, owner && !to_hard, lane);
+        // ---- tiles where many pixels stay uncertified (noise at the threshold): classify every frame of all 32 pixels right here,
+        // while the tile's bytes are still in L2, instead of queueing the pixels one by one (G == 1: lane = pixel of the tile)
+        bool finished_here = false;
+        if (G == 1 && MODE != 2 && a.inline_min > 0) {
+            const bool dirty = owner && !to_hard && !(acc.bound * 1.0001f < a.thr_sq);
+            const unsigned db = __ballot_sync(0xffffffffu, dirty);
+            if (__popc(db) >= a.inline_min) {
+                inline_dense_tile<C>(a, tile, lane, pix, dirty, acc, mask_slots);
+                if (lane == 0) atomicAdd(a.counters + 1, (unsigned long long)__popc(db));
+                finished_here = dirty;
+            }
+        }
+        finish_pixel<C>(a, acc, pix, p, owner && !to_hard && !finished_here, lane);
         task += n_warps;
     }
 }
@@ -1256,10 +1750,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard
     const int lane = threadIdx.x & 31;
     const int cap = 4 * WPL * 4 * G, pad = cap - a.n_sub;
     const uint32_t acc_slot = smem_u32(smem_raw + kBarBytes) + threadIdx.x * 4;
+    const MaskSlots ms{smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512)) + threadIdx.x * 2, kWarpsPerCta * 32u * 2u};
     const unsigned int total = a.ghq_count[0];
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PPW; base < total; base += n_warps * PPW)
-        drain_hard<C, WPL, G, MODE>(a, base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, acc_slot);
+        drain_hard<C, WPL, G, MODE>(a, base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, acc_slot, ms);
 }
 
 // Iterative tier for long whole-stack series (hundreds of frames): instead of the solver's repeated passes over the pixel's
@@ -1391,6 +1886,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
 template <int C>
 __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
     grid_dependency_wait();
+    __shared__ unsigned short mask_words[kMaskGroups][256];  // per-thread outlier masks of the dense pass
+    const MaskSlots ms{smem_u32(&mask_words[0][threadIdx.x]), 256u * 2u};
     const unsigned int mirrored = a.ghq_count[0], total = mirrored + a.gq_count[0];
     const int lane = threadIdx.x & 31;
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -1398,7 +1895,7 @@ __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(cons
         const unsigned int v = base + lane;
         const bool in_range = v < total;
         const long long slot = !in_range ? 0 : (v < mirrored ? (long long)v : a.n_pixels - 1 - (long long)(v - mirrored));
-        drain_queue<C>(a, a.gq + slot, in_range, lane);
+        drain_queue<C>(a, a.gq + slot, in_range, lane, ms);
     }
 }
 

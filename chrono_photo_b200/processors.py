@@ -298,6 +298,18 @@ class SimpleProcessor:
         return ms.value
 
 
+def set_tuning(key, value):
+    """Tuning / test knobs of the library (chb_set_tuning): 'force_variant', 'hist', 'pdl', 'video_queue_cap', 'inline_min'."""
+    _lib.check(_lib.lib().chb_set_tuning(str(key).encode(), int(value)))
+
+
+def fetch_last_device(stack, d_image_ptr, d_mask_ptr=None, dev_slot=0):
+    """The last call's band of device slot dev_slot copied into caller-owned device buffers (raw device pointers), on the
+    context's compute stream -- the input of a band gather over NVLink (chb_fetch_last_device)."""
+    _lib.check(_lib.lib().chb_fetch_last_device(stack._h, int(dev_slot), C.c_void_p(int(d_image_ptr)),
+                                                C.c_void_p(int(d_mask_ptr)) if d_mask_ptr else None))
+
+
 def fetch_last(stack, want_mask=False):
     out = np.empty((stack.height, stack.width, stack.channels), dtype=np.uint8)
     mask = np.empty_like(out) if want_mask else None

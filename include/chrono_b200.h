@@ -155,6 +155,10 @@ int chb_outlier_device(chb_stack *stack, const chb_outlier_params *params, const
                        int want_mask, float *kernel_ms);
 int chb_simple_device(chb_stack *stack, const chb_simple_params *params, const int32_t *indices, int n_indices, float *kernel_ms);
 int chb_fetch_last(chb_stack *stack, uint8_t *out_image, uint8_t *out_mask, uint64_t *n_warnings);
+/* The band of device slot dev_slot of the stack's last compositing call, copied into caller-owned DEVICE buffers on that
+ * GPU (rows * W * C bytes each; d_mask nullable), asynchronously on the context's compute stream: the input of the final
+ * band gather when one rank per GPU holds a band and the image is assembled over NVLink. */
+int chb_fetch_last_device(chb_stack *stack, int dev_slot, void *d_image, void *d_mask);
 /* Back-to-back launches without a host round trip per call: chb_outlier_enqueue only launches (it waits by itself when
  * the window / sample / fade tables differ from the previous call's), chb_stack_wait waits for everything enqueued and
  * returns the device time of the last launch and its warning count. */
@@ -185,6 +189,10 @@ uint64_t chb_last_hard_pixels(void);
 /* Device time (ms, max over devices) of the streaming kernel alone in the calling thread's last outlier call; the call's
  * kernel_ms also covers the two tier kernels that follow it. */
 float chb_last_main_kernel_ms(void); /* pixels whose medians needed the iterative solver */
+
+/* Tuning / test knobs (not needed for normal use; initial values come from the environment variables CHB_<KEY> read once at
+ * load time): "force_variant", "hist", "pdl", "video_queue_cap", "inline_min"; value -1 = automatic. */
+int chb_set_tuning(const char *key, int value);
 
 /* The --sample subset the library draws for (seed, window length n, cnt): cnt ascending positions in [0, n).
  * Deterministic replacement of rand::seq::sample_indices (src/chrono.rs:157), exported so a checker can use the same set. */

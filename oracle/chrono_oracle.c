@@ -791,3 +791,83 @@ int orc_video_windows(int image_count, int in_has_start, int in_start, int in_ha
     }
     return count < 0 ? 0 : count;
 }
+
+/* ------------------------------------------------------------------------------------------------ synthetic series
+ * Twin of the device generator (chrono_photo_b200/csrc/chb_common.cuh synth_byte; recipes of SURVEY.md 8d / DESIGN.md):
+ * the bench's reference arm and the post-run verification build their input without touching the product library.
+ * kind 1 = S1 (src/util/create_example_data.rs:10-49 without the JPEG round trip), 2 = S2 (gradient + uniform noise
+ * +-5 + 8 discs), 3 = iid uniform bytes, 4 = gradient + Gaussian-like noise + discs. Not part of the reference. */
+static inline uint32_t synth_hash32(uint64_t seed, uint32_t f, uint32_t y, uint32_t x, uint32_t ch) {
+    uint64_t z = seed ^ (0x9E3779B97F4A7C15ULL * ((uint64_t)f + 1));
+    z ^= ((uint64_t)y << 32) | (uint64_t)x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z += (uint64_t)ch * 0xD1B54A32D192ED03ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+
+static uint8_t synth_sample(int kind, uint64_t seed, int f, int n_frames, int y, int x, int ch, int W, int H) {
+    const uint32_t h = synth_hash32(seed, (uint32_t)f, (uint32_t)y, (uint32_t)x, (uint32_t)ch);
+    if (kind == 3) return (uint8_t)(h >> 24);
+    if (kind == 1) {
+        int v = (ch == 2 ? 140 : 240) + (int)(((uint64_t)h * 10) >> 32);
+        if (ch == 0) {
+            int dx = x - (100 + f * 10), dy = y - (H / 3 + f * 5);
+            if (dx >= -8 && dx <= 8 && dy >= -8 && dy <= 8) v = 0;
+            dx = x - (W - 24);
+            dy = y - (H - 68);
+            if (dx >= -8 && dx <= 8 && dy >= -8 && dy <= 8) v = 0;
+        }
+        return (uint8_t)v;
+    }
+    int v = 48 + (int)(((long long)x * 96) / W) + (int)(((long long)y * 64) / H) + 16 * ch;
+    if (kind == 2) v += (int)(((uint64_t)h * 11) >> 32) - 5;
+    else v += (int)(h & 7) + (int)((h >> 8) & 7) + (int)((h >> 16) & 7) + (int)((h >> 24) & 7) - 14;
+    for (int k = 0; k < 8; k++) { /* disc k on its linear track, wrapping around the image */
+        const long long x0 = ((long long)W * (2 * k + 1)) / 16, y0 = ((long long)H * ((5 * k + 3) % 16)) / 16;
+        const long long lx = 200LL * (1 + (k % 3)), ly = (k & 1) ? 200LL : -200LL;
+        const long long nf = n_frames > 0 ? n_frames : 1;
+        const long long cx = (x0 + (lx * f) / nf) % W, cy = ((y0 + (ly * f) / nf) % H + H) % H;
+        const long long dx = x - cx, dy = y - cy;
+        if (dx * dx + dy * dy <= 1600) v = (k & 1) ? 232 - 8 * ch : 24 + 8 * ch;
+    }
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+typedef struct {
+    int kind, f0, n_out, n_frames, W, H, C, row0, rows, t, n_threads;
+    uint64_t seed;
+    uint8_t *out;
+} synth_job_t;
+
+static void *synth_worker(void *arg) {
+    const synth_job_t *J = (const synth_job_t *)arg;
+    const long long tasks = (long long)J->n_out * J->rows;
+    for (long long task = J->t; task < tasks; task += J->n_threads) {
+        const int fi = (int)(task / J->rows), r = (int)(task % J->rows);
+        uint8_t *o = J->out + ((size_t)fi * J->rows + r) * (size_t)J->W * J->C;
+        for (int x = 0; x < J->W; x++)
+            for (int c = 0; c < J->C; c++)
+                o[(size_t)x * J->C + c] = synth_sample(J->kind, J->seed, J->f0 + fi, J->n_frames, J->row0 + r, x, c, J->W, J->H);
+    }
+    return NULL;
+}
+
+/* Frames [f0, f0 + n_out) of an n_frames series, rows [row0, row0 + rows) of a W x H image: out is [n_out][rows][W][C]. */
+int orc_synth_frames(int kind, uint64_t seed, int f0, int n_out, int n_frames, int width, int full_height, int channels,
+                     int row0, int rows, uint8_t *out, int n_threads) {
+    if (!out || kind < 1 || kind > 4 || width < 1 || rows < 0 || n_out < 0 || channels < 1 || channels > 4) return -1;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_t th[256];
+    synth_job_t J[256];
+    for (int t = 0; t < n_threads; t++) {
+        J[t] = (synth_job_t){kind, f0, n_out, n_frames, width, full_height, channels, row0, rows, t, n_threads, seed, out};
+        if (n_threads > 1) pthread_create(&th[t], NULL, synth_worker, &J[t]);
+    }
+    if (n_threads == 1) synth_worker(&J[0]);
+    else
+        for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    return 0;
+}

@@ -131,6 +131,11 @@ int orc_video_windows(int image_count,
                       int out_has_start, int out_start, int out_has_end, int out_end, int out_step,
                       int32_t *win_start, int32_t *win_end, int32_t *out_number, int cap);
 
+/* Synthetic series of the bench / tests (twin of the device generator, not part of the reference): frames [f0, f0 + n_out)
+ * of an n_frames series, rows [row0, row0 + rows) of a width x full_height image, out = [n_out][rows][width][channels]. */
+int orc_synth_frames(int kind, uint64_t seed, int f0, int n_out, int n_frames, int width, int full_height, int channels,
+                     int row0, int rows, uint8_t *out, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

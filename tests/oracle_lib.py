@@ -66,6 +66,7 @@ def lib():
         l.orc_fade_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
         l.orc_crop_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         l.orc_video_windows.argtypes = [C.c_int] * 11 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        l.orc_synth_frames.argtypes = [C.c_int, C.c_uint64] + [C.c_int] * 8 + [C.c_void_p, C.c_int]
         _lib = l
     return _lib
 
@@ -216,3 +217,17 @@ def video_windows(image_count, vin, vout, cap=4096):
                                 ws.ctypes.data, we.ctypes.data, num.ctypes.data, cap)
     m = min(n, cap)
     return n, ws[:m], we[:m], num[:m]
+
+
+def synth_frames(kind, seed, n_frames, width, full_height, channels=3, row0=0, rows=None, f0=0, n_out=None, n_threads=None):
+    """Synthetic series of the bench / tests generated on the host by the oracle's twin of the device generator:
+    frames [f0, f0 + n_out) of an n_frames series, rows [row0, row0 + rows) -> uint8 [n_out][rows][width][channels]."""
+    rows = full_height - row0 if rows is None else rows
+    n_out = n_frames - f0 if n_out is None else n_out
+    n_threads = (os.cpu_count() or 1) if n_threads is None else n_threads
+    out = np.empty((n_out, rows, width, channels), dtype=np.uint8)
+    rc = lib().orc_synth_frames(int(kind), int(seed), int(f0), int(n_out), int(n_frames), int(width), int(full_height), int(channels),
+                                int(row0), int(rows), out.ctypes.data, int(n_threads))
+    if rc != 0:
+        raise ValueError("orc_synth_frames: bad argument")
+    return out

@@ -378,7 +378,7 @@ def test_config5_chrono_video_with_shake_crop(ctx):
     fs.close()
 
 
-def test_long_series_histogram_tier(ctx, monkeypatch):
+def test_long_series_histogram_tier(ctx):
     # whole-stack series of >= 256 frames send the iterative tier through the shared-memory histogram kernel; shorter ones
     # (and CHB_HIST=0) through the solver. Both must equal the oracle: iid bytes (every pixel), objects, flat bands, RGBA.
     rng = np.random.default_rng(21)
@@ -387,12 +387,15 @@ def test_long_series_histogram_tier(ctx, monkeypatch):
     flat = np.full((256, 4, 32, 3), 255, np.uint8)
     flat[::7, :, :5] = 0
     rgba = make_stack(rng, 257, 5, 33, 4, n_obj=40, noise=12)
-    for force in ("1", "0"):
-        monkeypatch.setenv("CHB_HIST", force)
-        for st in (uni, objs, flat, rgba):
-            check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
-            check_outlier(ctx, st, (False, 3.0, 5.0), "average", "forward", weights=(1, 0.5, 0, 1))
-            check_outlier(ctx, st, (False, 1.0, 2.0), "median", "average", weights=(1, -0.5, 1, 0))
+    try:
+        for force in (1, 0):
+            cp.set_tuning("hist", force)
+            for st in (uni, objs, flat, rgba):
+                check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
+                check_outlier(ctx, st, (False, 3.0, 5.0), "average", "forward", weights=(1, 0.5, 0, 1))
+                check_outlier(ctx, st, (False, 1.0, 2.0), "median", "average", weights=(1, -0.5, 1, 0))
+    finally:
+        cp.set_tuning("hist", -1)
 
 
 def test_every_pixel_through_the_tier_queues(ctx):
@@ -483,16 +486,19 @@ def test_video_run_adversarial_series(ctx):
         fs.close()
 
 
-def test_video_run_exact_queue_overflow_falls_back_in_place(ctx, monkeypatch):
+def test_video_run_exact_queue_overflow_falls_back_in_place(ctx):
     # pixel-windows the certificate cannot clear go to a global queue finished by a second kernel; when it is full the
     # warps finish them in place. Threshold 0 makes every pixel-window take that path.
     rng = np.random.default_rng(12)
     st = make_stack(rng, 50, 16, 64, 3, n_obj=30)
     fs = upload(ctx, st)
-    for cap in ("0", "37", "100000"):
-        monkeypatch.setenv("CHB_VIDEO_QUEUE_CAP", cap)
-        _check_video_run(ctx, fs, st, 0, 25, 26, (True, 0.0, 0.2), "first", "extreme")
-        _check_video_run(ctx, fs, st, 3, 9, 30, (True, 0.05, 0.2), "random", "forward")
+    try:
+        for cap in (0, 37, 100000):
+            cp.set_tuning("video_queue_cap", cap)
+            _check_video_run(ctx, fs, st, 0, 25, 26, (True, 0.0, 0.2), "first", "extreme")
+            _check_video_run(ctx, fs, st, 3, 9, 30, (True, 0.05, 0.2), "random", "forward")
+    finally:
+        cp.set_tuning("video_queue_cap", -1)
     fs.close()
 
 
