@@ -235,19 +235,23 @@ def verify_rows(H, want=64):
 
 def verify_photo(orc, np, mode, kind, n, H, W, image, mask):
     """image/mask: the full (H, W, 3) result of the timed stack. Bit-exact comparison of row blocks with the oracle."""
-    bad, rows_done = 0, 0
+    bad, rows_done, where = 0, 0, []
     for r0, r in verify_rows(H):
         st = orc.synth_frames(kind, 42, n, W, H, rows=r, row0=r0)
         res = oracle_call(orc, mode, st, os.cpu_count() or 1)
         if mode.startswith("outlier"):
             oimg, omsk, _ = res
-            bad += int((oimg != image[r0:r0 + r]).any(axis=2).sum())
+            d = (oimg != image[r0:r0 + r]).any(axis=2)
             if mask is not None:
-                bad += int((omsk != mask[r0:r0 + r]).any(axis=2).sum())
+                d |= (omsk != mask[r0:r0 + r]).any(axis=2)
         else:
-            bad += int((res != image[r0:r0 + r]).any(axis=2).sum())
+            d = (res != image[r0:r0 + r]).any(axis=2)
+        bad += int(d.sum())
+        for y, x in np.argwhere(d)[:4]:
+            where.append({"y": int(r0 + y), "x": int(x), "gpu": image[r0 + y, x].tolist() + ([int(mask[r0 + y, x, 0])] if mask is not None else []),
+                          "oracle": (oimg if mode.startswith("outlier") else res)[y, x].tolist() + ([int(omsk[y, x, 0])] if mask is not None else [])})
         rows_done += r
-    return rows_done, bad
+    return rows_done, bad, where
 
 
 class Env:
@@ -472,7 +476,9 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
                 full_img = proc.process(stack)
         if env.rank == 0 and full_img is not None:
             orc = oracle()
-            vrows, bad = verify_photo(orc, np, mode, kind, n, H_img, W, full_img, full_msk)
+            vrows, bad, where = verify_photo(orc, np, mode, kind, n, H_img, W, full_img, full_msk)
+            if where:
+                vinfo["first_differences"] = where
             verified = dict(vinfo, rows=vrows, pixels_differing_from_oracle=bad, configs=[wl],
                             ok=(bad == 0 and vinfo.get("gathered_vs_single_gpu_pixels_differing", 0) == 0),
                             what="composite" + (" + mask" if is_outlier else "") + " of the timed stack, bit for bit against the CPU oracle on the same synthetic frames")
@@ -652,8 +658,7 @@ def run_video(env, wl, steps, warmup, do_e2e, do_cpu, cpu_target_s, do_verify, s
             rng = np.random.default_rng(43)
             offs = rng.integers(-8, 9, size=(n, 2)).astype(np.int32)
             offs[0] = (0, 0); offs[1] = (-8, -8); offs[2] = (8, 8)  # the crop then is exactly 1904x1064 (Crop::create, src/shake.rs:136-176)
-            crop = cp.crop_create([tuple(o) for o in offs], FW, FH)
-            (cw, ch), origins = crop[0], crop[1]
+            origins, cw, ch = cp.crop_create(offs, FW, FH)
             assert (cw, ch) == (W, H), (cw, ch)
             host = torch.empty((n, FH, FW, 3), dtype=torch.uint8, pin_memory=True)
             fbytes, pitch = FH * FW * 3, FW * 3

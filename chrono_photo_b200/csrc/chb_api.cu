@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <condition_variable>
 #include <vector>
 
 using namespace chb;
@@ -90,13 +91,14 @@ struct Band {
     uint8_t* d_stack = nullptr;
     uint8_t* d_out = nullptr;
     uint8_t* d_mask = nullptr;
-    // ingest: two device staging frames + two pinned host staging frames
-    uint8_t* d_stage[2] = {nullptr, nullptr};
-    uint8_t* h_stage[2] = {nullptr, nullptr};
-    cudaEvent_t copied[2] = {nullptr, nullptr};  // H2D into d_stage[s] done
-    cudaEvent_t packed[2] = {nullptr, nullptr};  // pack kernel reading d_stage[s] done
-    bool h_busy[2] = {false, false};
-    int next_slot = 0;
+    // ingest: device staging for two frame groups (2 x 16 frames, allocated at the first upload). A group whose frames have all
+    // arrived is re-laid-out by ONE pack_group_kernel launch that writes whole 16-byte units (no byte scatter); the other
+    // region receives the next group's copies meanwhile.
+    uint8_t* d_stage = nullptr;  // [2 * 16][frame_bytes]
+    struct Region { int group = -1; uint32_t arrived = 0; } region[2];
+    cudaEvent_t copied = nullptr;               // recorded on d.copy after a group's last H2D (stream order covers the earlier ones)
+    cudaEvent_t packed[2] = {nullptr, nullptr};  // the pack launch that last read region r finished
+    uint8_t* d_tmp = nullptr;                    // one frame: chb_stack_download
     // per-call scratch
     uint32_t* d_wmask = nullptr;
     uint32_t* d_smask = nullptr;
@@ -129,6 +131,15 @@ struct chb_stack {
     std::vector<Band> bands;
     std::vector<uint8_t> uploaded;  // per frame
     std::mutex upload_mu, call_mu;
+    // pageable sources: a pool of pinned host frames; a caller thread owns one slot while it copies its frame into it (no lock
+    // held during the memcpy), so several decode threads stage in parallel
+    static constexpr int kHostSlots = 8;
+    uint8_t* h_slot[kHostSlots] = {};
+    bool h_in_use[kHostSlots] = {};
+    std::vector<cudaEvent_t> h_done[kHostSlots];  // per band: the H2D out of the slot finished
+    bool h_pending[kHostSlots] = {};
+    std::mutex slot_mu;
+    std::condition_variable slot_cv;
     // pinned host scratch for per-call tables
     uint32_t* h_wmask = nullptr;
     uint32_t* h_smask = nullptr;
@@ -204,12 +215,10 @@ extern "C" int chb_ctx_set_stream(chb_ctx* ctx, int dev_slot, void* cuda_stream)
 // ------------------------------------------------------------------------------------------------ stack
 static void free_band(Band& b) {
     cudaFree(b.d_stack); cudaFree(b.d_out); cudaFree(b.d_mask);
-    for (int s = 0; s < 2; s++) {
-        cudaFree(b.d_stage[s]);
-        if (b.h_stage[s]) cudaFreeHost(b.h_stage[s]);
-        if (b.copied[s]) cudaEventDestroy(b.copied[s]);
+    cudaFree(b.d_stage); cudaFree(b.d_tmp);
+    if (b.copied) cudaEventDestroy(b.copied);
+    for (int s = 0; s < 2; s++)
         if (b.packed[s]) cudaEventDestroy(b.packed[s]);
-    }
     cudaFree(b.d_wmask); cudaFree(b.d_smask); cudaFree(b.d_win); cudaFree(b.d_posg); cudaFree(b.d_fade); cudaFree(b.d_counters);
     cudaFree(b.d_dbg_median); cudaFree(b.d_dbg_q1); cudaFree(b.d_dbg_q3); cudaFree(b.d_dbg_nout);
     if (b.ev0) cudaEventDestroy(b.ev0);
@@ -229,6 +238,10 @@ extern "C" int chb_stack_destroy(chb_stack* st) {
         cudaSetDevice(st->ctx->devs[b.dev_slot].id);
         cudaDeviceSynchronize();
         free_band(b);
+    }
+    for (int k = 0; k < chb_stack::kHostSlots; k++) {
+        if (st->h_slot[k]) cudaFreeHost(st->h_slot[k]);
+        for (cudaEvent_t e : st->h_done[k]) cudaEventDestroy(e);
     }
     if (st->h_wmask) cudaFreeHost(st->h_wmask);
     if (st->h_smask) cudaFreeHost(st->h_smask);
@@ -278,11 +291,8 @@ extern "C" int chb_stack_create(chb_ctx* ctx, int width, int height, int channel
         CUB(cudaMemset(b.d_stack, 0, b.stack_bytes));  // frames beyond n_frames in the last group must read as zero
         CUB(cudaMalloc(&b.d_out, b.frame_bytes));
         CUB(cudaMalloc(&b.d_mask, b.frame_bytes));
-        for (int s = 0; s < 2; s++) {
-            CUB(cudaMalloc(&b.d_stage[s], b.frame_bytes));
-            CUB(cudaEventCreateWithFlags(&b.copied[s], cudaEventDisableTiming));
-            CUB(cudaEventCreateWithFlags(&b.packed[s], cudaEventDisableTiming));
-        }
+        CUB(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
+        for (int s = 0; s < 2; s++) CUB(cudaEventCreateWithFlags(&b.packed[s], cudaEventDisableTiming));
         CUB(cudaMalloc(&b.d_wmask, sizeof(uint32_t) * kMaxGroupsTable * 4));
         CUB(cudaMalloc(&b.d_smask, sizeof(uint32_t) * kMaxGroupsTable * 4));
         CUB(cudaMalloc(&b.d_win, sizeof(int32_t) * (size_t)n_frames));
@@ -309,9 +319,57 @@ static int grid_for(long long work_items, int threads, int sm_count, int waves) 
     return (int)std::max<long long>(1, std::min(blocks, cap));
 }
 
+// ---- ingest (replaces TimeSlicer::write_time_slices, src/slicer.rs:106-231, and the chunk streams, src/streams.rs:93-202) ----
+constexpr int kStageFrames = 2 * kGroupFrames;
+
+// Re-layout of whatever has arrived in region r. complete: every frame of the group is there -> one launch writing whole units
+// (frames beyond n_frames in the last group are written as zeros); otherwise the present frames are scattered one by one
+// (read-modify-write of their byte inside each unit: slow, but only taken by out-of-order or partial uploads).
+static int pack_region(chb_stack* st, Band& b, Dev& d, int r) {
+    Band::Region& R = b.region[r];
+    if (R.group < 0 || R.arrived == 0) { R.group = -1; R.arrived = 0; return CHB_OK; }
+    const int g = R.group;
+    const int in_group = std::min(kGroupFrames, st->N - g * kGroupFrames);
+    const uint32_t full = in_group >= 32 ? 0xffffffffu : ((1u << in_group) - 1u);
+    CU(cudaEventRecord(b.copied, d.copy));
+    CU(cudaStreamWaitEvent(d.pack, b.copied, 0));
+    if (R.arrived == full) {
+        PackGroupArgs pa;
+        for (int k = 0; k < kGroupFrames; k++) pa.src[k] = k < in_group ? b.d_stage + (size_t)(r * kGroupFrames + k) * b.frame_bytes : nullptr;
+        pack_group_kernel<<<grid_for(b.n_pixels, 256, d.sm_count, 8), 256, 0, d.pack>>>(pa, b.d_stack, b.n_pixels, st->C, st->NG, g);
+        g_launches++;
+    } else {
+        for (int k = 0; k < kGroupFrames; k++) {
+            if (!((R.arrived >> k) & 1u)) continue;
+            pack_frame_kernel<<<grid_for(b.n_pixels, 256, d.sm_count, 8), 256, 0, d.pack>>>(b.d_stage + (size_t)(r * kGroupFrames + k) * b.frame_bytes, b.d_stack,
+                                                                                          b.n_pixels, st->C, st->NG, g * kGroupFrames + k);
+            g_launches++;
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(b.packed[r], d.pack));
+    R.group = -1;
+    R.arrived = 0;
+    return CHB_OK;
+}
+
+// Enqueues the re-layout of every frame that has been uploaded but not packed yet (incomplete groups). The caller holds upload_mu.
+static int flush_ingest_locked(chb_stack* st) {
+    for (Band& b : st->bands) {
+        Dev& d = st->ctx->devs[b.dev_slot];
+        if (b.region[0].arrived == 0 && b.region[1].arrived == 0) continue;
+        CU(cudaSetDevice(d.id));
+        for (int r = 0; r < 2; r++) {
+            int rc = pack_region(st, b, d, r);
+            if (rc) return rc;
+        }
+    }
+    return CHB_OK;
+}
+
 // Orders a compute stream after every ingest step enqueued so far on this band (H2D copies on d.copy, re-layout on d.pack), so a
 // compositing launch issued right after a run of uploads never reads a partly packed stack -- with or without chb_stack_sync.
-// (Waiting on an event that was never recorded is a no-op.)
+// (Waiting on an event that was never recorded is a no-op.) Call flush_ingest first.
 static cudaError_t wait_ingest(Band& b, cudaStream_t s) {
     for (int k = 0; k < 2; k++) {
         if (!b.packed[k]) continue;
@@ -320,44 +378,108 @@ static cudaError_t wait_ingest(Band& b, cudaStream_t s) {
     }
     return cudaSuccess;
 }
+static int flush_ingest(chb_stack* st) {
+    std::lock_guard<std::mutex> lk(st->upload_mu);
+    return flush_ingest_locked(st);
+}
 
-// Ingest of one frame into every band. `pinned`: the source can be DMA'd directly.
+// A pinned host frame for a pageable source: blocks until a slot of the pool is free and its previous DMA has left.
+static int acquire_host_slot(chb_stack* st, int& slot) {
+    {
+        std::unique_lock<std::mutex> lk(st->slot_mu);
+        st->slot_cv.wait(lk, [&] { for (bool u : st->h_in_use) if (!u) return true; return false; });
+        slot = 0;
+        while (st->h_in_use[slot]) slot++;
+        st->h_in_use[slot] = true;
+    }
+    auto release = [&](int code) {
+        std::lock_guard<std::mutex> lk(st->slot_mu);
+        st->h_in_use[slot] = false;
+        st->slot_cv.notify_one();
+        return code;
+    };
+    const size_t bytes = (size_t)st->W * st->H * st->C;
+    if (!st->h_slot[slot]) {
+        cudaError_t e = cudaMallocHost(&st->h_slot[slot], bytes);
+        if (e != cudaSuccess) return release(fail(CHB_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)));
+        st->h_done[slot].resize(st->bands.size(), nullptr);
+        for (size_t k = 0; k < st->bands.size(); k++) {
+            cudaSetDevice(st->ctx->devs[st->bands[k].dev_slot].id);
+            e = cudaEventCreateWithFlags(&st->h_done[slot][k], cudaEventDisableTiming);
+            if (e != cudaSuccess) return release(fail(CHB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)));
+        }
+    }
+    if (st->h_pending[slot]) {
+        for (cudaEvent_t ev : st->h_done[slot]) {
+            cudaError_t e = cudaEventSynchronize(ev);
+            if (e != cudaSuccess) return release(fail(CHB_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e)));
+        }
+        st->h_pending[slot] = false;
+    }
+    return CHB_OK;
+}
+static void release_host_slot(chb_stack* st, int slot) {
+    std::lock_guard<std::mutex> lk(st->slot_mu);
+    st->h_in_use[slot] = false;
+    st->slot_cv.notify_one();
+}
+
+// Ingest of one frame into every band. `pinned`: the source can be DMA'd directly; otherwise it is first copied into a pinned
+// slot of the pool by the calling thread (in parallel with other callers).
 static int upload_impl(chb_stack* st, int frame_idx, const uint8_t* host, size_t pitch, int crop_x, int crop_y, bool pinned) {
     if (!st || !host) return fail(CHB_ERR_INVALID, "chb_stack_upload: null argument");
     if (frame_idx < 0 || frame_idx >= st->N) return fail(CHB_ERR_INVALID, "chb_stack_upload: frame %d outside [0, %d)", frame_idx, st->N);
     if (crop_x < 0 || crop_y < 0) return fail(CHB_ERR_INVALID, "chb_stack_upload: negative crop origin");
     const size_t row_bytes = (size_t)st->W * st->C;
     if (pitch < row_bytes + (size_t)crop_x * st->C) return fail(CHB_ERR_INVALID, "chb_stack_upload: row pitch %zu too small", pitch);
-    std::lock_guard<std::mutex> lk(st->upload_mu);
-    for (Band& b : st->bands) {
-        Dev& d = st->ctx->devs[b.dev_slot];
-        CU(cudaSetDevice(d.id));
-        const int s = b.next_slot;
-        b.next_slot ^= 1;
-        const uint8_t* src = host + (size_t)(crop_y + b.row0) * pitch + (size_t)crop_x * st->C;
-        // the pack kernel that last read d_stage[s] must be done before the copy overwrites it
-        CU(cudaStreamWaitEvent(d.copy, b.packed[s], 0));
-        if (pinned) {
-            if (pitch == row_bytes) CU(cudaMemcpyAsync(b.d_stage[s], src, b.frame_bytes, cudaMemcpyHostToDevice, d.copy));
-            else CU(cudaMemcpy2DAsync(b.d_stage[s], row_bytes, src, pitch, row_bytes, (size_t)b.rows, cudaMemcpyHostToDevice, d.copy));
-        } else {
-            if (!b.h_stage[s]) CU(cudaMallocHost(&b.h_stage[s], b.frame_bytes));
-            if (b.h_busy[s]) CU(cudaEventSynchronize(b.copied[s]));  // previous DMA out of this pinned slot
-            if (pitch == row_bytes) memcpy(b.h_stage[s], src, b.frame_bytes);
-            else
-                for (int r = 0; r < b.rows; r++) memcpy(b.h_stage[s] + (size_t)r * row_bytes, src + (size_t)r * pitch, row_bytes);
-            CU(cudaMemcpyAsync(b.d_stage[s], b.h_stage[s], b.frame_bytes, cudaMemcpyHostToDevice, d.copy));
-            b.h_busy[s] = true;
-        }
-        CU(cudaEventRecord(b.copied[s], d.copy));
-        CU(cudaStreamWaitEvent(d.pack, b.copied[s], 0));
-        pack_frame_kernel<<<grid_for(b.n_pixels, 256, d.sm_count, 8), 256, 0, d.pack>>>(b.d_stage[s], b.d_stack, b.n_pixels, st->C, st->NG, frame_idx);
-        g_launches++;
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(b.packed[s], d.pack));
+    const uint8_t* src0 = host + (size_t)crop_y * pitch + (size_t)crop_x * st->C;  // pixel (0, 0) of the cropped frame
+    int hs = -1;
+    if (!pinned) {
+        int rc = acquire_host_slot(st, hs);
+        if (rc) return rc;
+        uint8_t* dst = st->h_slot[hs];
+        if (pitch == row_bytes) memcpy(dst, src0, row_bytes * (size_t)st->H);
+        else
+            for (int r = 0; r < st->H; r++) memcpy(dst + (size_t)r * row_bytes, src0 + (size_t)r * pitch, row_bytes);
+        src0 = dst;
+        pitch = row_bytes;
     }
-    st->uploaded[frame_idx] = 1;
-    return CHB_OK;
+    int rc = CHB_OK;
+    {
+        std::lock_guard<std::mutex> lk(st->upload_mu);
+        const int g = frame_idx / kGroupFrames, k = frame_idx % kGroupFrames, r = g & 1;
+        for (size_t bi = 0; bi < st->bands.size() && rc == CHB_OK; bi++) {
+            Band& b = st->bands[bi];
+            Dev& d = st->ctx->devs[b.dev_slot];
+            auto cu = [&](cudaError_t e, const char* what) {
+                if (e != cudaSuccess && rc == CHB_OK) rc = fail(CHB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+                return e == cudaSuccess;
+            };
+            if (!cu(cudaSetDevice(d.id), "cudaSetDevice")) break;
+            if (!b.d_stage && !cu(cudaMalloc(&b.d_stage, (size_t)kStageFrames * b.frame_bytes), "cudaMalloc(ingest staging)")) break;
+            Band::Region& R = b.region[r];
+            if ((R.group >= 0 && R.group != g) || ((R.arrived >> k) & 1u)) {  // the region holds another group, or this frame again
+                rc = pack_region(st, b, d, r);
+                if (rc) break;
+            }
+            R.group = g;
+            // the pack launch that last read this region must be done before a copy overwrites it
+            if (!cu(cudaStreamWaitEvent(d.copy, b.packed[r], 0), "cudaStreamWaitEvent")) break;
+            uint8_t* dst = b.d_stage + (size_t)(r * kGroupFrames + k) * b.frame_bytes;
+            const uint8_t* src = src0 + (size_t)b.row0 * pitch;
+            if (pitch == row_bytes) cu(cudaMemcpyAsync(dst, src, b.frame_bytes, cudaMemcpyHostToDevice, d.copy), "cudaMemcpyAsync");
+            else cu(cudaMemcpy2DAsync(dst, row_bytes, src, pitch, row_bytes, (size_t)b.rows, cudaMemcpyHostToDevice, d.copy), "cudaMemcpy2DAsync");
+            if (rc) break;
+            if (hs >= 0) cu(cudaEventRecord(st->h_done[hs][bi], d.copy), "cudaEventRecord");
+            R.arrived |= 1u << k;
+            const int in_group = std::min(kGroupFrames, st->N - g * kGroupFrames);
+            if (R.arrived == ((1u << in_group) - 1u)) rc = pack_region(st, b, d, r);
+        }
+        if (hs >= 0) st->h_pending[hs] = true;
+        if (rc == CHB_OK) st->uploaded[frame_idx] = 1;
+    }
+    if (hs >= 0) release_host_slot(st, hs);
+    return rc;
 }
 
 extern "C" int chb_stack_upload(chb_stack* st, int frame_idx, const uint8_t* host_pixels, size_t row_pitch, int crop_x, int crop_y) {
@@ -373,15 +495,18 @@ extern "C" int chb_stack_download(chb_stack* st, int frame_idx, uint8_t* host_pi
     const size_t row_bytes = (size_t)st->W * st->C;
     if (row_pitch < row_bytes) return fail(CHB_ERR_INVALID, "chb_stack_download: row pitch %zu too small", row_pitch);
     std::lock_guard<std::mutex> lk(st->upload_mu);
+    int rc = flush_ingest_locked(st);
+    if (rc) return rc;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
         CU(cudaStreamSynchronize(d.copy));
         CU(cudaStreamSynchronize(d.pack));
-        unpack_frame_kernel<<<grid_for(b.n_pixels, 256, d.sm_count, 8), 256, 0, d.pack>>>(b.d_stack, b.d_stage[0], b.n_pixels, st->C, st->NG, frame_idx);
+        if (!b.d_tmp) CU(cudaMalloc(&b.d_tmp, b.frame_bytes));
+        unpack_frame_kernel<<<grid_for(b.n_pixels, 256, d.sm_count, 8), 256, 0, d.pack>>>(b.d_stack, b.d_tmp, b.n_pixels, st->C, st->NG, frame_idx);
         g_launches++;
         CU(cudaGetLastError());
-        CU(cudaMemcpy2DAsync(host_pixels + (size_t)b.row0 * row_pitch, row_pitch, b.d_stage[0], row_bytes, row_bytes, (size_t)b.rows,
+        CU(cudaMemcpy2DAsync(host_pixels + (size_t)b.row0 * row_pitch, row_pitch, b.d_tmp, row_bytes, row_bytes, (size_t)b.rows,
                              cudaMemcpyDeviceToHost, d.pack));
         CU(cudaStreamSynchronize(d.pack));
     }
@@ -391,6 +516,8 @@ extern "C" int chb_stack_download(chb_stack* st, int frame_idx, uint8_t* host_pi
 extern "C" int chb_stack_sync(chb_stack* st) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_stack_sync: null stack");
     std::lock_guard<std::mutex> lk(st->upload_mu);
+    int rc = flush_ingest_locked(st);
+    if (rc) return rc;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
@@ -566,6 +693,8 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     // the caller holds st->call_mu: launch and fetch form one critical section per stack
     Window win;
     int rc = build_window(st, indices, n_indices, win, "chb_outlier");
+    if (rc) return rc;
+    rc = flush_ingest(st);  // frames uploaded but not yet re-laid-out (incomplete groups)
     if (rc) return rc;
     const int n = (int)win.frames.size();
     // --sample (src/chrono.rs:151-163)
@@ -913,6 +1042,10 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
         return fail(CHB_ERR_INVALID, "chb_outlier_video: relative thresholds need at least 3 samples (quantile() underflows, src/chrono.rs:569-570)");
     for (int f = first_start; f < first_start + n_windows - 1 + n; f++)
         if (!st->uploaded[f]) return fail(CHB_ERR_STATE, "chb_outlier_video: frame %d was never uploaded", f);
+    {
+        int frc = flush_ingest(st);
+        if (frc) return frc;
+    }
 
     VideoArgs va;
     memset(&va, 0, sizeof va);
@@ -1097,6 +1230,8 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
     // SimpleProcessor accepts any index order in principle (src/simple.rs:142-146), but every caller passes ascending
     // windows (src/main.rs:398-404); the time-sliced stack relies on it.
     int rc = build_window(st, indices, n_indices, win, "chb_simple");
+    if (rc) return rc;
+    rc = flush_ingest(st);
     if (rc) return rc;
     const int n = (int)win.frames.size();
     SimpleArgs a;

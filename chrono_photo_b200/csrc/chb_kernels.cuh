@@ -654,20 +654,39 @@ struct MaskSlots {
 };
 struct IntMedians {  // frame-major constants of the integer distance: byte c = floor / ceil of band c's median (0: weight 0)
     uint32_t lof, hif;
+    // one-sided form used by the dense pass. With lo = floor(median), hi = lo + d (d = 0 or 1), L = |x - lo|:
+    //   |x - lo| + |x - hi| = 2 L + s d with s = +1 for x <= lo, -1 for x >= hi, and L s = lo - x on both sides, hence
+    //   4 dist_sq = sum_c (2 L + s d)^2 = 4 [ sum L^2 + sum d lo - sum d x ] + sum d
+    // -- one VABSDIFF4 and two IDP.4A per frame instead of two and three. negd: byte c = -d_c (signed operand of the
+    // second IDP.4A); k2 = sum d; t = ceil((thr4 - k2) / 4), so that 4 dist_sq >= thr4 <=> q >= t for the bracket q;
+    // c0 = sum d lo - t rides in the first accumulator: the pass works on q - t (negative <=> not an outlier).
+    uint32_t negd;
+    int c0, t, k2;
 };
 template <int C>
 __device__ __forceinline__ IntMedians make_int_medians(const OutlierArgs& a, const float (&median)[4]) {
-    IntMedians m{0u, 0u};
+    IntMedians m{0u, 0u, 0u, 0, 0, 0};
+    int k1 = 0;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         if (a.w[c] != 0.0f) {
             const int lo = (int)median[c];  // medians are >= 0: truncation is floor
-            const int hi = lo + (median[c] != (float)lo ? 1 : 0);
+            const int d = median[c] != (float)lo ? 1 : 0;
             m.lof |= (uint32_t)lo << (8 * c);
-            m.hif |= (uint32_t)hi << (8 * c);
+            m.hif |= (uint32_t)(lo + d) << (8 * c);
+            m.negd |= d ? (0xffu << (8 * c)) : 0u;
+            k1 += d * lo;
+            m.k2 += d;
         }
     }
+    m.t = (a.thr4 - m.k2 + 3) >> 2;  // ceil((thr4 - k2) / 4), also for negative numerators
+    m.c0 = k1 - m.t;
     return m;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b_signed, int c) {  // sum of a.u8[i] * b.s8[i] + c
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_signed), "r"(c));
+    return d;
 }
 // 4 * dist_sq of one frame given as a frame-major word (byte c = band c; bands of weight 0 must be zero in x)
 __device__ __forceinline__ uint32_t int_dist_frame(const IntMedians& m, uint32_t x) {
@@ -678,9 +697,8 @@ __device__ __forceinline__ uint32_t int_dist_frame(const IntMedians& m, uint32_t
 template <int C>
 __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint8_t* colbase, long long band_stride, int f0, int n,
                                                 const IntMedians& im, const MaskSlots& ms, int& k_out, uint32_t& maxkey_out) {
-    const int thr4 = a.thr4;
-    const uint32_t negthr = (uint32_t)(-thr4);
-    const uint32_t lof = im.lof, hif = im.hif;
+    const uint32_t lof = im.lof, negd = im.negd;
+    const int c0 = im.c0;
     bool use[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) use[c] = (c < C) && (a.w[c] != 0.0f);
@@ -696,7 +714,7 @@ __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint
         const int sg = 16 * g - f0;  // window position of the group's frame 0
         const bool full = (sg >= 0) && (sg + 16 <= n);
         uint32_t om16 = 0;
-        int gkey = INT_MIN;  // max over the group's frames of 16 * (4 dist_sq - thr4) + (15 - j)
+        int gkey = INT_MIN;  // max over the group's frames of 16 * (q - t) + (15 - j)
         auto body = [&](auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
@@ -710,10 +728,9 @@ __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) {
                     const int j = 4 * q + kk;
-                    const uint32_t L = absdiff4(pf[kk], lof), H = absdiff4(pf[kk], hif);
-                    const uint32_t lh = __dp4a(L, H, 0u);
-                    // dm = 4 dist_sq - thr4 (the subtraction rides in the first accumulator): negative <=> not an outlier
-                    const int dm = (int)(__dp4a(H, H, __dp4a(L, L, negthr)) + lh + lh);
+                    const uint32_t L = absdiff4(pf[kk], lof);
+                    // dm = q - t with 4 dist_sq = 4 q + k2 (see IntMedians): negative <=> not an outlier
+                    const int dm = dp4a_us(pf[kk], negd, (int)__dp4a(L, L, (uint32_t)c0));
                     if (FULL) {
                         om16 = __funnelshift_l((uint32_t)dm, om16, 1);  // collects the NON-outlier bits, frame j at bit 15 - j
                         gkey = max(gkey, dm * 16 + (15 - j));
@@ -730,7 +747,7 @@ __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint
         ms.put(g - gA, om16);
         k += __popc(om16);
         const int s = sg + 15 - (gkey & 15);
-        maxkey = max(maxkey, ((uint32_t)((gkey >> 4) + thr4) << 12) | (uint32_t)(4095 - s));
+        maxkey = max(maxkey, ((uint32_t)(4 * ((gkey >> 4) + im.t) + im.k2) << 12) | (uint32_t)(4095 - s));
     };
     // one copy of the group body in the instruction stream (the streaming kernel's warps interleave this loop with the band
     // code: the footprint decides whether both stay in the instruction cache): the next group's loads are issued into a
@@ -1373,7 +1390,7 @@ struct PixelAcc {
 // (absolute thresholds only); otherwise run the iterative solver.
 template <int C, int WPL, int G, int MODE, bool FAST>
 __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)[4 * WPL], int c, int j, long long pix, bool write_dbg,
-                                             int cap, int pad, PixelAcc& acc) {
+                                             int cap, int pad, PixelAcc& acc, bool skip_cert = false) {
     constexpr int W4 = 4 * WPL;
     constexpr bool GENERIC = (MODE == 0);  // MODE 1 / 2: lean whole-stack kernels for absolute / relative thresholds
     const float w = a.w[c];
@@ -1455,7 +1472,9 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         if (a.dbg_q1) a.dbg_q1[pix * 4 + c] = q1;
         if (a.dbg_q3) a.dbg_q3[pix * 4 + c] = q3;
     }
-    if (!(w < 0.0f)) {  // negative weights only lower dist_sq; NaN poisons the bound (-> exact path)
+    if (skip_cert) {  // (warp-uniform) the tile is going to be classified frame by frame whatever this band's term is
+        acc.bound = __int_as_float(0x7f800000);
+    } else if (!(w < 0.0f)) {  // negative weights only lower dist_sq; NaN poisons the bound (-> exact path)
         // certificate term: an upper bound of |x - median| over the window's frames. Bytes that are not window frames
         // (zero in the registers) are replaced by the centre value, so they contribute 0.
         const uint32_t cc = rep4(center);
@@ -1641,6 +1660,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
         const uint8_t* src = a.stack + (long long)tile * tile_bytes(C, a.NG) + ((long long)c * a.NG + a.g0) * (kTilePixels * kUnitBytes) + (task % G) * kRowBytes;
         if (G == 1) {
             if (lane == 0) {
+                // the warp's ld.shared reads of the slab (generic proxy, ordered before this point by __syncwarp) must be ordered
+                // before the bulk copy's writes (async proxy): without the proxy fence the copy may overwrite bytes a delayed
+                // read has not fetched yet -- seen as medians off by one in ~2 of 750 000 tiles when the load / store unit is busy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(bar, (uint32_t)staged_groups * 512u);
                 bulk_g2s(stage, src, (uint32_t)staged_groups * 512u, bar);
             }
@@ -1707,7 +1730,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
                 const int nt = last ? task + n_warps : task;
                 if (nt < n_tasks) prefetch_band(nt, last ? 0 : c + 1);
             }
-            process_band<C, WPL, G, MODE, true>(a, A, c, j, pix, owner, cap, pad, acc);
+            // once enough pixels of the tile have lost their certificate the tile is finished by the dense per-frame pass below,
+            // which is exact for every pixel: the remaining bands' certificate terms are not computed
+            bool skip_cert = false;
+            if (G == 1 && MODE != 2 && c > 0 && a.inline_min > 0)
+                skip_cert = __popc(__ballot_sync(0xffffffffu, owner && !acc.hard && !(acc.bound * 1.0001f < a.thr_sq))) >= a.inline_min;
+            process_band<C, WPL, G, MODE, true>(a, A, c, j, pix, owner, cap, pad, acc, skip_cert);
         }
         // ---- hard pixels wait in the warp's queue until a warp-full can run the iterative solver together
         // iterative tier: an order statistic outside its window, or a pixel the IQR bound could not clear

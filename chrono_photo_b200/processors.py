@@ -17,6 +17,15 @@ from . import _lib
 from .options import BackgroundMode, Fade, OutlierSelectionMode, Threshold
 
 
+def _check_out(arr, shape, name):
+    """User-supplied result buffers go straight to the C library: a wrong dtype, shape or stride would make it write out of bounds."""
+    if not isinstance(arr, np.ndarray) or arr.dtype != np.uint8 or tuple(arr.shape) != tuple(shape) or not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError(f"{name} must be a C-contiguous uint8 array of shape {tuple(shape)}")
+    if not arr.flags["WRITEABLE"]:
+        raise ValueError(f"{name} must be writeable")
+    return arr
+
+
 def _u8(a):
     a = np.ascontiguousarray(a, dtype=np.uint8)
     return a
@@ -84,6 +93,8 @@ class FrameStack:
         """Frame frame_idx as a (height, width, channels) uint8 array (inverse of upload)."""
         if out is None:
             out = np.empty((self.height, self.width, self.channels), dtype=np.uint8)
+        else:
+            _check_out(out, (self.height, self.width, self.channels), "out")
         _lib.check(_lib.lib().chb_stack_download(self._h, int(frame_idx), C.c_void_p(out.ctypes.data), out.strides[0]))
         return out
 
@@ -170,8 +181,8 @@ class OutlierProcessor:
         debug=True additionally returns a dict of per-pixel sub-results (median, q1, q3, n_outliers).
         out / mask_out: optional preallocated (e.g. pinned) C-contiguous uint8 arrays to receive the results."""
         shape = (stack.height, stack.width, stack.channels)
-        out = np.empty(shape, dtype=np.uint8) if out is None else out
-        mask = (np.empty(shape, dtype=np.uint8) if mask_out is None else mask_out) if want_mask else None
+        out = np.empty(shape, dtype=np.uint8) if out is None else _check_out(out, shape, "out")
+        mask = (np.empty(shape, dtype=np.uint8) if mask_out is None else _check_out(mask_out, shape, "mask_out")) if want_mask else None
         ip, n, _keep = _indices(image_indices)
         warn = C.c_uint64(0)
         p = self._params()
@@ -210,13 +221,13 @@ class OutlierProcessor:
     # ---- chrono-video: runs of sliding windows (src/main.rs:254-331) ------------------------------------------------
     MAX_VIDEO_WINDOW = 64
 
-    def process_video_run(self, stack, first_start, window_len, n_windows, want_mask=True):
+    def process_video_run(self, stack, first_start, window_len, n_windows, want_mask=True, out=None, mask_out=None):
         """n_windows windows of window_len consecutive frames, window i = frames [first_start + i, ... + window_len):
         one sliding-window launch sequence (chb_outlier_video). Returns (images, masks, warnings) with images / masks of
-        shape (n_windows, H, W, C)."""
+        shape (n_windows, H, W, C). out / mask_out: optional preallocated (e.g. pinned) arrays of that shape."""
         shape = (n_windows, stack.height, stack.width, stack.channels)
-        out = np.empty(shape, dtype=np.uint8)
-        mask = np.empty(shape, dtype=np.uint8) if want_mask else None
+        out = np.empty(shape, dtype=np.uint8) if out is None else _check_out(out, shape, "out")
+        mask = (np.empty(shape, dtype=np.uint8) if mask_out is None else _check_out(mask_out, shape, "mask_out")) if want_mask else None
         warn = (C.c_uint64 * n_windows)()
         p = self._params()
         _lib.check(_lib.lib().chb_outlier_video(stack._h, C.byref(p), int(first_start), int(window_len), int(n_windows), C.c_void_p(out.ctypes.data),

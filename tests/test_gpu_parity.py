@@ -398,6 +398,33 @@ def test_long_series_histogram_tier(ctx):
         cp.set_tuning("hist", -1)
 
 
+@pytest.mark.parametrize("kind", [4, 3, 2])
+def test_repeated_calls_at_scale_are_bit_identical_and_match_the_oracle(ctx, kind):
+    # Round 2 found a cross-proxy write-after-read race (TMA bulk copy overwriting a slab whose ld.shared reads were still in
+    # flight: medians off by one in ~2 of 750 000 tiles per call) that no small case ever hit. Medians of EVERY pixel matter
+    # for the noisy series (kind 4: an outlier frame in every pixel), so: a few GB of stack, repeated calls compared bit for
+    # bit with the first one, rows of it compared with the oracle, with and without the in-kernel dense pass.
+    n, h, w = 200, 1024, 6016
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    fs.fill_synthetic(kind, 42)
+    proc = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), cp.BackgroundMode.FIRST, cp.OutlierSelectionMode.EXTREME)
+    try:
+        for inline_min in (12, 0):
+            cp.set_tuning("inline_min", inline_min)
+            img0, msk0 = proc.process(fs)
+            for _ in range(6):
+                proc.enqueue_device(fs)
+                img, msk = proc.process(fs)
+                assert np.array_equal(img, img0) and np.array_equal(msk, msk0), f"kind {kind} inline_min {inline_min}: two calls differ"
+            for r0 in (0, 500, h - 8):
+                st = orc.synth_frames(kind, 42, n, w, h, rows=8, row0=r0)
+                oimg, omsk, _ = orc.outlier(st, orc.threshold(True, 0.05, 0.2), 0, 2, n_threads=8)
+                assert np.array_equal(img0[r0:r0 + 8], oimg) and np.array_equal(msk0[r0:r0 + 8], omsk), f"kind {kind} rows {r0}"
+    finally:
+        cp.set_tuning("inline_min", 12)
+    fs.close()
+
+
 def test_every_pixel_through_the_tier_queues(ctx):
     # pixels for the iterative tier and for the exact path travel through per-launch global queues (one slot per pixel) drained
     # by the follow-up kernels; iid bytes send EVERY pixel through both queues

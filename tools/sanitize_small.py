@@ -22,4 +22,12 @@ for n, c in ((25, 3), (200, 3), (70, 4), (300, 3)):
     cp.SimpleProcessor(darker=True).process(fs)
     cp.SimpleProcessor((1, 0.5, 0.25, 0), cp.Fade(0, False, [(0, 1.0), (9, 0.0)]), False).process(fs, list(range(0, n, 3)))
     fs.close()
+# noise at the threshold / iid bytes: tiles classified frame by frame inside the streaming kernel and in the iterative tier (dense pass)
+for kind in (4, 3):
+    fs = cp.FrameStack(ctx, 256, 8, 3, 200)
+    fs.fill_synthetic(kind, 42)
+    for bg, om in ((0, 2), (1, 4), (2, 3), (3, 5), (0, 0), (0, 1)):
+        cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), bg, om, seed=3).process(fs)
+    cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2).process(fs, list(range(5, 190)))
+    fs.close()
 print("sanitize run done")
