@@ -548,6 +548,29 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
                        "NCCL gather of the bands onto rank 0 -> D2H of the whole image" if gather else "D2H of composite" + (" + mask" if is_outlier else ""))}
             if gather:
                 e2e["gather_ms"] = env.max_over_ranks(sum(gather_ms) / max(1, len(gather_ms)))
+            # the same step from PAGEABLE frames uploaded by 8 host threads (what decode threads hand over: chb_stack_upload stages
+            # every frame through a pool of pinned slots, the memcpy into the slot runs in the calling thread)
+            if primary and not env.multi_proc and psutil.virtual_memory().available > 1.5 * n * fb:
+                from concurrent.futures import ThreadPoolExecutor
+                pageable = host.numpy().copy()
+                pbase = pageable.ctypes.data
+                n_thr = 8
+
+                def pageable_step():
+                    with ThreadPoolExecutor(n_thr) as ex:
+                        list(ex.map(lambda f: stack2.upload_raw(f, pbase + f * fb, pitch, pinned=False), range(n)))
+                    if is_outlier:
+                        proc.process(stack2, out=out_np, mask_out=msk_np)
+                    else:
+                        _lib.check(_lib.lib().chb_simple(stack2._h, proc._params(), None, 0, out_np.ctypes.data))
+
+                pageable_step()
+                t0 = time.perf_counter()
+                pageable_step()
+                dt = time.perf_counter() - t0
+                e2e["pageable"] = {"value": e_pf / dt, "unit": "pixel-frames/s", "ms_per_step": dt * 1e3, "uploader_threads": n_thr,
+                                   "h2d_gbs": n * fb / dt / 1e9, "path": "pageable host frames -> chb_stack_upload from 8 threads -> kernels -> D2H"}
+                del pageable
             if e_note:
                 e2e["note"] = e_note
             stack2.close()
@@ -663,7 +686,7 @@ def run_video(env, wl, steps, warmup, do_e2e, do_cpu, cpu_target_s, do_verify, s
             host = torch.empty((n, FH, FW, 3), dtype=torch.uint8, pin_memory=True)
             fbytes, pitch = FH * FW * 3, FW * 3
             for f in range(n):  # the resident synthetic clip written back into shaky full-size host frames
-                ox, oy = origins[f]
+                ox, oy = int(origins[f][0]), int(origins[f][1])
                 stack.download_raw(f, host.data_ptr() + f * fbytes + oy * pitch + ox * 3, pitch)
             stack2 = cp.FrameStack(ctx, W, H, 3, n)
             chunk = 128
@@ -672,8 +695,7 @@ def run_video(env, wl, steps, warmup, do_e2e, do_cpu, cpu_target_s, do_verify, s
 
             def e2e_step():
                 for f in range(n):
-                    ox, oy = origins[f]
-                    stack2.upload_raw(f, host.data_ptr() + f * fbytes, pitch, crop_xy=(int(ox), int(oy)), pinned=True)
+                    stack2.upload_raw(f, host.data_ptr() + f * fbytes, pitch, crop_xy=(int(origins[f][0]), int(origins[f][1])), pinned=True)
                 for pos, count in runs:
                     idx = wins[pos][1]
                     if count > 1:

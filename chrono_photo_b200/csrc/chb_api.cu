@@ -13,6 +13,8 @@
 #include <mutex>
 #include <string>
 #include <condition_variable>
+#include <map>
+#include <tuple>
 #include <vector>
 
 using namespace chb;
@@ -313,6 +315,26 @@ extern "C" size_t chb_stack_device_bytes(const chb_stack* st, int dev_slot) {
     return st->bands[dev_slot].stack_bytes;
 }
 
+// Launch attributes and occupancy of a (kernel, device, dynamic smem) triple are set / queried once and remembered: the launch
+// path of a compositing call makes no cudaFuncSetAttribute / occupancy call after the first use (host time that shows at the
+// size of config 1 and of an eighth of config 3).
+static int kernel_config(const void* kern, int device, int threads, int smem, int* occ_out) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, int, int>, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple(kern, device, smem);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int occ = 1;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        it = cache.emplace(key, std::max(1, occ)).first;
+    }
+    if (occ_out) *occ_out = it->second;
+    return CHB_OK;
+}
+
 static int grid_for(long long work_items, int threads, int sm_count, int waves) {
     long long blocks = (work_items + threads - 1) / threads;
     long long cap = (long long)sm_count * waves;
@@ -424,6 +446,39 @@ static void release_host_slot(chb_stack* st, int slot) {
     st->slot_cv.notify_one();
 }
 
+// The bookkeeping every ingest path shares: picks the frame's staging slot in its group's region, lets `enqueue` put the band's
+// rows there (a copy enqueued on d.copy), and launches the group's re-layout once its last frame has arrived.
+template <typename Enqueue>
+static int stage_frame(chb_stack* st, int frame_idx, Enqueue&& enqueue) {
+    int rc = CHB_OK;
+    std::lock_guard<std::mutex> lk(st->upload_mu);
+    const int g = frame_idx / kGroupFrames, k = frame_idx % kGroupFrames, r = g & 1;
+    for (size_t bi = 0; bi < st->bands.size() && rc == CHB_OK; bi++) {
+        Band& b = st->bands[bi];
+        Dev& d = st->ctx->devs[b.dev_slot];
+        auto cu = [&](cudaError_t e, const char* what) {
+            if (e != cudaSuccess && rc == CHB_OK) rc = fail(CHB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+            return e == cudaSuccess;
+        };
+        if (!cu(cudaSetDevice(d.id), "cudaSetDevice")) break;
+        if (!b.d_stage && !cu(cudaMalloc(&b.d_stage, (size_t)kStageFrames * b.frame_bytes), "cudaMalloc(ingest staging)")) break;
+        Band::Region& R = b.region[r];
+        if ((R.group >= 0 && R.group != g) || ((R.arrived >> k) & 1u)) {  // the region holds another group, or this frame again
+            rc = pack_region(st, b, d, r);
+            if (rc) break;
+        }
+        R.group = g;
+        // the pack launch that last read this region must be done before a copy overwrites it
+        if (!cu(cudaStreamWaitEvent(d.copy, b.packed[r], 0), "cudaStreamWaitEvent")) break;
+        if (!cu(enqueue(bi, b, d, b.d_stage + (size_t)(r * kGroupFrames + k) * b.frame_bytes), "ingest copy")) break;
+        R.arrived |= 1u << k;
+        const int in_group = std::min(kGroupFrames, st->N - g * kGroupFrames);
+        if (R.arrived == ((1u << in_group) - 1u)) rc = pack_region(st, b, d, r);
+    }
+    if (rc == CHB_OK) st->uploaded[frame_idx] = 1;
+    return rc;
+}
+
 // Ingest of one frame into every band. `pinned`: the source can be DMA'd directly; otherwise it is first copied into a pinned
 // slot of the pool by the calling thread (in parallel with other callers).
 static int upload_impl(chb_stack* st, int frame_idx, const uint8_t* host, size_t pitch, int crop_x, int crop_y, bool pinned) {
@@ -444,39 +499,16 @@ static int upload_impl(chb_stack* st, int frame_idx, const uint8_t* host, size_t
         src0 = dst;
         pitch = row_bytes;
     }
-    int rc = CHB_OK;
-    {
+    const int rc = stage_frame(st, frame_idx, [&](size_t bi, Band& b, Dev& d, uint8_t* dst) -> cudaError_t {
+        const uint8_t* src = src0 + (size_t)b.row0 * pitch;
+        cudaError_t e = pitch == row_bytes ? cudaMemcpyAsync(dst, src, b.frame_bytes, cudaMemcpyHostToDevice, d.copy)
+                                           : cudaMemcpy2DAsync(dst, row_bytes, src, pitch, row_bytes, (size_t)b.rows, cudaMemcpyHostToDevice, d.copy);
+        if (e == cudaSuccess && hs >= 0) e = cudaEventRecord(st->h_done[hs][bi], d.copy);
+        return e;
+    });
+    if (hs >= 0) {
         std::lock_guard<std::mutex> lk(st->upload_mu);
-        const int g = frame_idx / kGroupFrames, k = frame_idx % kGroupFrames, r = g & 1;
-        for (size_t bi = 0; bi < st->bands.size() && rc == CHB_OK; bi++) {
-            Band& b = st->bands[bi];
-            Dev& d = st->ctx->devs[b.dev_slot];
-            auto cu = [&](cudaError_t e, const char* what) {
-                if (e != cudaSuccess && rc == CHB_OK) rc = fail(CHB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
-                return e == cudaSuccess;
-            };
-            if (!cu(cudaSetDevice(d.id), "cudaSetDevice")) break;
-            if (!b.d_stage && !cu(cudaMalloc(&b.d_stage, (size_t)kStageFrames * b.frame_bytes), "cudaMalloc(ingest staging)")) break;
-            Band::Region& R = b.region[r];
-            if ((R.group >= 0 && R.group != g) || ((R.arrived >> k) & 1u)) {  // the region holds another group, or this frame again
-                rc = pack_region(st, b, d, r);
-                if (rc) break;
-            }
-            R.group = g;
-            // the pack launch that last read this region must be done before a copy overwrites it
-            if (!cu(cudaStreamWaitEvent(d.copy, b.packed[r], 0), "cudaStreamWaitEvent")) break;
-            uint8_t* dst = b.d_stage + (size_t)(r * kGroupFrames + k) * b.frame_bytes;
-            const uint8_t* src = src0 + (size_t)b.row0 * pitch;
-            if (pitch == row_bytes) cu(cudaMemcpyAsync(dst, src, b.frame_bytes, cudaMemcpyHostToDevice, d.copy), "cudaMemcpyAsync");
-            else cu(cudaMemcpy2DAsync(dst, row_bytes, src, pitch, row_bytes, (size_t)b.rows, cudaMemcpyHostToDevice, d.copy), "cudaMemcpy2DAsync");
-            if (rc) break;
-            if (hs >= 0) cu(cudaEventRecord(st->h_done[hs][bi], d.copy), "cudaEventRecord");
-            R.arrived |= 1u << k;
-            const int in_group = std::min(kGroupFrames, st->N - g * kGroupFrames);
-            if (R.arrived == ((1u << in_group) - 1u)) rc = pack_region(st, b, d, r);
-        }
-        if (hs >= 0) st->h_pending[hs] = true;
-        if (rc == CHB_OK) st->uploaded[frame_idx] = 1;
+        st->h_pending[hs] = true;
     }
     if (hs >= 0) release_host_slot(st, hs);
     return rc;
@@ -811,15 +843,17 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
             CU(cudaMemcpyAsync(b.d_win, st->h_win, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
             if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
         }
-        CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
         if (!b.d_queue) {  // one slot per pixel: the queues of the iterative tier and of the exact path cannot overflow
             CU(cudaMalloc(&b.d_queue, sizeof(QueueEntry) * (size_t)b.n_pixels));
             CU(cudaMalloc(&b.d_hqueue, sizeof(long long) * (size_t)b.n_pixels));
-            // one allocation, one memset per call: the two queue counters (16 words reserved), then the per-tile flag words
+            // one allocation: words 0..7 the two queue counters, words 8..15 the call's four 64-bit counters, then the per-tile
+            // flag words. The flag words are zeroed once here -- compact_hard_kernel clears every word it consumes -- so a call
+            // starts with ONE 64-byte memset.
             CU(cudaMalloc(&b.d_qcount, sizeof(uint32_t) * (16 + (size_t)b.n_tiles)));
+            CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(uint32_t) * (16 + (size_t)b.n_tiles), s));
             b.d_hflags = b.d_qcount + 16;
         }
-        CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(uint32_t) * (16 + (size_t)b.n_tiles), s));
+        CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(uint32_t) * 16, s));
         OutlierArgs ab = a;
         ab.gq = b.d_queue; ab.gq_count = b.d_qcount;
         ab.ghq = b.d_hqueue; ab.ghq_count = b.d_qcount + 1;
@@ -831,7 +865,7 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         ab.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
         ab.out_image = b.d_out;
         ab.out_mask = want_mask ? b.d_mask : nullptr;
-        ab.counters = b.d_counters;
+        ab.counters = reinterpret_cast<unsigned long long*>(b.d_qcount + 8);
         if (dbg) {
             if (dbg->median && !b.d_dbg_median) CU(cudaMalloc(&b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
             if (dbg->q1 && !b.d_dbg_q1) CU(cudaMalloc(&b.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels));
@@ -851,9 +885,10 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         if (n_tasks >= (1LL << 31)) return fail(CHB_ERR_UNSUPPORTED, "chb_outlier: band too large (%lld tile slices)", n_tasks);
         int occ = 1;
         const int smem = outlier_smem_bytes(var.wpl, var.g);
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem));
+        {
+            int krc = kernel_config((const void*)kern, d.id, kWarpsPerCta * 32, smem, &occ);
+            if (krc) return krc;
+        }
         // persistent grid: every resident warp strides over the tile slices, so its exact-path queue fills up
         const int blocks = grid_for(n_tasks * 32, kWarpsPerCta * 32, d.sm_count, std::max(1, occ));
         CU(cudaEventRecord(b.ev0, s));
@@ -881,14 +916,17 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         if (use_hist) {
             CU(launch_dep(st->C == 3 ? outlier_hist_kernel<3> : outlier_hist_kernel<4>, d.sm_count * 8, kWarpsPerCta * 32, 0));
         } else {
-            CU(cudaFuncSetAttribute(hard_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            {
+                int krc = kernel_config((const void*)hard_kern, d.id, kWarpsPerCta * 32, smem, nullptr);
+                if (krc) return krc;
+            }
             CU(launch_dep(hard_kern, blocks, kWarpsPerCta * 32, smem));
         }
         CU(launch_dep(st->C == 3 ? outlier_exact_kernel<3> : outlier_exact_kernel<4>, d.sm_count * 4, 256, 0));
         g_launches += 4;
         CU(cudaGetLastError());
         CU(cudaEventRecord(b.ev1, s));
-        CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_qcount + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
     }
     (void)P;
     if (!tables_cached) st->last_tables = blob;
@@ -1157,9 +1195,10 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             const long long n_tasks = b.n_tiles * vb.n_blocks;
             if (n_tasks >= (1LL << 31)) return fail(CHB_ERR_UNSUPPORTED, "chb_outlier_video: band too large (%lld tasks)", n_tasks);
             int occ = 1;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kVideoWarps * 32, smem));
+            {
+                int krc = kernel_config((const void*)kern, d.id, kVideoWarps * 32, smem, &occ);
+                if (krc) return krc;
+            }
             const int blocks = grid_for(n_tasks * 32, kVideoWarps * 32, d.sm_count, std::max(1, occ));
             kern<<<blocks, kVideoWarps * 32, smem, s>>>(vb);
             if (st->C == 3) video_exact_kernel<3><<<d.sm_count * 8, 128, 0, s>>>(vb);

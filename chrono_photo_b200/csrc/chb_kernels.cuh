@@ -1930,7 +1930,8 @@ __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(cons
 // Between the streaming kernel and the iterative tier: the per-tile flag words become that tier's queue. A block takes 1024
 // consecutive tiles and writes their flagged pixels in tile order (blocks land in the order of their atomicAdd), so entries
 // that are neighbours in the queue are neighbours in the image.
-__global__ void __launch_bounds__(256) compact_hard_kernel(const uint32_t* __restrict__ flags, long long n_tiles, long long* __restrict__ ghq,
+// The flag words are cleared as they are read, so the next call finds them zero without a per-call memset of the whole array.
+__global__ void __launch_bounds__(256) compact_hard_kernel(uint32_t* __restrict__ flags, long long n_tiles, long long* __restrict__ ghq,
                                                            unsigned int* __restrict__ ghq_count) {
     constexpr int kTilesPerThread = 4;
     __shared__ uint32_t warp_tot[8];
@@ -1944,6 +1945,7 @@ __global__ void __launch_bounds__(256) compact_hard_kernel(const uint32_t* __res
 #pragma unroll
         for (int k = 0; k < kTilesPerThread; k++) {
             f[k] = (t0 + k < n_tiles) ? flags[t0 + k] : 0u;
+            if (f[k]) flags[t0 + k] = 0u;
             cnt += (uint32_t)__popc(f[k]);
         }
         uint32_t incl = cnt;
