@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "chb_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "chb_kernels.cuh"), os.path.join(HERE, "csrc", "chb_common.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "chb_kernels.cuh"), os.path.join(HERE, "csrc", "chb_common.cuh"), os.path.join(HERE, "csrc", "chb_jpeg.inc"),
         os.path.join(HERE, "..", "include", "chrono_b200.h")]
 OUT = os.path.join(HERE, "libchrono_b200.so")
 
@@ -13,6 +13,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",  # Rust never contracts a*b+c; blended bytes must round like the reference
     "-shared", "-Xcompiler", "-fPIC", "--threads", "0",
+    "-lnvjpeg",  # JPEG ingest / output encode on the GPU (chb_jpeg.inc)
 ]
 
 

@@ -521,6 +521,8 @@ extern "C" int chb_stack_upload_pinned(chb_stack* st, int frame_idx, const uint8
     return upload_impl(st, frame_idx, pinned_pixels, row_pitch, crop_x, crop_y, true);
 }
 
+#include "chb_jpeg.inc"
+
 extern "C" int chb_stack_download(chb_stack* st, int frame_idx, uint8_t* host_pixels, size_t row_pitch) {
     if (!st || !host_pixels) return fail(CHB_ERR_INVALID, "chb_stack_download: null argument");
     if (frame_idx < 0 || frame_idx >= st->N) return fail(CHB_ERR_INVALID, "chb_stack_download: frame %d outside [0, %d)", frame_idx, st->N);

@@ -84,6 +84,11 @@ class FrameStack:
         fn = _lib.lib().chb_stack_upload_pinned if pinned else _lib.lib().chb_stack_upload
         _lib.check(fn(self._h, int(frame_idx), C.c_void_p(ptr), int(row_pitch), int(crop_xy[0]), int(crop_xy[1])))
 
+    def upload_jpeg(self, frame_idx, data, crop_xy=(0, 0)):
+        """One JPEG-compressed frame (bytes-like): decoded on the GPU into the stack (chb_stack_upload_jpeg)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        _lib.check(_lib.lib().chb_stack_upload_jpeg(self._h, int(frame_idx), C.c_void_p(buf.ctypes.data), buf.size, int(crop_xy[0]), int(crop_xy[1])))
+
     def upload_all(self, frames, crops=None):
         for i in range(self.n_frames):
             self.upload(i, frames[i], crops[i] if crops is not None else (0, 0))
@@ -307,6 +312,19 @@ class SimpleProcessor:
         _lib.check(_lib.lib().chb_simple_device(stack._h, C.byref(p), ip, n, C.byref(ms)))
         self.kernel_ms = ms.value
         return ms.value
+
+
+def encode_jpeg(ctx, image, quality=95):
+    """save_image's JPEG branch (src/main.rs:520-571) on the GPU: (H, W, 3) uint8 -> bytes."""
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    if img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("image must be (H, W, 3) uint8")
+    h, w, _ = img.shape
+    cap = w * h * 3 + 65536
+    out = np.empty(cap, np.uint8)
+    size = C.c_size_t(0)
+    _lib.check(_lib.lib().chb_encode_jpeg(ctx._h, C.c_void_p(img.ctypes.data), w, h, img.strides[0], int(quality), C.c_void_p(out.ctypes.data), cap, C.byref(size)))
+    return out[:size.value].tobytes()
 
 
 def set_tuning(key, value):

@@ -190,6 +190,18 @@ uint64_t chb_last_hard_pixels(void);
  * kernel_ms also covers the two tier kernels that follow it. */
 float chb_last_main_kernel_ms(void); /* pixels whose medians needed the iterative solver */
 
+/* ---- JPEG at either end of the path, on the GPU (nvJPEG) -------------------------------------------------------------
+ * chb_stack_upload_jpeg replaces ImageStream::next -> image::open (src/streams.rs:63-69) + the time-slice write for one frame:
+ * the COMPRESSED bytes cross PCIe, the frame is decoded on the device into interleaved RGB8 and re-laid-out like
+ * chb_stack_upload (crop origin = the frame's Crop, src/shake.rs:136-176). Callable from several decode threads (nvJPEG's
+ * Huffman stage runs in the caller). RGB stacks only. chb_encode_jpeg is save_image's JPEG branch (src/main.rs:520-571,
+ * quality 1..100): *out_size receives the stream length; with out == NULL or a too small buffer it fails with
+ * CHB_ERR_INVALID after setting *out_size to the needed size. Decoders differ in the last bit: parity is defined on decoded
+ * frames. */
+int chb_stack_upload_jpeg(chb_stack *stack, int frame_idx, const uint8_t *jpeg, size_t n_bytes, int crop_x, int crop_y);
+int chb_encode_jpeg(chb_ctx *ctx, const uint8_t *rgb, int width, int height, size_t row_pitch, int quality, uint8_t *out,
+                    size_t out_cap, size_t *out_size);
+
 /* Tuning / test knobs (not needed for normal use; initial values come from the environment variables CHB_<KEY> read once at
  * load time): "force_variant", "hist", "pdl", "video_queue_cap", "inline_min"; value -1 = automatic. */
 int chb_set_tuning(const char *key, int value);

@@ -89,6 +89,51 @@ def test_upload_with_pitch_and_crop(ctx):
     fs.close()
 
 
+def test_jpeg_ingest_and_encode_round_trip(ctx):
+    # JPEG in (nvJPEG decode on the device into the stack, crop origin applied) and JPEG out (save_image's JPEG branch).
+    # Codecs differ in the last bit, so parity is defined on DECODED frames: the stack's content after the JPEG upload is
+    # what both the CUDA path and the oracle then composite.
+    rng = np.random.default_rng(5)
+    n, h, w = 20, 64, 96
+    yy, xx = np.mgrid[0:h + 8, 0:w + 16]
+    frames = []
+    for f in range(n):
+        base = np.stack([(xx * 2 + f) % 256, (yy * 3) % 256, (xx + yy) % 256], axis=2).astype(np.float32)
+        img = np.clip(base + rng.normal(0, 3, base.shape), 0, 255).astype(np.uint8)
+        if 5 <= f < 9:
+            img[20:40, 30 + 4 * f:50 + 4 * f] = (250, 10, 10)
+        frames.append(img)
+    jpegs = [cp.encode_jpeg(ctx, fr, quality=95) for fr in frames]
+    assert all(j[:2] == b"\xff\xd8" and j[-2:] == b"\xff\xd9" for j in jpegs) and len(jpegs[0]) < frames[0].nbytes
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    import threading
+    crops = [(int(rng.integers(0, 16)), int(rng.integers(0, 8))) for _ in range(n)]
+    errs = []
+
+    def work(ids):
+        try:
+            for f in ids:
+                fs.upload_jpeg(f, jpegs[f], crops[f])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    threads = [threading.Thread(target=work, args=(range(k, n, 4),)) for k in range(4)]  # four decode threads, frames out of order
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+    fs.sync()
+    st = np.stack([fs.download(f) for f in range(n)])
+    for f in range(n):  # lossy but close to the source crop
+        src = frames[f][crops[f][1]:crops[f][1] + h, crops[f][0]:crops[f][0] + w].astype(np.int32)
+        assert np.abs(st[f].astype(np.int32) - src).mean() < 4.0, f
+    check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme", fs=fs)
+    assert np.array_equal(cp.SimpleProcessor(darker=True).process(fs), orc.simple(st, True))
+    with pytest.raises(cp._lib.ChbError):
+        fs.upload_jpeg(0, b"not a jpeg at all")
+    with pytest.raises(cp._lib.ChbError):
+        fs.upload_jpeg(0, jpegs[0], (17, 0))  # crop window leaves the image
+    fs.close()
+
+
 @pytest.mark.parametrize("kind", [1, 2, 3, 4])
 def test_device_generator_equals_host_twin(ctx, kind):
     n, h, w = 21, 48, 80
