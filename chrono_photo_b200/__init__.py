@@ -5,9 +5,9 @@
 """
 from .options import (BackgroundMode, Fade, FadeMode, FrameRange, OutlierSelectionMode, ParseEnumError, ParseOptionError,
                       SelectionMode, ShakeAnchor, ShakeParams, Threshold)
-from .processors import (Context, FrameStack, OutlierProcessor, ShakeAnalyzer, SimpleProcessor, crop_create, encode_jpeg, fetch_last, fetch_last_device,
+from .processors import (Context, FrameStack, OutlierProcessor, ShakeAnalyzer, SimpleProcessor, crop_create, decode_jpeg, encode_jpeg, fetch_last, fetch_last_device,
                          sample_positions, set_tuning, synth_frame_host, video_windows)
 
 __all__ = ["BackgroundMode", "Fade", "FadeMode", "FrameRange", "OutlierSelectionMode", "ParseEnumError", "ParseOptionError",
            "SelectionMode", "ShakeAnchor", "ShakeParams", "Threshold", "Context", "ShakeAnalyzer", "FrameStack", "OutlierProcessor", "SimpleProcessor", "crop_create",
-           "encode_jpeg", "fetch_last", "fetch_last_device", "set_tuning", "sample_positions", "synth_frame_host", "video_windows"]
+           "decode_jpeg", "encode_jpeg", "fetch_last", "fetch_last_device", "set_tuning", "sample_positions", "synth_frame_host", "video_windows"]

@@ -62,6 +62,7 @@ SYMBOLS = {
     "chb_set_tuning": (_i, [C.c_char_p, _i]),
     "chb_stack_upload_jpeg": (_i, [_vp, _i, _vp, C.c_size_t, _i, _i]),
     "chb_encode_jpeg": (_i, [_vp, _vp, _i, _i, C.c_size_t, _i, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "chb_decode_jpeg": (_i, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(_i), C.POINTER(_i)]),
     "chb_outlier_enqueue": (_i, [_vp, C.POINTER(OutlierParams), _i32p, _i, _i]),
     "chb_stack_wait": (_i, [_vp, _f32p, _u64p]),
     "chb_outlier_video": (_i, [_vp, C.POINTER(OutlierParams), _i, _i, _i, _vp, _vp, _u64p]),

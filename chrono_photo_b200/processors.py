@@ -327,6 +327,18 @@ def encode_jpeg(ctx, image, quality=95):
     return out[:size.value].tobytes()
 
 
+def decode_jpeg(ctx, data):
+    """JPEG bytes -> (H, W, 3) uint8 host image, decoded on the GPU (chb_decode_jpeg): the host copy the shake analysis reads
+    (image::open per frame, src/shake.rs:248-283)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    w, h = C.c_int(0), C.c_int(0)
+    _lib.check(_lib.lib().chb_decode_jpeg(ctx._h, C.c_void_p(buf.ctypes.data), buf.size, None, 0, 0, C.byref(w), C.byref(h)))
+    out = np.empty((h.value, w.value, 3), dtype=np.uint8)
+    _lib.check(_lib.lib().chb_decode_jpeg(ctx._h, C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(out.ctypes.data), out.nbytes, w.value * 3,
+                                          C.byref(w), C.byref(h)))
+    return out
+
+
 def set_tuning(key, value):
     """Tuning / test knobs of the library (chb_set_tuning): 'force_variant', 'hist', 'pdl', 'video_queue_cap', 'inline_min'."""
     _lib.check(_lib.lib().chb_set_tuning(str(key).encode(), int(value)))

@@ -201,6 +201,11 @@ float chb_last_main_kernel_ms(void); /* pixels whose medians needed the iterativ
 int chb_stack_upload_jpeg(chb_stack *stack, int frame_idx, const uint8_t *jpeg, size_t n_bytes, int crop_x, int crop_y);
 int chb_encode_jpeg(chb_ctx *ctx, const uint8_t *rgb, int width, int height, size_t row_pitch, int quality, uint8_t *out,
                     size_t out_cap, size_t *out_size);
+/* JPEG stream -> interleaved RGB8 HOST image (decoded on the device, copied back): the host copy the callers around the path
+ * need, e.g. the shake analysis that reads every frame before ingest (image::open in src/shake.rs:248-283). out == NULL:
+ * only *out_width / *out_height are set. */
+int chb_decode_jpeg(chb_ctx *ctx, const uint8_t *jpeg, size_t n_bytes, uint8_t *out, size_t out_cap, size_t row_pitch,
+                    int *out_width, int *out_height);
 
 /* Tuning / test knobs (not needed for normal use; initial values come from the environment variables CHB_<KEY> read once at
  * load time): "force_variant", "hist", "pdl", "video_queue_cap", "inline_min"; value -1 = automatic. */
