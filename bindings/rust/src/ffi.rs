@@ -119,6 +119,14 @@ extern "C" {
                             anchor_radius: c_int, search_radius: c_int, first_frame: *const u8, row_pitch: usize, out: *mut *mut ChbShake) -> c_int;
     pub fn chb_shake_offset(analyzer: *mut ChbShake, frame: *const u8, row_pitch: usize, out_dx: *mut i32, out_dy: *mut i32, diffs: *mut i32) -> c_int;
     pub fn chb_shake_destroy(analyzer: *mut ChbShake) -> c_int;
+    pub fn chb_crop_create(offsets_xy: *const i32, n: c_int, width: c_int, height: c_int, out_xy: *mut i32, out_w: *mut i32, out_h: *mut i32) -> c_int;
+    // JPEG at either end of the path (nvJPEG): ImageStream::next -> image::open (src/streams.rs:63-69) and save_image's JPEG
+    // branch (src/main.rs:520-571)
+    pub fn chb_stack_upload_jpeg(stack: *mut ChbStack, frame_idx: c_int, jpeg: *const u8, n_bytes: usize, crop_x: c_int, crop_y: c_int) -> c_int;
+    pub fn chb_decode_jpeg(ctx: *mut ChbCtx, jpeg: *const u8, n_bytes: usize, out: *mut u8, out_cap: usize, row_pitch: usize,
+                           out_width: *mut c_int, out_height: *mut c_int) -> c_int;
+    pub fn chb_encode_jpeg(ctx: *mut ChbCtx, rgb: *const u8, width: c_int, height: c_int, row_pitch: usize, quality: c_int, out: *mut u8,
+                           out_cap: usize, out_size: *mut usize) -> c_int;
 }
 
 pub unsafe fn last_error() -> String {

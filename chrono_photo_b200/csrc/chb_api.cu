@@ -48,10 +48,12 @@ struct Tuning {
     std::atomic<int> pdl{1};               // CHB_PDL: tier kernels as programmatic dependent launches
     std::atomic<int> video_queue_cap{-1};  // CHB_VIDEO_QUEUE_CAP: capacity of the video exact-path queue (tests the in-place fallback)
     std::atomic<int> inline_min{12};       // CHB_INLINE_MIN: uncertified pixels per tile from which the tile is finished inside K1 (0 = never)
+    std::atomic<int> video_direct{0};      // CHB_VIDEO_DIRECT: 0 = chrono-video runs with absolute thresholds use the sliding-count kernel too
+    std::atomic<int> hard_inline_min{1};   // CHB_HARD_INLINE_MIN: same for a warp-full of the iterative tier (finished inside outlier_hard_kernel)
     Tuning() {
         auto env = [](const char* k, std::atomic<int>& v) { if (const char* e = getenv(k)) v.store(atoi(e)); };
         env("CHB_FORCE_VARIANT", force_variant); env("CHB_HIST", hist); env("CHB_PDL", pdl);
-        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min);
+        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min); env("CHB_HARD_INLINE_MIN", hard_inline_min); env("CHB_VIDEO_DIRECT", video_direct);
     }
 };
 static Tuning g_tune;
@@ -63,6 +65,8 @@ extern "C" int chb_set_tuning(const char* key, int value) {
     else if (k == "pdl") g_tune.pdl.store(value);
     else if (k == "video_queue_cap") g_tune.video_queue_cap.store(value);
     else if (k == "inline_min") g_tune.inline_min.store(value);
+    else if (k == "hard_inline_min") g_tune.hard_inline_min.store(value);
+    else if (k == "video_direct") g_tune.video_direct.store(value);
     else return fail(CHB_ERR_INVALID, "chb_set_tuning: unknown key '%s'", key);
     return CHB_OK;
 }
@@ -85,23 +89,14 @@ struct chb_ctx {
     std::vector<Dev> devs;
 };
 
-struct Band {
-    int dev_slot = 0;
-    int row0 = 0, rows = 0;
-    long long n_pixels = 0, n_tiles = 0;
-    size_t stack_bytes = 0, frame_bytes = 0;
-    uint8_t* d_stack = nullptr;
+// Per-band device state of ONE compositing call in flight. A stack owns kCallSlots of them, so that chb_outlier / chb_simple
+// entered from several host threads (the reference calls process() from a rayon pool: src/main.rs:260-261, :378-379) overlap their
+// launches, tier kernels and D2H copies instead of queueing on one output buffer. Allocated at first use of the slot.
+static constexpr int kCallSlots = 4;
+struct CallBuf {
+    cudaStream_t own_stream = nullptr;  // slots >= 1; slot 0 runs on the device's compute stream (chb_ctx_set_stream)
     uint8_t* d_out = nullptr;
     uint8_t* d_mask = nullptr;
-    // ingest: device staging for two frame groups (2 x 16 frames, allocated at the first upload). A group whose frames have all
-    // arrived is re-laid-out by ONE pack_group_kernel launch that writes whole 16-byte units (no byte scatter); the other
-    // region receives the next group's copies meanwhile.
-    uint8_t* d_stage = nullptr;  // [2 * 16][frame_bytes]
-    struct Region { int group = -1; uint32_t arrived = 0; } region[2];
-    cudaEvent_t copied = nullptr;               // recorded on d.copy after a group's last H2D (stream order covers the earlier ones)
-    cudaEvent_t packed[2] = {nullptr, nullptr};  // the pack launch that last read region r finished
-    uint8_t* d_tmp = nullptr;                    // one frame: chb_stack_download
-    // per-call scratch
     uint32_t* d_wmask = nullptr;
     uint32_t* d_smask = nullptr;
     int32_t* d_win = nullptr;
@@ -111,20 +106,52 @@ struct Band {
     float *d_dbg_median = nullptr, *d_dbg_q1 = nullptr, *d_dbg_q3 = nullptr;
     int* d_dbg_nout = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;  // ev_mid: after the streaming kernel, before the tier kernels
-    // chrono-video: two slots of window planes (composites, masks), per-window warning counters
+    QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters ([0..1] exact, [2..3] iterative tier)
+    long long* d_hqueue = nullptr;        // iterative-tier queue (pixel indices)
+    uint32_t* d_hflags = nullptr;         // per-tile flag words the iterative-tier queue is built from
+    unsigned int* d_qcount = nullptr;
+};
+
+struct Band {
+    int dev_slot = 0;
+    int row0 = 0, rows = 0;
+    long long n_pixels = 0, n_tiles = 0;
+    size_t stack_bytes = 0, frame_bytes = 0;
+    uint8_t* d_stack = nullptr;
+    CallBuf call[kCallSlots];
+    // ingest: device staging for two frame groups (2 x 16 frames, allocated at the first upload). A group whose frames have all
+    // arrived is re-laid-out by ONE pack_group_kernel launch that writes whole 16-byte units (no byte scatter); the other
+    // region receives the next group's copies meanwhile.
+    uint8_t* d_stage = nullptr;  // [2 * 16][frame_bytes]
+    struct Region { int group = -1; uint32_t arrived = 0; } region[2];
+    cudaEvent_t copied = nullptr;               // recorded on d.copy after a group's last H2D (stream order covers the earlier ones)
+    cudaEvent_t packed[2] = {nullptr, nullptr};  // the pack launch that last read region r finished
+    uint8_t* d_tmp = nullptr;                    // one frame: chb_stack_download
+    // chrono-video (runs on call slot 0): two slots of window planes (composites, masks), per-window warning counters
     uint8_t* d_vout[2] = {nullptr, nullptr};
     uint8_t* d_vmask[2] = {nullptr, nullptr};
     int v_cap_windows = 0;
     unsigned long long* d_vwarn = nullptr;
     int vwarn_cap = 0;
-    QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters ([0..1] exact, [2..3] iterative tier)
-    long long* d_hqueue = nullptr;        // iterative-tier queue (pixel indices)
-    uint32_t* d_hflags = nullptr;         // per-tile flag words the iterative-tier queue is built from
-    unsigned int* d_qcount = nullptr;
     VideoQueueEntry* d_vqueue = nullptr;  // exact-path queue of a chunk + its counter
     unsigned int* d_vqcount = nullptr;
     cudaEvent_t v_done[2] = {nullptr, nullptr};    // kernel writing slot s finished
     cudaEvent_t v_copied[2] = {nullptr, nullptr};  // D2H of slot s finished
+};
+
+// Host side of a call slot: pinned scratch for the per-call tables and what the slot's last call left behind.
+struct CallSlot {
+    bool ready = false, in_use = false;
+    uint32_t* h_wmask = nullptr;
+    uint32_t* h_smask = nullptr;
+    int32_t* h_win = nullptr;
+    int32_t* h_posg = nullptr;
+    float* h_fade = nullptr;
+    unsigned long long* h_counters = nullptr;  // [n_bands * 4]
+    int last_kind = 0;  // what ran last on the slot: 0 nothing yet, 1 a single-window call (its planes can be fetched), 2 a video run
+    bool last_has_mask = false;
+    uint64_t last_warnings = 0;
+    std::vector<uint8_t> last_tables;  // fingerprint of the per-call tables currently on the devices
 };
 
 struct chb_stack {
@@ -132,7 +159,12 @@ struct chb_stack {
     int W = 0, H = 0, C = 0, N = 0, NG = 0;
     std::vector<Band> bands;
     std::vector<uint8_t> uploaded;  // per frame
-    std::mutex upload_mu, call_mu;
+    std::mutex upload_mu;
+    // call slots: the host-buffer entry points (chb_outlier, chb_simple) take any free slot; the device-side API (chb_*_device,
+    // chb_outlier_enqueue, chb_stack_wait, chb_fetch_last*, chb_outlier_video*) is defined on "the last call" and owns slot 0
+    CallSlot slots[kCallSlots];
+    std::mutex call_mu;
+    std::condition_variable call_cv;
     // pageable sources: a pool of pinned host frames; a caller thread owns one slot while it copies its frame into it (no lock
     // held during the memcpy), so several decode threads stage in parallel
     static constexpr int kHostSlots = 8;
@@ -142,19 +174,9 @@ struct chb_stack {
     bool h_pending[kHostSlots] = {};
     std::mutex slot_mu;
     std::condition_variable slot_cv;
-    // pinned host scratch for per-call tables
-    uint32_t* h_wmask = nullptr;
-    uint32_t* h_smask = nullptr;
-    int32_t* h_win = nullptr;
-    int32_t* h_posg = nullptr;
-    float* h_fade = nullptr;
-    unsigned long long* h_counters = nullptr;  // [n_bands * 2]
-    bool last_has_mask = false;
-    uint64_t last_warnings = 0;
-    std::vector<uint8_t> last_tables;  // fingerprint of the per-call tables currently on the devices
 };
 
-static constexpr int kMaxWindowFrames = 4096;  // largest window span the register-resident kernels hold
+static constexpr int kMaxWindowFrames = 4096;  // largest window span the register-resident kernels hold (longer whole-stack series: histogram tier)
 static constexpr int kMaxGroupsTable = kMaxWindowFrames / 16;
 
 // ------------------------------------------------------------------------------------------------ context
@@ -216,22 +238,27 @@ extern "C" int chb_ctx_set_stream(chb_ctx* ctx, int dev_slot, void* cuda_stream)
 
 // ------------------------------------------------------------------------------------------------ stack
 static void free_band(Band& b) {
-    cudaFree(b.d_stack); cudaFree(b.d_out); cudaFree(b.d_mask);
+    cudaFree(b.d_stack);
     cudaFree(b.d_stage); cudaFree(b.d_tmp);
     if (b.copied) cudaEventDestroy(b.copied);
     for (int s = 0; s < 2; s++)
         if (b.packed[s]) cudaEventDestroy(b.packed[s]);
-    cudaFree(b.d_wmask); cudaFree(b.d_smask); cudaFree(b.d_win); cudaFree(b.d_posg); cudaFree(b.d_fade); cudaFree(b.d_counters);
-    cudaFree(b.d_dbg_median); cudaFree(b.d_dbg_q1); cudaFree(b.d_dbg_q3); cudaFree(b.d_dbg_nout);
-    if (b.ev0) cudaEventDestroy(b.ev0);
-    if (b.ev1) cudaEventDestroy(b.ev1);
-    if (b.ev_mid) cudaEventDestroy(b.ev_mid);
+    for (CallBuf& cb : b.call) {
+        cudaFree(cb.d_out); cudaFree(cb.d_mask);
+        cudaFree(cb.d_wmask); cudaFree(cb.d_smask); cudaFree(cb.d_win); cudaFree(cb.d_posg); cudaFree(cb.d_fade); cudaFree(cb.d_counters);
+        cudaFree(cb.d_dbg_median); cudaFree(cb.d_dbg_q1); cudaFree(cb.d_dbg_q3); cudaFree(cb.d_dbg_nout);
+        cudaFree(cb.d_queue); cudaFree(cb.d_hqueue); cudaFree(cb.d_qcount);
+        if (cb.ev0) cudaEventDestroy(cb.ev0);
+        if (cb.ev1) cudaEventDestroy(cb.ev1);
+        if (cb.ev_mid) cudaEventDestroy(cb.ev_mid);
+        if (cb.own_stream) cudaStreamDestroy(cb.own_stream);
+    }
     for (int s = 0; s < 2; s++) {
         cudaFree(b.d_vout[s]); cudaFree(b.d_vmask[s]);
         if (b.v_done[s]) cudaEventDestroy(b.v_done[s]);
         if (b.v_copied[s]) cudaEventDestroy(b.v_copied[s]);
     }
-    cudaFree(b.d_vwarn); cudaFree(b.d_vqueue); cudaFree(b.d_vqcount); cudaFree(b.d_queue); cudaFree(b.d_hqueue); cudaFree(b.d_qcount);
+    cudaFree(b.d_vwarn); cudaFree(b.d_vqueue); cudaFree(b.d_vqcount);
 }
 
 extern "C" int chb_stack_destroy(chb_stack* st) {
@@ -245,15 +272,72 @@ extern "C" int chb_stack_destroy(chb_stack* st) {
         if (st->h_slot[k]) cudaFreeHost(st->h_slot[k]);
         for (cudaEvent_t e : st->h_done[k]) cudaEventDestroy(e);
     }
-    if (st->h_wmask) cudaFreeHost(st->h_wmask);
-    if (st->h_smask) cudaFreeHost(st->h_smask);
-    if (st->h_win) cudaFreeHost(st->h_win);
-    if (st->h_posg) cudaFreeHost(st->h_posg);
-    if (st->h_fade) cudaFreeHost(st->h_fade);
-    if (st->h_counters) cudaFreeHost(st->h_counters);
+    for (CallSlot& cs : st->slots) {
+        if (cs.h_wmask) cudaFreeHost(cs.h_wmask);
+        if (cs.h_smask) cudaFreeHost(cs.h_smask);
+        if (cs.h_win) cudaFreeHost(cs.h_win);
+        if (cs.h_posg) cudaFreeHost(cs.h_posg);
+        if (cs.h_fade) cudaFreeHost(cs.h_fade);
+        if (cs.h_counters) cudaFreeHost(cs.h_counters);
+    }
     delete st;
     return CHB_OK;
 }
+
+// Buffers of call slot `slot` (pinned tables, per band: output planes, tables, events, a stream for slots >= 1), at first use.
+// The caller owns the slot.
+static int ensure_call_slot(chb_stack* st, int slot) {
+    CallSlot& cs = st->slots[slot];
+    if (cs.ready) return CHB_OK;
+    const int nd = (int)st->bands.size();
+    CU(cudaMallocHost(&cs.h_wmask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+    CU(cudaMallocHost(&cs.h_smask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+    CU(cudaMallocHost(&cs.h_win, sizeof(int32_t) * (size_t)std::max(st->N, 1)));
+    CU(cudaMallocHost(&cs.h_posg, sizeof(int32_t) * (size_t)st->NG));
+    CU(cudaMallocHost(&cs.h_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
+    CU(cudaMallocHost(&cs.h_counters, sizeof(unsigned long long) * 4 * nd));
+    for (Band& b : st->bands) {
+        CallBuf& cb = b.call[slot];
+        CU(cudaSetDevice(st->ctx->devs[b.dev_slot].id));
+        if (slot > 0) CU(cudaStreamCreateWithFlags(&cb.own_stream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&cb.d_out, b.frame_bytes));
+        CU(cudaMalloc(&cb.d_mask, b.frame_bytes));
+        CU(cudaMalloc(&cb.d_wmask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+        CU(cudaMalloc(&cb.d_smask, sizeof(uint32_t) * kMaxGroupsTable * 4));
+        CU(cudaMalloc(&cb.d_win, sizeof(int32_t) * (size_t)st->N));
+        CU(cudaMalloc(&cb.d_posg, sizeof(int32_t) * (size_t)st->NG));
+        CU(cudaMalloc(&cb.d_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
+        CU(cudaMalloc(&cb.d_counters, sizeof(unsigned long long) * 4));
+        CU(cudaEventCreate(&cb.ev0));
+        CU(cudaEventCreate(&cb.ev1));
+        CU(cudaEventCreate(&cb.ev_mid));
+    }
+    cs.ready = true;
+    return CHB_OK;
+}
+
+// Takes a call slot for the duration of one entry point: slot 0 (the device-side API's "last call") or the lowest free one.
+struct SlotGuard {
+    chb_stack* st;
+    int slot = -1;
+    SlotGuard(chb_stack* s, bool want_zero) : st(s) {
+        std::unique_lock<std::mutex> lk(st->call_mu);
+        if (want_zero) {
+            st->call_cv.wait(lk, [&] { return !st->slots[0].in_use; });
+            slot = 0;
+        } else {
+            st->call_cv.wait(lk, [&] { for (const CallSlot& c : st->slots) if (!c.in_use) return true; return false; });
+            slot = 0;
+            while (st->slots[slot].in_use) slot++;
+        }
+        st->slots[slot].in_use = true;
+    }
+    ~SlotGuard() {
+        { std::lock_guard<std::mutex> lk(st->call_mu); st->slots[slot].in_use = false; }
+        st->call_cv.notify_all();
+    }
+};
+static cudaStream_t call_stream(const Dev& d, const CallBuf& cb, int slot) { return slot == 0 ? d.compute : cb.own_stream; }
 
 extern "C" int chb_stack_create(chb_ctx* ctx, int width, int height, int channels, int n_frames, chb_stack** out) {
     if (!ctx || !out) return fail(CHB_ERR_INVALID, "chb_stack_create: null argument");
@@ -272,12 +356,6 @@ extern "C" int chb_stack_create(chb_ctx* ctx, int width, int height, int channel
         cudaError_t e__ = (call);                                                                                   \
         if (e__ != cudaSuccess) return bail(fail(CHB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__)); \
     } while (0)
-    CUB(cudaMallocHost(&st->h_wmask, sizeof(uint32_t) * kMaxGroupsTable * 4));
-    CUB(cudaMallocHost(&st->h_smask, sizeof(uint32_t) * kMaxGroupsTable * 4));
-    CUB(cudaMallocHost(&st->h_win, sizeof(int32_t) * (size_t)std::max(n_frames, 1)));
-    CUB(cudaMallocHost(&st->h_posg, sizeof(int32_t) * (size_t)st->NG));
-    CUB(cudaMallocHost(&st->h_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
-    CUB(cudaMallocHost(&st->h_counters, sizeof(unsigned long long) * 4 * nd));
     st->bands.resize(nd);
     for (int k = 0; k < nd; k++) {
         Band& b = st->bands[k];
@@ -291,21 +369,15 @@ extern "C" int chb_stack_create(chb_ctx* ctx, int width, int height, int channel
         CUB(cudaSetDevice(ctx->devs[k].id));
         CUB(cudaMalloc(&b.d_stack, b.stack_bytes));
         CUB(cudaMemset(b.d_stack, 0, b.stack_bytes));  // frames beyond n_frames in the last group must read as zero
-        CUB(cudaMalloc(&b.d_out, b.frame_bytes));
-        CUB(cudaMalloc(&b.d_mask, b.frame_bytes));
         CUB(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
         for (int s = 0; s < 2; s++) CUB(cudaEventCreateWithFlags(&b.packed[s], cudaEventDisableTiming));
-        CUB(cudaMalloc(&b.d_wmask, sizeof(uint32_t) * kMaxGroupsTable * 4));
-        CUB(cudaMalloc(&b.d_smask, sizeof(uint32_t) * kMaxGroupsTable * 4));
-        CUB(cudaMalloc(&b.d_win, sizeof(int32_t) * (size_t)n_frames));
-        CUB(cudaMalloc(&b.d_posg, sizeof(int32_t) * (size_t)st->NG));
-        CUB(cudaMalloc(&b.d_fade, sizeof(float) * CHB_MAX_FADE_VALUES));
-        CUB(cudaMalloc(&b.d_counters, sizeof(unsigned long long) * 4));
-        CUB(cudaEventCreate(&b.ev0));
-        CUB(cudaEventCreate(&b.ev1));
         CUB(cudaDeviceSynchronize());
     }
 #undef CUB
+    {
+        const int rc = ensure_call_slot(st, 0);
+        if (rc) return bail(rc);
+    }
     *out = st;
     return CHB_OK;
 }
@@ -712,19 +784,22 @@ static int fade_to_dev(const chb_fade& f, FadeDev& out, const char* who) {
     out.n_values = f.n_values;
     out.values = nullptr;
     if (!f.is_none) {
-        if (f.n_values < 1 || f.n_values > CHB_MAX_FADE_VALUES || !f.values) return fail(CHB_ERR_INVALID, "%s: fade needs 1..%d values", who, CHB_MAX_FADE_VALUES);
+        if (f.n_values < 1 || !f.values) return fail(CHB_ERR_INVALID, "%s: a fade needs at least one value", who);
+        if (f.n_values > CHB_MAX_FADE_VALUES)  // a build limit, not invalid input: the reference accepts any length
+            return fail(CHB_ERR_UNSUPPORTED, "%s: fade of %d values; this build holds at most %d", who, f.n_values, CHB_MAX_FADE_VALUES);
         if (f.mode != CHB_FADE_CLAMP && f.mode != CHB_FADE_REPEAT) return fail(CHB_ERR_INVALID, "%s: unknown fade mode", who);
     }
     return CHB_OK;
 }
 
-static int collect_outlier(chb_stack* st, const chb_debug_planes* dbg, float* kernel_ms, bool want_mask);
+static int collect_outlier(chb_stack* st, int slot, const chb_debug_planes* dbg, float* kernel_ms, bool want_mask);
 
-static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, bool want_mask,
+static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, const int32_t* indices, int n_indices, bool want_mask,
                         const chb_debug_planes* dbg, float* kernel_ms, bool enqueue_only = false) {
     if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_outlier: null argument");
     if (prm->background > CHB_BG_MEDIAN || prm->outlier > CHB_OUT_BACKWARD) return fail(CHB_ERR_INVALID, "chb_outlier: unknown background / outlier mode");
-    // the caller holds st->call_mu: launch and fetch form one critical section per stack
+    // the caller owns call slot `slot`: launch and fetch form one critical section per slot
+    CallSlot& cs = st->slots[slot];
     Window win;
     int rc = build_window(st, indices, n_indices, win, "chb_outlier");
     if (rc) return rc;
@@ -751,9 +826,15 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         const int v = g_tune.force_variant.load();
         if (v >= 0 && v < kNumVariants && kVariants[v].wpl * kVariants[v].g >= win.n_groups) vidx = v;
     }
-    if (vidx < 0)
-        return fail(CHB_ERR_UNSUPPORTED, "chb_outlier: window spans %d frames; this build holds at most %d per launch", win.n_groups * 16, kMaxWindowFrames);
-    const Variant var = kVariants[vidx];
+    // Series longer than the register-resident variants hold (more than 4096 frames): every pixel goes through the histogram tier
+    // (outlier_hist_kernel reads a series of any length: one warp per pixel, a 256-bin histogram per band) and the per-frame path
+    // for what its certificate cannot clear. Whole-stack launches only (a window or a --sample subset of such a series would need
+    // byte masks the histogram kernel does not apply).
+    const bool long_series = vidx < 0;
+    if (long_series && (sub || n != st->N))
+        return fail(CHB_ERR_UNSUPPORTED, "chb_outlier: a window or --sample subset spanning %d frames; beyond %d frames only whole-stack launches are supported",
+                    win.n_groups * 16, kMaxWindowFrames);
+    const Variant var = long_series ? Variant{0, 1} : kVariants[vidx];
     const int cap_groups = var.wpl * var.g;
 
     OutlierArgs a;
@@ -783,20 +864,21 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     a.exact_quartiles = (dbg && (dbg->q1 || dbg->q3)) ? 1 : 0;
     a.seed = prm->seed;
     // dense per-frame pass with per-group outlier masks: integer distance, contiguous window of at most kMaskGroups groups
-    a.mask_path = (a.int_dist && a.contig_f0 >= 0 && win.n_groups <= kMaskGroups) ? 1 : 0;
+    a.mask_path = (a.int_dist && a.thr4 >= 5 && a.contig_f0 >= 0 && win.n_groups <= kMaskGroups) ? 1 : 0;  // thr4 >= 5: see dense_masks_int
     // ... run inside the streaming kernel (lane = pixel: the G == 1 variants) for tiles with at least this many uncertified pixels
     a.inline_min = (a.mask_path && var.g == 1) ? g_tune.inline_min.load() : 0;
+    a.hard_inline_min = (a.mask_path && var.g == 1) ? g_tune.hard_inline_min.load() : 0;
 
     // host tables
-    byte_masks(win.frames, win.g0, cap_groups, st->h_wmask);
+    if (!long_series) byte_masks(win.frames, win.g0, cap_groups, cs.h_wmask);
     unsigned patch = 0;
     for (int i = 0; i < var.wpl; i++)
         for (int jx = 0; jx < var.g; jx++) {
-            const uint32_t* m = st->h_wmask + (size_t)(i * var.g + jx) * 4;
+            const uint32_t* m = cs.h_wmask + (size_t)(i * var.g + jx) * 4;
             if ((m[0] & m[1] & m[2] & m[3]) != 0xffffffffu && i < var.wpl - 1) patch |= 1u << i;
         }
     a.patch_slots = patch;
-    a.lead_slots_full = (win.n_groups >= (var.wpl - 1) * var.g) ? 1 : 0;
+    a.lead_slots_full = (!long_series && win.n_groups >= (var.wpl - 1) * var.g) ? 1 : 0;
     // frames that exist in the stack, lie inside the span, but are not part of the window must be masked after the load
     {
         int in_span_existing = std::min(st->N, (win.g0 + win.n_groups) * kGroupFrames) - win.g0 * kGroupFrames;
@@ -805,19 +887,20 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
     if (sub) {
         std::vector<int32_t> sframes(spos.size());
         for (size_t i = 0; i < spos.size(); i++) sframes[i] = win.frames[spos[i]];
-        byte_masks(sframes, win.g0, cap_groups, st->h_smask);
+        byte_masks(sframes, win.g0, cap_groups, cs.h_smask);
     }
-    memcpy(st->h_win, win.frames.data(), sizeof(int32_t) * (size_t)n);
-    if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
+    memcpy(cs.h_win, win.frames.data(), sizeof(int32_t) * (size_t)n);
+    if (!prm->fade.is_none) memcpy(cs.h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
 
     // the lean kernel covers whole-stack launches whose leading register slots are all real frame groups
     const bool generic = sub || a.window_masked || a.patch_slots || !a.lead_slots_full || a.exact_quartiles;
     const int kmode = generic ? 0 : (a.absolute ? 1 : 2);
-    OutlierKernel kern;
-    if (st->C == 3) kern = kmode == 0 ? kernel_for<3, 0>(vidx) : (kmode == 1 ? kernel_for<3, 1>(vidx) : kernel_for<3, 2>(vidx));
+    OutlierKernel kern = nullptr, hard_kern = nullptr;
+    if (long_series) { /* no streaming kernel */ }
+    else if (st->C == 3) kern = kmode == 0 ? kernel_for<3, 0>(vidx) : (kmode == 1 ? kernel_for<3, 1>(vidx) : kernel_for<3, 2>(vidx));
     else kern = kmode == 0 ? kernel_for<4, 0>(vidx) : (kmode == 1 ? kernel_for<4, 1>(vidx) : kernel_for<4, 2>(vidx));
-    OutlierKernel hard_kern;
-    if (st->C == 3) hard_kern = kmode == 0 ? hard_kernel_for<3, 0>(vidx) : (kmode == 1 ? hard_kernel_for<3, 1>(vidx) : hard_kernel_for<3, 2>(vidx));
+    if (long_series) { /* the histogram kernel is the iterative tier */ }
+    else if (st->C == 3) hard_kern = kmode == 0 ? hard_kernel_for<3, 0>(vidx) : (kmode == 1 ? hard_kernel_for<3, 1>(vidx) : hard_kernel_for<3, 2>(vidx));
     else hard_kern = kmode == 0 ? hard_kernel_for<4, 0>(vidx) : (kmode == 1 ? hard_kernel_for<4, 1>(vidx) : hard_kernel_for<4, 2>(vidx));
 
     // fingerprint of the device-side tables of this call
@@ -826,81 +909,95 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         auto put = [&](const void* p, size_t nbytes) { const uint8_t* q = (const uint8_t*)p; blob.insert(blob.end(), q, q + nbytes); };
         const int hdr[4] = {1 /* outlier */, cap_groups, n, sub ? 1 : 0};
         put(hdr, sizeof hdr);
-        put(st->h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4);
-        if (sub) put(st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4);
-        put(st->h_win, sizeof(int32_t) * (size_t)n);
-        if (!prm->fade.is_none) put(st->h_fade, sizeof(float) * (size_t)prm->fade.n_values);
+        put(cs.h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4);
+        if (sub) put(cs.h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4);
+        put(cs.h_win, sizeof(int32_t) * (size_t)n);
+        if (!prm->fade.is_none) put(cs.h_fade, sizeof(float) * (size_t)prm->fade.n_values);
     }
-    const bool tables_cached = (blob == st->last_tables);
-    if (!tables_cached) st->last_tables.clear();  // set again once every band's copies and launches were enqueued
+    const bool tables_cached = (blob == cs.last_tables);
+    if (!tables_cached) cs.last_tables.clear();  // set again once every band's copies and launches were enqueued
     const size_t P = (size_t)st->W * st->H;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
-        cudaStream_t s = d.compute;
+        CallBuf& cb = b.call[slot];
+        cudaStream_t s = call_stream(d, cb, slot);
         CU(wait_ingest(b, s));
         if (!tables_cached) {  // window / sample / fade tables: uploaded only when they differ from the previous call's
-            CU(cudaMemcpyAsync(b.d_wmask, st->h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
-            if (sub) CU(cudaMemcpyAsync(b.d_smask, st->h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
-            CU(cudaMemcpyAsync(b.d_win, st->h_win, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
-            if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(cb.d_wmask, cs.h_wmask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
+            if (sub) CU(cudaMemcpyAsync(cb.d_smask, cs.h_smask, sizeof(uint32_t) * (size_t)cap_groups * 4, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(cb.d_win, cs.h_win, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+            if (!prm->fade.is_none) CU(cudaMemcpyAsync(cb.d_fade, cs.h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
         }
-        if (!b.d_queue) {  // one slot per pixel: the queues of the iterative tier and of the exact path cannot overflow
-            CU(cudaMalloc(&b.d_queue, sizeof(QueueEntry) * (size_t)b.n_pixels));
-            CU(cudaMalloc(&b.d_hqueue, sizeof(long long) * (size_t)b.n_pixels));
+        if (!cb.d_queue) {  // one slot per pixel: the queues of the iterative tier and of the exact path cannot overflow
+            CU(cudaMalloc(&cb.d_queue, sizeof(QueueEntry) * (size_t)b.n_pixels));
+            CU(cudaMalloc(&cb.d_hqueue, sizeof(long long) * (size_t)b.n_pixels));
             // one allocation: words 0..7 the two queue counters, words 8..15 the call's four 64-bit counters, then the per-tile
             // flag words. The flag words are zeroed once here -- compact_hard_kernel clears every word it consumes -- so a call
             // starts with ONE 64-byte memset.
-            CU(cudaMalloc(&b.d_qcount, sizeof(uint32_t) * (16 + (size_t)b.n_tiles)));
-            CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(uint32_t) * (16 + (size_t)b.n_tiles), s));
-            b.d_hflags = b.d_qcount + 16;
+            CU(cudaMalloc(&cb.d_qcount, sizeof(uint32_t) * (16 + (size_t)b.n_tiles)));
+            CU(cudaMemsetAsync(cb.d_qcount, 0, sizeof(uint32_t) * (16 + (size_t)b.n_tiles), s));
+            cb.d_hflags = cb.d_qcount + 16;
         }
-        CU(cudaMemsetAsync(b.d_qcount, 0, sizeof(uint32_t) * 16, s));
+        CU(cudaMemsetAsync(cb.d_qcount, 0, sizeof(uint32_t) * 16, s));
         OutlierArgs ab = a;
-        ab.gq = b.d_queue; ab.gq_count = b.d_qcount;
-        ab.ghq = b.d_hqueue; ab.ghq_count = b.d_qcount + 1;
-        ab.hflags = b.d_hflags;
+        ab.gq = cb.d_queue; ab.gq_count = cb.d_qcount;
+        ab.ghq = cb.d_hqueue; ab.ghq_count = cb.d_qcount + 1;
+        ab.hflags = cb.d_hflags;
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
-        ab.wmask = b.d_wmask; ab.smask = sub ? b.d_smask : nullptr; ab.win_frames = b.d_win;
-        ab.fade.values = b.d_fade;
+        ab.wmask = cb.d_wmask; ab.smask = sub ? cb.d_smask : nullptr; ab.win_frames = cb.d_win;
+        ab.fade.values = cb.d_fade;
         ab.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
-        ab.out_image = b.d_out;
-        ab.out_mask = want_mask ? b.d_mask : nullptr;
-        ab.counters = reinterpret_cast<unsigned long long*>(b.d_qcount + 8);
+        ab.out_image = cb.d_out;
+        ab.out_mask = want_mask ? cb.d_mask : nullptr;
+        ab.counters = reinterpret_cast<unsigned long long*>(cb.d_qcount + 8);
         if (dbg) {
-            if (dbg->median && !b.d_dbg_median) CU(cudaMalloc(&b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
-            if (dbg->q1 && !b.d_dbg_q1) CU(cudaMalloc(&b.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels));
-            if (dbg->q3 && !b.d_dbg_q3) CU(cudaMalloc(&b.d_dbg_q3, sizeof(float) * 4 * (size_t)b.n_pixels));
-            if (dbg->n_outliers && !b.d_dbg_nout) CU(cudaMalloc(&b.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels));
+            if (dbg->median && !cb.d_dbg_median) CU(cudaMalloc(&cb.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (dbg->q1 && !cb.d_dbg_q1) CU(cudaMalloc(&cb.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (dbg->q3 && !cb.d_dbg_q3) CU(cudaMalloc(&cb.d_dbg_q3, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (dbg->n_outliers && !cb.d_dbg_nout) CU(cudaMalloc(&cb.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels));
             // the median plane drives the other debug stores inside the kernel
-            if (!b.d_dbg_median && (dbg->q1 || dbg->q3)) CU(cudaMalloc(&b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
-            if (b.d_dbg_median) CU(cudaMemsetAsync(b.d_dbg_median, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
-            if (b.d_dbg_q1) CU(cudaMemsetAsync(b.d_dbg_q1, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
-            if (b.d_dbg_q3) CU(cudaMemsetAsync(b.d_dbg_q3, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
-            ab.dbg_median = b.d_dbg_median;
-            ab.dbg_q1 = dbg->q1 ? b.d_dbg_q1 : nullptr;
-            ab.dbg_q3 = dbg->q3 ? b.d_dbg_q3 : nullptr;
-            ab.dbg_nout = dbg->n_outliers ? b.d_dbg_nout : nullptr;
+            if (!cb.d_dbg_median && (dbg->q1 || dbg->q3)) CU(cudaMalloc(&cb.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
+            if (cb.d_dbg_median) CU(cudaMemsetAsync(cb.d_dbg_median, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
+            if (cb.d_dbg_q1) CU(cudaMemsetAsync(cb.d_dbg_q1, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
+            if (cb.d_dbg_q3) CU(cudaMemsetAsync(cb.d_dbg_q3, 0, sizeof(float) * 4 * (size_t)b.n_pixels, s));
+            ab.dbg_median = cb.d_dbg_median;
+            ab.dbg_q1 = dbg->q1 ? cb.d_dbg_q1 : nullptr;
+            ab.dbg_q3 = dbg->q3 ? cb.d_dbg_q3 : nullptr;
+            ab.dbg_nout = dbg->n_outliers ? cb.d_dbg_nout : nullptr;
         }
         const long long n_tasks = b.n_tiles * var.g;
         if (n_tasks >= (1LL << 31)) return fail(CHB_ERR_UNSUPPORTED, "chb_outlier: band too large (%lld tile slices)", n_tasks);
+        if (long_series) {  // histogram tier over every pixel of the band, then the per-frame path
+            ab.hist_all = 1;
+            CU(cudaEventRecord(cb.ev0, s));
+            CU(cudaEventRecord(cb.ev_mid, s));
+            if (st->C == 3) outlier_hist_kernel<3><<<d.sm_count * 8, kWarpsPerCta * 32, 0, s>>>(ab);
+            else outlier_hist_kernel<4><<<d.sm_count * 8, kWarpsPerCta * 32, 0, s>>>(ab);
+            if (st->C == 3) outlier_exact_kernel<3><<<d.sm_count * 4, 256, 0, s>>>(ab);
+            else outlier_exact_kernel<4><<<d.sm_count * 4, 256, 0, s>>>(ab);
+            g_launches += 2;
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(cb.ev1, s));
+            CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, cb.d_qcount + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
+            continue;
+        }
         int occ = 1;
-        const int smem = outlier_smem_bytes(var.wpl, var.g);
+        const int smem = outlier_smem_bytes(var.wpl, var.g, st->C);
         {
             int krc = kernel_config((const void*)kern, d.id, kWarpsPerCta * 32, smem, &occ);
             if (krc) return krc;
         }
         // persistent grid: every resident warp strides over the tile slices, so its exact-path queue fills up
         const int blocks = grid_for(n_tasks * 32, kWarpsPerCta * 32, d.sm_count, std::max(1, occ));
-        CU(cudaEventRecord(b.ev0, s));
+        CU(cudaEventRecord(cb.ev0, s));
         kern<<<blocks, kWarpsPerCta * 32, smem, s>>>(ab);
-        if (!b.ev_mid) CU(cudaEventCreate(&b.ev_mid));
-        CU(cudaEventRecord(b.ev_mid, s));
+        CU(cudaEventRecord(cb.ev_mid, s));
         // iterative tier: long whole-stack series with relative thresholds (six ranks per band) use the histogram kernel -- one
         // shared-memory atomic per sample instead of the solver's repeated passes (measured on 1000 x UHD: 1.0 ms against
         // 1.7 ms; with absolute thresholds, two ranks, the solver's 0.6 ms wins). CHB_HIST=0 / 1 forces the choice (tests).
-        compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(b.d_hflags, b.n_tiles, b.d_hqueue, b.d_qcount + 1);
+        compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(cb.d_hflags, b.n_tiles, cb.d_hqueue, cb.d_qcount + 1);
         bool use_hist = kmode == 2 && n >= 256;
         if (g_tune.hist.load() >= 0) use_hist = kmode != 0 && n >= 256 && g_tune.hist.load() != 0;
         // the two tier kernels are programmatic dependent launches: their CTAs become resident while the previous kernel's
@@ -927,71 +1024,76 @@ static int outlier_impl(chb_stack* st, const chb_outlier_params* prm, const int3
         CU(launch_dep(st->C == 3 ? outlier_exact_kernel<3> : outlier_exact_kernel<4>, d.sm_count * 4, 256, 0));
         g_launches += 4;
         CU(cudaGetLastError());
-        CU(cudaEventRecord(b.ev1, s));
-        CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_qcount + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(cb.ev1, s));
+        CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, cb.d_qcount + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
     }
     (void)P;
-    if (!tables_cached) st->last_tables = blob;
+    if (!tables_cached) cs.last_tables = blob;
+    cs.last_kind = 1;
     if (enqueue_only && tables_cached) {  // nothing on the host is reused before the launch has read it: return without waiting
-        st->last_has_mask = want_mask;
+        cs.last_has_mask = want_mask;
         return CHB_OK;
     }
-    return collect_outlier(st, dbg, kernel_ms, want_mask);
+    return collect_outlier(st, slot, dbg, kernel_ms, want_mask);
 }
 
 // Waits for the launches of every band and gathers timing, counters and debug planes.
-static int collect_outlier(chb_stack* st, const chb_debug_planes* dbg, float* kernel_ms, bool want_mask) {
+static int collect_outlier(chb_stack* st, int slot, const chb_debug_planes* dbg, float* kernel_ms, bool want_mask) {
+    CallSlot& cs = st->slots[slot];
     float ms_max = 0.0f, main_max = 0.0f;
     uint64_t warnings = 0, slow = 0, hard = 0;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
+        CallBuf& cb = b.call[slot];
         CU(cudaSetDevice(d.id));
-        CU(cudaStreamSynchronize(d.compute));
+        CU(cudaStreamSynchronize(call_stream(d, cb, slot)));
         float ms = 0.0f;
-        CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
+        CU(cudaEventElapsedTime(&ms, cb.ev0, cb.ev1));
         ms_max = std::max(ms_max, ms);
-        if (b.ev_mid) {
+        {
             float mm = 0.0f;
-            if (cudaEventElapsedTime(&mm, b.ev0, b.ev_mid) == cudaSuccess) main_max = std::max(main_max, mm);
+            if (cudaEventElapsedTime(&mm, cb.ev0, cb.ev_mid) == cudaSuccess) main_max = std::max(main_max, mm);
             else cudaGetLastError();
         }
-        warnings += st->h_counters[4 * b.dev_slot];
-        slow += st->h_counters[4 * b.dev_slot + 1];
-        hard += st->h_counters[4 * b.dev_slot + 2];
+        warnings += cs.h_counters[4 * b.dev_slot];
+        slow += cs.h_counters[4 * b.dev_slot + 1];
+        hard += cs.h_counters[4 * b.dev_slot + 2];
         if (dbg) {
             const size_t off = (size_t)b.row0 * st->W;
-            if (dbg->median) CU(cudaMemcpy(dbg->median + off * 4, b.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
-            if (dbg->q1) CU(cudaMemcpy(dbg->q1 + off * 4, b.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
-            if (dbg->q3) CU(cudaMemcpy(dbg->q3 + off * 4, b.d_dbg_q3, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
-            if (dbg->n_outliers) CU(cudaMemcpy(dbg->n_outliers + off, b.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+            if (dbg->median) CU(cudaMemcpy(dbg->median + off * 4, cb.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+            if (dbg->q1) CU(cudaMemcpy(dbg->q1 + off * 4, cb.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+            if (dbg->q3) CU(cudaMemcpy(dbg->q3 + off * 4, cb.d_dbg_q3, sizeof(float) * 4 * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
+            if (dbg->n_outliers) CU(cudaMemcpy(dbg->n_outliers + off, cb.d_dbg_nout, sizeof(int) * (size_t)b.n_pixels, cudaMemcpyDeviceToHost));
         }
     }
     if (kernel_ms) *kernel_ms = ms_max;
-    st->last_has_mask = want_mask;
-    st->last_warnings = warnings;
+    cs.last_has_mask = want_mask;
+    cs.last_warnings = warnings;
     g_last_slow = slow;
     g_last_hard = hard;
     g_last_main_ms = main_max;
     return CHB_OK;
 }
 
-static int fetch_impl(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
+static int fetch_impl(chb_stack* st, int slot, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
+    CallSlot& cs = st->slots[slot];
+    if (cs.last_kind != 1) return fail(CHB_ERR_STATE, "chb_fetch_last: %s", cs.last_kind == 2 ? "the last call was a video run (its planes went to the caller's buffers)" : "no call has run on this stack yet");
+    if (out_mask && !cs.last_has_mask) return fail(CHB_ERR_STATE, "chb_fetch_last: the last call did not produce a mask");
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
+        CallBuf& cb = b.call[slot];
+        cudaStream_t s = call_stream(d, cb, slot);
         CU(cudaSetDevice(d.id));
         const size_t off = (size_t)b.row0 * st->W * st->C;
-        if (out_image) CU(cudaMemcpyAsync(out_image + off, b.d_out, b.frame_bytes, cudaMemcpyDeviceToHost, d.compute));
-        if (out_mask) {
-            if (!st->last_has_mask) return fail(CHB_ERR_STATE, "chb_fetch_last: the last call did not produce a mask");
-            CU(cudaMemcpyAsync(out_mask + off, b.d_mask, b.frame_bytes, cudaMemcpyDeviceToHost, d.compute));
-        }
+        if (out_image) CU(cudaMemcpyAsync(out_image + off, cb.d_out, b.frame_bytes, cudaMemcpyDeviceToHost, s));
+        if (out_mask) CU(cudaMemcpyAsync(out_mask + off, cb.d_mask, b.frame_bytes, cudaMemcpyDeviceToHost, s));
     }
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
-        CU(cudaStreamSynchronize(d.compute));
+        CU(cudaStreamSynchronize(call_stream(d, b.call[slot], slot)));
     }
-    if (n_warnings) *n_warnings = st->last_warnings;
+    if (n_warnings) *n_warnings = cs.last_warnings;
     return CHB_OK;
 }
 
@@ -1000,49 +1102,54 @@ extern "C" int chb_outlier_debug(chb_stack* st, const chb_outlier_params* prm, c
     if (!out_image || !st) return fail(CHB_ERR_INVALID, "chb_outlier: null argument");
     int rc = chb_stack_sync(st);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    rc = outlier_impl(st, prm, indices, n_indices, out_mask != nullptr, dbg, nullptr);
+    SlotGuard g(st, false);  // any free call slot: concurrent callers overlap launches, tier kernels and D2H copies
+    rc = ensure_call_slot(st, g.slot);
     if (rc) return rc;
-    return fetch_impl(st, out_image, out_mask, n_warnings);
+    rc = outlier_impl(st, g.slot, prm, indices, n_indices, out_mask != nullptr, dbg, nullptr);
+    if (rc) return rc;
+    return fetch_impl(st, g.slot, out_image, out_mask, n_warnings);
 }
 extern "C" int chb_outlier(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, uint8_t* out_image,
                            uint8_t* out_mask, uint64_t* n_warnings) {
     return chb_outlier_debug(st, prm, indices, n_indices, out_image, out_mask, n_warnings, nullptr);
 }
+// ---- device-side API: defined on "the last call" of the stack, i.e. on call slot 0
 extern "C" int chb_outlier_device(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, int want_mask, float* kernel_ms) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_outlier_device: null stack");
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    return outlier_impl(st, prm, indices, n_indices, want_mask != 0, nullptr, kernel_ms);
+    SlotGuard g(st, true);
+    return outlier_impl(st, 0, prm, indices, n_indices, want_mask != 0, nullptr, kernel_ms);
 }
 extern "C" int chb_outlier_enqueue(chb_stack* st, const chb_outlier_params* prm, const int32_t* indices, int n_indices, int want_mask) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_outlier_enqueue: null stack");
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    return outlier_impl(st, prm, indices, n_indices, want_mask != 0, nullptr, nullptr, true);
+    SlotGuard g(st, true);
+    return outlier_impl(st, 0, prm, indices, n_indices, want_mask != 0, nullptr, nullptr, true);
 }
 extern "C" int chb_stack_wait(chb_stack* st, float* last_kernel_ms, uint64_t* n_warnings) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_stack_wait: null stack");
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    int rc = collect_outlier(st, nullptr, last_kernel_ms, st->last_has_mask);
+    SlotGuard g(st, true);
+    if (st->slots[0].last_kind != 1) return fail(CHB_ERR_STATE, "chb_stack_wait: no single-window call is pending on this stack");
+    int rc = collect_outlier(st, 0, nullptr, last_kernel_ms, st->slots[0].last_has_mask);
     if (rc) return rc;
-    if (n_warnings) *n_warnings = st->last_warnings;
+    if (n_warnings) *n_warnings = st->slots[0].last_warnings;
     return CHB_OK;
 }
 extern "C" int chb_fetch_last_device(chb_stack* st, int dev_slot, void* d_image, void* d_mask) {
     if (!st || !d_image) return fail(CHB_ERR_INVALID, "chb_fetch_last_device: null argument");
     if (dev_slot < 0 || dev_slot >= (int)st->bands.size()) return fail(CHB_ERR_INVALID, "chb_fetch_last_device: bad device slot");
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    if (d_mask && !st->last_has_mask) return fail(CHB_ERR_STATE, "chb_fetch_last_device: the last call did not produce a mask");
+    SlotGuard g(st, true);
+    if (st->slots[0].last_kind != 1) return fail(CHB_ERR_STATE, "chb_fetch_last_device: the last call on this stack was not a single-window call");
+    if (d_mask && !st->slots[0].last_has_mask) return fail(CHB_ERR_STATE, "chb_fetch_last_device: the last call did not produce a mask");
     Band& b = st->bands[dev_slot];
     Dev& d = st->ctx->devs[b.dev_slot];
     CU(cudaSetDevice(d.id));
-    CU(cudaMemcpyAsync(d_image, b.d_out, b.frame_bytes, cudaMemcpyDeviceToDevice, d.compute));
-    if (d_mask) CU(cudaMemcpyAsync(d_mask, b.d_mask, b.frame_bytes, cudaMemcpyDeviceToDevice, d.compute));
+    CU(cudaMemcpyAsync(d_image, b.call[0].d_out, b.frame_bytes, cudaMemcpyDeviceToDevice, d.compute));
+    if (d_mask) CU(cudaMemcpyAsync(d_mask, b.call[0].d_mask, b.frame_bytes, cudaMemcpyDeviceToDevice, d.compute));
     return CHB_OK;
 }
 extern "C" int chb_fetch_last(chb_stack* st, uint8_t* out_image, uint8_t* out_mask, uint64_t* n_warnings) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_fetch_last: null stack");
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    return fetch_impl(st, out_image, out_mask, n_warnings);
+    SlotGuard g(st, true);
+    return fetch_impl(st, 0, out_image, out_mask, n_warnings);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 dispatch (chrono-video)
@@ -1058,6 +1165,19 @@ static VideoKernel video_kernel_for(int nw) {
         case 12: return video_kernel<C, 12>;
         case 14: return video_kernel<C, 14>;
         default: return video_kernel<C, 16>;
+    }
+}
+template <int C>
+static VideoKernel video_direct_kernel_for(int nw) {
+    switch (nw) {
+        case 2: return video_direct_kernel<C, 2>;
+        case 4: return video_direct_kernel<C, 4>;
+        case 6: return video_direct_kernel<C, 6>;
+        case 8: return video_direct_kernel<C, 8>;
+        case 10: return video_direct_kernel<C, 10>;
+        case 12: return video_direct_kernel<C, 12>;
+        case 14: return video_direct_kernel<C, 14>;
+        default: return video_direct_kernel<C, 16>;
     }
 }
 static constexpr int kMaxVideoWindow = 64;
@@ -1119,9 +1239,13 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
     va.mask_b = word_mask(nw - 1);
     va.res_words = (!prm->thr_absolute || prm->background == CHB_BG_AVERAGE) ? 2 : 1;
     const int smem = video_smem_bytes(st->C, va.res_words);
-    VideoKernel kern = st->C == 3 ? video_kernel_for<3>(nw) : video_kernel_for<4>(nw);
-    if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
-    st->last_tables.clear();  // the fade table on the devices no longer belongs to a single-window call
+    // absolute thresholds: every window recomputed from registers (video_direct_kernel); relative: the sliding counts, which also
+    // yield the quartiles (video_kernel). CHB_VIDEO_DIRECT=0 forces the sliding kernel (tests, A/B).
+    const bool direct = prm->thr_absolute && g_tune.video_direct.load() != 0;
+    VideoKernel kern = direct ? (st->C == 3 ? video_direct_kernel_for<3>(nw) : video_direct_kernel_for<4>(nw))
+                              : (st->C == 3 ? video_kernel_for<3>(nw) : video_kernel_for<4>(nw));
+    if (!prm->fade.is_none) memcpy(st->slots[0].h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
+    st->slots[0].last_tables.clear();  // the fade table on the devices no longer belongs to a single-window call
 
     // chunks of whole 16-start blocks; two slots of output planes per band (kernel of chunk k+1 overlaps the D2H of chunk k)
     size_t max_frame_bytes = 0;
@@ -1158,10 +1282,10 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
         }
         cudaStream_t s = d.compute;
         CU(wait_ingest(b, s));
-        if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync(b.d_counters, 0, sizeof(unsigned long long) * 4, s));
+        if (!prm->fade.is_none) CU(cudaMemcpyAsync(b.call[0].d_fade, st->slots[0].h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(b.call[0].d_counters, 0, sizeof(unsigned long long) * 4, s));
         CU(cudaMemsetAsync(b.d_vwarn, 0, sizeof(unsigned long long) * (size_t)n_windows, s));
-        CU(cudaEventRecord(b.ev0, s));
+        CU(cudaEventRecord(b.call[0].ev0, s));
     }
     std::vector<bool> slot_in_flight(2 * st->bands.size(), false);
     for (int k = 0; k < n_chunks; k++) {
@@ -1180,9 +1304,9 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             VideoArgs vb = va;
             vb.o.stack = b.d_stack;
             vb.o.n_pixels = b.n_pixels; vb.o.n_tiles = b.n_tiles;
-            vb.o.fade.values = b.d_fade;
+            vb.o.fade.values = b.call[0].d_fade;
             vb.o.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
-            vb.o.counters = b.d_counters;
+            vb.o.counters = b.call[0].d_counters;
             vb.first_start = s_lo; vb.n_windows = cw;
             vb.blk0 = cb0; vb.n_blocks = cb1 - cb0 + 1;
             vb.out_stride = (long long)b.frame_bytes;
@@ -1226,15 +1350,15 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
-        CU(cudaEventRecord(b.ev1, d.compute));
-        CU(cudaMemcpyAsync(st->h_counters + 4 * b.dev_slot, b.d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, d.compute));
+        CU(cudaEventRecord(b.call[0].ev1, d.compute));
+        CU(cudaMemcpyAsync(st->slots[0].h_counters + 4 * b.dev_slot, b.call[0].d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, d.compute));
         CU(cudaStreamSynchronize(d.compute));
         CU(cudaStreamSynchronize(d.copy));
         float ms = 0.0f;
-        CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
+        CU(cudaEventElapsedTime(&ms, b.call[0].ev0, b.call[0].ev1));
         ms_max = std::max(ms_max, ms);
-        slow += st->h_counters[4 * b.dev_slot + 1];
-        hard += st->h_counters[4 * b.dev_slot + 2];
+        slow += st->slots[0].h_counters[4 * b.dev_slot + 1];
+        hard += st->slots[0].h_counters[4 * b.dev_slot + 2];
         CU(cudaMemcpy(wtmp.data(), b.d_vwarn, sizeof(unsigned long long) * (size_t)n_windows, cudaMemcpyDeviceToHost));
         for (int i = 0; i < n_windows; i++) {
             warn_total += wtmp[i];
@@ -1242,7 +1366,8 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
         }
     }
     if (kernel_ms) *kernel_ms = ms_max;
-    st->last_warnings = warn_total;
+    st->slots[0].last_warnings = warn_total;
+    st->slots[0].last_kind = 2;
     g_last_slow = slow;
     g_last_hard = hard;
     return CHB_OK;
@@ -1253,20 +1378,21 @@ extern "C" int chb_outlier_video(chb_stack* st, const chb_outlier_params* prm, i
     if (!st || !out_images) return fail(CHB_ERR_INVALID, "chb_outlier_video: null argument");
     int rc = chb_stack_sync(st);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(st->call_mu);
+    SlotGuard g(st, true);
     return video_impl(st, prm, first_start, window_len, n_windows, out_images, out_masks, out_masks != nullptr, n_warnings, nullptr);
 }
 extern "C" int chb_outlier_video_device(chb_stack* st, const chb_outlier_params* prm, int first_start, int window_len, int n_windows, int want_mask,
                                         float* kernel_ms) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_outlier_video_device: null stack");
-    std::lock_guard<std::mutex> lk(st->call_mu);
+    SlotGuard g(st, true);
     return video_impl(st, prm, first_start, window_len, n_windows, nullptr, nullptr, want_mask != 0, nullptr, kernel_ms);
 }
 
 // ------------------------------------------------------------------------------------------------ K2 dispatch
-static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, float* kernel_ms) {
+static int simple_impl(chb_stack* st, int slot, const chb_simple_params* prm, const int32_t* indices, int n_indices, float* kernel_ms) {
     if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_simple: null argument");
-    // the caller holds st->call_mu
+    // the caller owns call slot `slot`
+    CallSlot& cs = st->slots[slot];
     Window win;
     // SimpleProcessor accepts any index order in principle (src/simple.rs:142-146), but every caller passes ascending
     // windows (src/main.rs:398-404); the time-sliced stack relies on it.
@@ -1292,7 +1418,7 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
         if (prm->weights[i] == 1.0f) a.use_mask |= 1u << i;
         else if (prm->weights[i] != 0.0f) int_path = false;
     }
-    st->last_tables.clear();  // this call overwrites the shared table buffers
+    cs.last_tables.clear();  // this call overwrites the shared table buffers
     std::vector<uint32_t> masks((size_t)win.n_groups * 4);
     byte_masks(win.frames, win.g0, win.n_groups, masks.data());
     bool all_in = true;
@@ -1305,13 +1431,14 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
             posg[gi] = (int32_t)k;
         }
     }
-    if (!prm->fade.is_none) memcpy(st->h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
-    memcpy(st->h_posg, posg.data(), sizeof(int32_t) * posg.size());
+    if (!prm->fade.is_none) memcpy(cs.h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
+    memcpy(cs.h_posg, posg.data(), sizeof(int32_t) * posg.size());
     std::vector<uint32_t*> tmp_masks;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
-        cudaStream_t s = d.compute;
+        CallBuf& cb = b.call[slot];
+        cudaStream_t s = call_stream(d, cb, slot);
         CU(wait_ingest(b, s));
         SimpleArgs ab = a;
         ab.stack = b.d_stack;
@@ -1319,18 +1446,18 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
         ab.wmask = nullptr;
         if (!all_in) {
             uint32_t* dm = nullptr;
-            if (win.n_groups <= kMaxGroupsTable) dm = b.d_wmask;
+            if (win.n_groups <= kMaxGroupsTable) dm = cb.d_wmask;
             else { CU(cudaMalloc(&dm, sizeof(uint32_t) * masks.size())); tmp_masks.push_back(dm); }
             CU(cudaMemcpyAsync(dm, masks.data(), sizeof(uint32_t) * masks.size(), cudaMemcpyHostToDevice, s));
             ab.wmask = dm;
         }
-        CU(cudaMemcpyAsync(b.d_posg, st->h_posg, sizeof(int32_t) * posg.size(), cudaMemcpyHostToDevice, s));
-        ab.pos_of_group = b.d_posg;
-        if (fade) CU(cudaMemcpyAsync(b.d_fade, st->h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
-        ab.fade.values = b.d_fade;
-        ab.out_image = b.d_out;
+        CU(cudaMemcpyAsync(cb.d_posg, cs.h_posg, sizeof(int32_t) * posg.size(), cudaMemcpyHostToDevice, s));
+        ab.pos_of_group = cb.d_posg;
+        if (fade) CU(cudaMemcpyAsync(cb.d_fade, cs.h_fade, sizeof(float) * (size_t)prm->fade.n_values, cudaMemcpyHostToDevice, s));
+        ab.fade.values = cb.d_fade;
+        ab.out_image = cb.d_out;
         const int blocks = grid_for(b.n_tiles * kTilePixels, 256, d.sm_count, 64);
-        CU(cudaEventRecord(b.ev0, s));
+        CU(cudaEventRecord(cb.ev0, s));
         if (int_path) {
             if (st->C == 3) simple_int_kernel<3><<<blocks, 256, 0, s>>>(ab);
             else simple_int_kernel<4><<<blocks, 256, 0, s>>>(ab);
@@ -1343,21 +1470,23 @@ static int simple_impl(chb_stack* st, const chb_simple_params* prm, const int32_
         }
         g_launches++;
         CU(cudaGetLastError());
-        CU(cudaEventRecord(b.ev1, s));
+        CU(cudaEventRecord(cb.ev1, s));
     }
     float ms_max = 0.0f;
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
+        CallBuf& cb = b.call[slot];
         CU(cudaSetDevice(d.id));
-        CU(cudaStreamSynchronize(d.compute));
+        CU(cudaStreamSynchronize(call_stream(d, cb, slot)));
         float ms = 0.0f;
-        CU(cudaEventElapsedTime(&ms, b.ev0, b.ev1));
+        CU(cudaEventElapsedTime(&ms, cb.ev0, cb.ev1));
         ms_max = std::max(ms_max, ms);
     }
     for (uint32_t* p : tmp_masks) cudaFree(p);
     if (kernel_ms) *kernel_ms = ms_max;
-    st->last_has_mask = false;
-    st->last_warnings = 0;
+    cs.last_kind = 1;
+    cs.last_has_mask = false;
+    cs.last_warnings = 0;
     return CHB_OK;
 }
 
@@ -1365,15 +1494,17 @@ extern "C" int chb_simple(chb_stack* st, const chb_simple_params* prm, const int
     if (!out_image || !st) return fail(CHB_ERR_INVALID, "chb_simple: null argument");
     int rc = chb_stack_sync(st);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    rc = simple_impl(st, prm, indices, n_indices, nullptr);
+    SlotGuard g(st, false);
+    rc = ensure_call_slot(st, g.slot);
     if (rc) return rc;
-    return fetch_impl(st, out_image, nullptr, nullptr);
+    rc = simple_impl(st, g.slot, prm, indices, n_indices, nullptr);
+    if (rc) return rc;
+    return fetch_impl(st, g.slot, out_image, nullptr, nullptr);
 }
 extern "C" int chb_simple_device(chb_stack* st, const chb_simple_params* prm, const int32_t* indices, int n_indices, float* kernel_ms) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_simple_device: null stack");
-    std::lock_guard<std::mutex> lk(st->call_mu);
-    return simple_impl(st, prm, indices, n_indices, kernel_ms);
+    SlotGuard g(st, true);
+    return simple_impl(st, 0, prm, indices, n_indices, kernel_ms);
 }
 
 // ------------------------------------------------------------------------------------------------ host arithmetic

@@ -124,6 +124,8 @@ struct OutlierArgs {
     int contig_f0;           // >= 0: the window is the contiguous frame range starting here (position s = frame contig_f0 + s)
     int mask_path;           // 1: integer distance, contiguous window of at most kMaskGroups groups: dense_masks_int + finish_masks
     int inline_min;          // > 0 (G == 1 kernels): a tile with at least this many uncertified pixels is finished inside the streaming kernel
+    int hard_inline_min;     // > 0 (G == 1 kernels): same for a warp-full of the iterative tier, finished inside outlier_hard_kernel
+    int hist_all;            // 1: outlier_hist_kernel takes every pixel of the band (series beyond the register-resident variants), not a queue
     unsigned long long seed, pixel_offset;
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
@@ -180,7 +182,8 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
     const bool rel = !a.absolute;
     const int nt = rel ? 6 : 2;  // targets in processing order: m1, m2, q1a, q1b, q3a, q3b
     // per-lane state. mode 0: jump at g; 1: walking in direction d from edge b with fc = F(b); 2: bisecting [b, hi].
-    int t = 0, kp = a.rk[2] + pad, mode = 0, steps = 0, d = 1, b = 0, hi = 255, cnth = cap;
+    // mode 2 keeps the counts at both ends of its bracket: cntl = #{x <= b - 1}, cnth = #{x <= hi}
+    int t = 0, kp = a.rk[2] + pad, mode = 0, steps = 0, d = 1, b = 0, hi = 255, cnth = cap, cntl = 0;
     uint32_t fc = 0;
     int g = __float2int_rn((float)ssum * inv_cnt);  // mean as the first guess for the median
     g = g < 0 ? 0 : (g > 254 ? 254 : g);
@@ -195,7 +198,14 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
         int e2w = b + 2 * d;
         const bool e2_out = (e2w < 0) | (e2w > 255);
         e2w = e2w < 0 ? 0 : (e2w > 255 ? 255 : e2w);
-        const int mid = (b + hi) >> 1;
+        // mode 2: the bracket is cut where a uniform spread of its cnth - cntl samples over its values puts the rank (iid bytes:
+        // one or two steps instead of log2(width)); every third cut is a plain bisection, which bounds the worst case
+        int mid = (b + hi) >> 1;
+        if (mode == 2 && steps % 3 != 2) {
+            const float est = __fdividef((float)(kp + 1 - cntl) * (float)(hi - b + 1), (float)(cnth - cntl));
+            const int ei = b - 1 + __float2int_rn(est);
+            mid = ei < b ? b : (ei > hi - 1 ? hi - 1 : ei);
+        }
         int e1 = m0 ? g : (m1 ? b + d : mid);
         int e2 = m0 ? g + 1 : (m1 ? e2w : mid + 1);
         e1 = act ? e1 : 0;
@@ -219,7 +229,7 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
         // ---- mode 2: bisect
         const bool ge = nj >= kp + 1;
         // ---- new state
-        int nb, nhi = hi, ncnth = cnth, nmode = mode, nsteps = steps, nd = d;
+        int nb, nhi = hi, ncnth = cnth, ncntl = cntl, nmode = mode, nsteps = steps, nd = d;
         uint32_t nfc = fc;
         bool res;
         int v, cv;
@@ -233,6 +243,15 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
             nmode = 1; nsteps = 0;
             res = up0 ? (nb == 255) : (nb == 0);
             v = nb; cv = ncnth;
+            // second jump of the first rank (marked by steps == 7; hi / cntl, unused outside mode 2, carry the first jump's value
+            // and count): when the two jumps straddle the answer they ARE a bracket with both counts known -- iid bytes, whose
+            // side mean lies far beyond the answer, go on by interpolation inside it instead of walking back and bisecting
+            if (!res && t == 0 && steps == 7) {
+                const int g0 = hi, n0 = cntl;
+                if (g > g0 && !up0) { nmode = 2; nb = g0 + 1; nhi = g; ncntl = n0; ncnth = nj; }
+                else if (g < g0 && up0) { nmode = 2; nb = g + 1; nhi = g0; ncntl = nj; ncnth = n0; }
+                if (nmode == 2) { res = nb >= nhi; v = nhi; cv = ncnth; }
+            }
             if (!res && t == 0 && !rejumped) {
                 // A pixel reaches this solver because its mean is no guess for its median: an object rests on it for a good part
                 // of the series. The samples on the median's side of g are mostly background, and F(g), F(g+1) and the sum give
@@ -249,8 +268,20 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
                     const int B = (((int)f1 - (int)ssum + cap * g) >> 1) - pad * g;
                     g2 = g - __float2int_rn(__fdividef((float)B, (float)max(below, 1)));
                 }
+                // ... unless the samples on that side spread far beyond the answer (iid bytes, wide unimodal noise: the side mean is
+                // tens of values away while only a few samples separate g from the rank). Then the number of samples still to be
+                // passed over the density the mean absolute deviation implies -- n / (3.5 MAD) per value, for uniform and Gaussian
+                // spreads alike -- is the better estimate; it is taken when it is less than a quarter of the way to the side mean
+                // (two clusters give a ratio of 7 (1 - p)(1/2 - p) for an object share p: below 1/4 only for p > 0.43).
+                {
+                    const int far = up0 ? kp + 1 - nj : nj - kp;
+                    const float madn = ((float)(up0 ? f2 : f1) - (float)pad * (float)(up0 ? g + 1 : g)) * a.inv_n_sub;
+                    const int step = __float2int_rn((float)far * 3.5f * madn * a.inv_n_sub);
+                    const int dside = up0 ? g2 - g : g - g2;
+                    if (4 * step < dside) g2 = up0 ? g + step : g - step;
+                }
                 g2 = g2 < 0 ? 0 : (g2 > 254 ? 254 : g2);
-                if (g2 > g + 3 || g2 < g - 3) { g = g2; nmode = 0; }  // close guesses just walk
+                if (g2 > g + 3 || g2 < g - 3) { nhi = g; ncntl = nj; g = g2; nmode = 0; nsteps = 7; }  // close guesses just walk
             }
         } else if (m1) {
             res = rb | rb1;
@@ -265,9 +296,11 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
             if (!res) {
                 if (u ? (nb >= 255) : (nb <= 0)) {  // walked into the end of the byte range
                     res = true; v = u ? 255 : 0; cv = ncnth; has_next = false;
-                } else if (nsteps >= 3) {  // far from the guess: bisect what is left
+                } else if (nsteps >= 3) {  // far from the guess: bracket what is left
                     nmode = 2;
+                    nsteps = 0;
                     nhi = u ? 255 : nb;
+                    ncntl = u ? n2 : pad;  // going down the bracket starts at 0, where the pad zeros sit
                     nb = u ? nb : 0;
                     ncnth = u ? cap : ncnth;
                 }
@@ -275,12 +308,14 @@ __device__ __forceinline__ void band_solve(const uint32_t (&x)[W4], uint32_t ssu
         } else {
             nhi = ge ? e1 : hi;
             ncnth = ge ? nj : cnth;
+            ncntl = ge ? cntl : nj;
             nb = ge ? b : e1 + 1;
+            nsteps = steps + 1;
             res = nb >= nhi;
             v = nhi; cv = ncnth;
         }
         if (act) {
-            b = nb; hi = nhi; cnth = ncnth; mode = nmode; steps = nsteps; d = nd; fc = nfc;
+            b = nb; hi = nhi; cnth = ncnth; cntl = ncntl; mode = nmode; steps = nsteps; d = nd; fc = nfc;
             // ---- resolved: store, then set up the next rank(s) of this lane
             if (res) {
 #pragma unroll 1
@@ -642,9 +677,13 @@ __device__ __forceinline__ void dense_pass_int(const OutlierArgs& a, const uint8
 // be finished by walking set bits (finish_masks) -- no second pass over the frames, whatever the policy. Two groups are
 // kept in registers, the reload of a buffer is issued as soon as the buffer has been evaluated.
 constexpr int kMaskGroups = 16;  // 256 frames: the G == 1 variants of K1 hold at most 13 groups
+__host__ __device__ constexpr int dense_ring_depth(int C) { return C == 3 ? 3 : 2; }  // frame groups of a pixel in flight (one being evaluated)
+constexpr uint32_t kRingStride = 256 * 16;  // every kernel that runs the dense pass has 256 threads: one 16-byte unit each per row
 struct MaskSlots {
     uint32_t base;    // shared-memory address of this thread's first halfword
     uint32_t stride;  // bytes between the halfwords of consecutive groups
+    // the dense pass's ring of frame groups: row (slot * C + band) holds one 16-byte unit per thread (filled by cp.async)
+    uint32_t ring;         // shared-memory address of this thread's unit in row 0; rows are kRingStride bytes apart
     __device__ __forceinline__ void put(int gi, uint32_t m) const { asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + gi * stride), "h"((unsigned short)m) : "memory"); }
     __device__ __forceinline__ uint32_t get(int gi) const {
         unsigned short v;
@@ -696,70 +735,101 @@ __device__ __forceinline__ uint32_t int_dist_frame(const IntMedians& m, uint32_t
 }
 template <int C>
 __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint8_t* colbase, long long band_stride, int f0, int n,
-                                                const IntMedians& im, const MaskSlots& ms, int& k_out, uint32_t& maxkey_out) {
+                                                const IntMedians& im, const MaskSlots ms, int& k_out, uint32_t& maxkey_out) {
     const uint32_t lof = im.lof, negd = im.negd;
     const int c0 = im.c0;
-    bool use[4];
+    bool all_use = true;
 #pragma unroll
-    for (int c = 0; c < 4; c++) use[c] = (c < C) && (a.w[c] != 0.0f);
+    for (int c = 0; c < C; c++) all_use = all_use && (a.w[c] != 0.0f);
     const int gA = f0 >> 4, gB = (f0 + n - 1) >> 4;
     int k = 0;
     uint32_t maxkey = 0;
-    auto load = [&](uint4 (&u)[4], int g) {
+    // one pointer per band and one running offset (in 16-byte units: the next frame group of the tile is kTilePixels units on)
+    const uint4* pb[C];
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-            u[c] = use[c] ? __ldg(reinterpret_cast<const uint4*>(colbase + c * band_stride + (long long)g * (kTilePixels * kUnitBytes))) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < C; c++) pb[c] = reinterpret_cast<const uint4*>(colbase + c * band_stride) + (long long)gA * kTilePixels;
+    // The pixel's units travel global -> shared memory by cp.async (LDGSTS: no register is tied up while a load is in flight)
+    // into a ring of D frame groups per thread, D - 1 of them ahead of the group being evaluated: the L2 latency of a group is
+    // covered by the evaluation of D - 1 others, where a register double buffer covered one and paid twelve moves per group.
+    // Every thread reads back only the 16 bytes it copied itself, so cp.async.wait_group is all the synchronisation needed.
+    constexpr int D = dense_ring_depth(C);
+    constexpr uint32_t kSlotBytes = C * kRingStride;
+    const int last_off = (gB - gA) * kTilePixels;
+    auto issue = [&](uint32_t saddr, int off) {  // (a group beyond the window's last one re-reads the last one: no branch, never used)
+        const int o = min(off, last_off);
+#pragma unroll
+        for (int c = 0; c < C; c++) cp_async16(saddr + c * kRingStride, pb[c] + o);
     };
-    auto group = [&](const uint4 (&u)[4], int g) {
+    // ONE copy of the 16-frame body in the instruction stream (the streaming kernel's warps interleave this loop with the band
+    // code: the footprint decides whether both stay in the instruction cache -- a second copy of the body, tried as a register
+    // ping-pong, cost 20 % through instruction-fetch stalls). Groups that are only partly inside the window (the first and the
+    // last one) run the same body: their bytes outside the window are replaced by floor(median), which gives such a frame the
+    // smallest value dm can take (-t < 0 since the host only takes this path for thr4 >= 5): never an outlier, and it can only
+    // hold the group's maximum when no frame of the pixel is an outlier, in which case the maximum is not used.
+#pragma unroll
+    for (int sl = 0; sl < D - 1; sl++) {
+        issue(ms.ring + sl * kSlotBytes, sl * kTilePixels);
+        cp_async_commit();
+    }
+    const uint32_t ring_end = ms.ring + D * kSlotBytes;
+    uint32_t rd = ms.ring, wr = ms.ring + (D - 1) * kSlotBytes;
+    int off = (D - 1) * kTilePixels;
+#pragma unroll 1
+    for (int g = gA; g <= gB; g++, off += kTilePixels) {
+        issue(wr, off);
+        cp_async_commit();
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+        uint4 cur[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) cur[c] = lds128(rd + c * kRingStride);
+        rd += kSlotBytes; rd = rd == ring_end ? ms.ring : rd;
+        wr += kSlotBytes; wr = wr == ring_end ? ms.ring : wr;
         const int sg = 16 * g - f0;  // window position of the group's frame 0
-        const bool full = (sg >= 0) && (sg + 16 <= n);
+        if (!all_use) {  // (uniform, rare) a band of weight 0 must read as zero: its bytes of lof / negd are zero as well
+#pragma unroll
+            for (int c = 0; c < C; c++)
+                if (a.w[c] == 0.0f) cur[c] = make_uint4(0, 0, 0, 0);
+        }
+        if (sg < 0 || sg + 16 > n) {  // (uniform) partial group
+            const int lo_j = sg < 0 ? -sg : 0, hi_j = (n - sg < 16) ? n - sg : 16;  // valid frames j in [lo_j, hi_j)
+            const uint32_t valid = ((1u << hi_j) - 1u) & ~((1u << lo_j) - 1u);
+            uint32_t vm[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) vm[q] = ((((valid >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;  // bit kk -> byte kk
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const uint32_t lo4 = rep4((int)((lof >> (8 * c)) & 0xffu));
+                cur[c].x = (cur[c].x & vm[0]) | (lo4 & ~vm[0]);
+                cur[c].y = (cur[c].y & vm[1]) | (lo4 & ~vm[1]);
+                cur[c].z = (cur[c].z & vm[2]) | (lo4 & ~vm[2]);
+                cur[c].w = (cur[c].w & vm[3]) | (lo4 & ~vm[3]);
+            }
+        }
         uint32_t om16 = 0;
         int gkey = INT_MIN;  // max over the group's frames of 16 * (q - t) + (15 - j)
-        auto body = [&](auto full_tag) {
-            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                uint32_t xw[4];
+        for (int q = 0; q < 4; q++) {
+            uint32_t xw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int c = 0; c < 4; c++) xw[c] = q == 0 ? u[c].x : (q == 1 ? u[c].y : (q == 2 ? u[c].z : u[c].w));
-                const uint32_t t0 = __byte_perm(xw[0], xw[1], 0x5140), t1 = __byte_perm(xw[0], xw[1], 0x7362);
-                const uint32_t t2 = __byte_perm(xw[2], xw[3], 0x5140), t3 = __byte_perm(xw[2], xw[3], 0x7362);
-                const uint32_t pf[4] = {__byte_perm(t0, t2, 0x5410), __byte_perm(t0, t2, 0x7632), __byte_perm(t1, t3, 0x5410), __byte_perm(t1, t3, 0x7632)};
+            for (int c = 0; c < C; c++) xw[c] = q == 0 ? cur[c].x : (q == 1 ? cur[c].y : (q == 2 ? cur[c].z : cur[c].w));
+            const uint32_t t0 = __byte_perm(xw[0], xw[1], 0x5140), t1 = __byte_perm(xw[0], xw[1], 0x7362);
+            const uint32_t t2 = __byte_perm(xw[2], xw[3], 0x5140), t3 = __byte_perm(xw[2], xw[3], 0x7362);
+            const uint32_t pfw[4] = {__byte_perm(t0, t2, 0x5410), __byte_perm(t0, t2, 0x7632), __byte_perm(t1, t3, 0x5410), __byte_perm(t1, t3, 0x7632)};
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                    const int j = 4 * q + kk;
-                    const uint32_t L = absdiff4(pf[kk], lof);
-                    // dm = q - t with 4 dist_sq = 4 q + k2 (see IntMedians): negative <=> not an outlier
-                    const int dm = dp4a_us(pf[kk], negd, (int)__dp4a(L, L, (uint32_t)c0));
-                    if (FULL) {
-                        om16 = __funnelshift_l((uint32_t)dm, om16, 1);  // collects the NON-outlier bits, frame j at bit 15 - j
-                        gkey = max(gkey, dm * 16 + (15 - j));
-                    } else if (sg + j >= 0 && sg + j < n) {  // uniform: first / last group of a window
-                        om16 |= dm >= 0 ? (1u << j) : 0u;
-                        gkey = max(gkey, dm * 16 + (15 - j));
-                    }
-                }
+            for (int kk = 0; kk < 4; kk++) {
+                const int j = 4 * q + kk;
+                const uint32_t L = absdiff4(pfw[kk], lof);
+                // dm = q - t with 4 dist_sq = 4 q + k2 (see IntMedians): negative <=> not an outlier
+                const int dm = dp4a_us(pfw[kk], negd, (int)__dp4a(L, L, (uint32_t)c0));
+                om16 = __funnelshift_l((uint32_t)dm, om16, 1);  // collects the NON-outlier bits, frame j at bit 15 - j
+                gkey = max(gkey, dm * 16 + (15 - j));
             }
-            if (FULL) om16 = (~__brev(om16)) >> 16;
-        };
-        if (full) body(std::true_type{});
-        else body(std::false_type{});
+        }
+        om16 = (~__brev(om16)) >> 16;
         ms.put(g - gA, om16);
         k += __popc(om16);
         const int s = sg + 15 - (gkey & 15);
         maxkey = max(maxkey, ((uint32_t)(4 * ((gkey >> 4) + im.t) + im.k2) << 12) | (uint32_t)(4095 - s));
-    };
-    // one copy of the group body in the instruction stream (the streaming kernel's warps interleave this loop with the band
-    // code: the footprint decides whether both stay in the instruction cache): the next group's loads are issued into a
-    // second register set before the current group is evaluated, then moved over
-    uint4 cur[4], nxt[4];
-    load(cur, gA);
-#pragma unroll 1
-    for (int g = gA; g <= gB; g++) {
-        if (g < gB) load(nxt, g + 1);
-        group(cur, g);
-#pragma unroll
-        for (int c = 0; c < 4; c++) cur[c] = nxt[c];
     }
     k_out = k;
     maxkey_out = maxkey;
@@ -769,7 +839,7 @@ __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint
 // set bits are the outlier list in frame order. Returns the mask byte; `pixel` receives the composite.
 template <int C>
 __device__ __forceinline__ uint8_t finish_masks(const OutlierArgs& a, const uint8_t* colbase, long long band_stride, unsigned long long pixel_id,
-                                                const float (&median)[4], const uint32_t (&band_sum)[4], const IntMedians& im, const MaskSlots& ms,
+                                                const float (&median)[4], const uint32_t (&band_sum)[4], const IntMedians& im, const MaskSlots ms,
                                                 int f0, int n, int frame_offset, int k, uint32_t maxkey, uint8_t (&pixel)[4], int& warn) {
     const int gA = f0 >> 4, n_g = ((f0 + n - 1) >> 4) - gA + 1;
     const int bit0 = f0 & 15;  // window position s sits at bit (s + bit0) & 15 of group (s + bit0) >> 4
@@ -952,7 +1022,7 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
             first_non = s;
         }
     };
-    if (DENSE && a.int_dist && contig_f0 >= 0) {
+    if (DENSE && a.int_dist && contig_f0 >= 0 && n <= 4096) {  // (the pass packs window positions into 12 bits)
         // every frame classified by the branch-free integer pass; the per-policy values are read off its summary
         DensePass dp;
         const uint8_t* colbase = src.tile + (long long)src.p * kUnitBytes;
@@ -1290,10 +1360,13 @@ struct QueueEntry {
 };
 constexpr int kBarBytes = 128;
 constexpr int kAccBytes = kWarpsPerCta * 32 * 12 * 4;
+static_assert(kWarpsPerCta * 32 * 16 == kRingStride, "the dense pass's ring is laid out for 256 threads");
 constexpr int kMaskBytes = kWarpsPerCta * 32 * kMaskGroups * 2;  // per-thread outlier masks of the in-kernel dense pass
 // dynamic shared memory of one CTA: one mbarrier per warp, per-thread result slots, one staged pixel-band per warp (G == 1: the tile's contiguous slab; G > 1: every lane's own units, [slot][lane])
-__host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g) {
-    return kBarBytes + kAccBytes + kWarpsPerCta * wpl * 512 + kMaskBytes;  // g == 1: one slab per warp; g > 1: wpl units per lane; then the mask slots
+__host__ __device__ constexpr int dense_ring_bytes(int C, int threads) { return dense_ring_depth(C) * C * threads * 16; }
+__host__ __device__ constexpr int outlier_smem_bytes(int wpl, int g, int C) {
+    // g == 1: one slab per warp; g > 1: wpl units per lane; then the mask slots and (lane = pixel kernels only) the dense pass's ring
+    return kBarBytes + kAccBytes + kWarpsPerCta * wpl * 512 + kMaskBytes + (g == 1 ? dense_ring_bytes(C, kWarpsPerCta * 32) : 0);
 }
 
 template <int C>
@@ -1310,7 +1383,7 @@ __device__ __forceinline__ void store_pixel(const OutlierArgs& a, long long pix,
 // `active` run along and their results are discarded. Returns the ballot of active lanes with an all-outlier warning.
 template <int C>
 __device__ __forceinline__ unsigned dense_pixels(const OutlierArgs& a, const uint8_t* colbase, long long pix, bool active, const float (&median)[4],
-                                                 const uint32_t (&band_sum)[4], const MaskSlots& ms) {
+                                                 const uint32_t (&band_sum)[4], const MaskSlots ms) {
     const long long bstride = (long long)a.NG * kTilePixels * kUnitBytes;
     const IntMedians im = make_int_medians<C>(a, median);
     int k = 0, warn = 0;
@@ -1327,7 +1400,7 @@ __device__ __forceinline__ unsigned dense_pixels(const OutlierArgs& a, const uin
 }
 
 template <int C>
-__device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry* slot, bool in_range, int lane, const MaskSlots& ms) {
+__device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry* slot, bool in_range, int lane, const MaskSlots ms) {
     long long pix = in_range ? slot->pix : -1;
     const bool active = pix >= 0;
     const unsigned act = __ballot_sync(0xffffffffu, active);
@@ -1562,7 +1635,7 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
 
 // Hard pixels, 32/G at a time: each pixel group reloads its own bands (L2) and runs the iterative solver.
 template <int C, int WPL, int G, int MODE>
-__device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase, int count, int lane, int cap, int pad, uint32_t acc_slot, const MaskSlots& ms) {
+__device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase, int count, int lane, int cap, int pad, uint32_t acc_slot, const MaskSlots ms) {
     const long long* hq = a.ghq + hbase;
     constexpr int W4 = 4 * WPL;
     constexpr long long kSlotStride = (long long)G * kTilePixels * kUnitBytes;
@@ -1587,13 +1660,14 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase
         }
         process_band<C, WPL, G, MODE, false>(a, A, c, j, pix, active && j == 0, cap, pad, acc);
     }
-    // a warp-full of mostly uncertified pixels (iid bytes, heavy noise) is classified frame by frame right here instead of going
-    // through the exact-path queue; its queue slots are marked empty
+    // the uncertified pixels of the warp-full are classified frame by frame right here, while their units are hot in L1 / L2,
+    // instead of going through the exact-path queue (their queue slots are marked empty): a pixel whose median needed the solver
+    // almost always holds an outlier, and the last launch of the call is left with the streaming kernel's own few pixels
     bool finished_here = false;
-    if (G == 1 && MODE != 2 && a.inline_min > 0) {
+    if (G == 1 && MODE != 2 && a.hard_inline_min > 0) {
         const bool dirty = active && !(acc.bound * 1.0001f < a.thr_sq);
         const unsigned db = __ballot_sync(0xffffffffu, dirty);
-        if (__popc(db) >= a.inline_min) {
+        if (__popc(db) >= a.hard_inline_min) {
             float median[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             uint32_t sum[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -1613,7 +1687,7 @@ __device__ __noinline__ void drain_hard(const OutlierArgs& a, unsigned int hbase
 
 // One tile finished inside the streaming kernel: lane = pixel of the tile, medians and sums from the thread's result slots.
 template <int C>
-__device__ __noinline__ void inline_dense_tile(const OutlierArgs& a, int tile, int lane, long long pix, bool dirty, const PixelAcc& acc, const MaskSlots& ms) {
+__device__ __noinline__ void inline_dense_tile(const OutlierArgs& a, int tile, int lane, long long pix, bool dirty, const PixelAcc& acc, const MaskSlots ms) {
     float median[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     uint32_t sum[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -1647,7 +1721,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_MINB) outlier_kernel(co
     uint8_t* const stage = smem_raw + kBarBytes + kAccBytes + warp_in_cta * (WPL * 512);
     const uint32_t stage_lane = smem_u32(stage) + j * kRowBytes + pl * 16;  // this lane's 16 bytes of row (slot * G + j)
     const int staged_groups = a.n_groups < WPL * G ? a.n_groups : WPL * G;
-    const MaskSlots mask_slots{smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512)) + threadIdx.x * 2, kWarpsPerCta * 32u * 2u};
+    const MaskSlots mask_slots{smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512)) + threadIdx.x * 2, kWarpsPerCta * 32u * 2u,
+                               smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512) + kMaskBytes) + threadIdx.x * 16};
     uint32_t parity = 0;
     if (kStage) {
         if (lane == 0) mbar_init(bar, 1);
@@ -1778,7 +1853,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard
     const int lane = threadIdx.x & 31;
     const int cap = 4 * WPL * 4 * G, pad = cap - a.n_sub;
     const uint32_t acc_slot = smem_u32(smem_raw + kBarBytes) + threadIdx.x * 4;
-    const MaskSlots ms{smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512)) + threadIdx.x * 2, kWarpsPerCta * 32u * 2u};
+    const MaskSlots ms{smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512)) + threadIdx.x * 2, kWarpsPerCta * 32u * 2u,
+                       smem_u32(smem_raw + kBarBytes + kAccBytes + kWarpsPerCta * (WPL * 512) + kMaskBytes) + threadIdx.x * 16};
     const unsigned int total = a.ghq_count[0];
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PPW; base < total; base += n_warps * PPW)
@@ -1798,11 +1874,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
     uint32_t* const hist = hist_all[warp_in_cta];
     for (int b = lane; b < 256; b += 32) hist[b] = 0;
     __syncwarp();
-    const unsigned int total = a.ghq_count[0];
+    const unsigned int total = a.hist_all ? (unsigned int)a.n_pixels : a.ghq_count[0];
+    if (a.hist_all && blockIdx.x == 0 && threadIdx.x == 0) a.ghq_count[0] = total;  // the per-frame path finds every slot of its queue mirrored
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool rel = !a.absolute;
     for (unsigned int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < total; idx += n_warps) {
-        const long long pix = a.ghq[idx];
+        const long long pix = a.hist_all ? (long long)idx : a.ghq[idx];
         const long long tile = pix >> 5;
         const int p = (int)(pix & 31);
         PixelAcc acc;
@@ -1874,19 +1951,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) outlier_hist_kernel(const _
             const float med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
             const int center = (mlo + mhi) >> 1;
             const float halfw = med - (float)center;
-            float iqi = 0.0f;
+            float iqi = 0.0f, q1 = 0.0f, q3 = 0.0f;
             if (rel) {  // quartiles (src/chrono.rs:559-579) and inverse IQR (:246-252)
                 const int q1a = stat(a.rk[0]), q3a = stat(a.rk[4]);
                 const int q1b = (a.rk[0] == a.rk[1]) ? q1a : stat(a.rk[1]);
                 const int q3b = (a.rk[4] == a.rk[5]) ? q3a : stat(a.rk[5]);
-                const float q1 = (a.rk[0] == a.rk[1]) ? (float)q1a : (1.0f - a.q1_frac) * (float)q1a + a.q1_frac * (float)q1b;
-                const float q3 = (a.rk[4] == a.rk[5]) ? (float)q3a : (1.0f - a.q3_frac) * (float)q3a + a.q3_frac * (float)q3b;
+                q1 = (a.rk[0] == a.rk[1]) ? (float)q1a : (1.0f - a.q1_frac) * (float)q1a + a.q1_frac * (float)q1b;
+                q3 = (a.rk[4] == a.rk[5]) ? (float)q3a : (1.0f - a.q3_frac) * (float)q3a + a.q3_frac * (float)q3b;
                 float iq = q3 - q1;
                 if (iq == 0.0f) iq = 1.0f;
                 iqi = 1.0f / iq;
             }
             acc.set_median(c, med);
             acc.set_iqr_inv(c, iqi);
+            if (a.dbg_median && lane == 0) {  // per-band sub-results (planes are zeroed by the host)
+                a.dbg_median[pix * 4 + c] = med;
+                if (a.dbg_q1) a.dbg_q1[pix * 4 + c] = q1;
+                if (a.dbg_q3) a.dbg_q3[pix * 4 + c] = q3;
+            }
             if (!(w < 0.0f)) {  // exact max |x - centre| from the smallest and the largest sample
                 const unsigned nz = __ballot_sync(0xffffffffu, lane_tot > 0);
                 int my_lo = 8 * lane + 7, my_hi = 8 * lane;
@@ -1915,7 +1997,8 @@ template <int C>
 __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(const __grid_constant__ OutlierArgs a) {
     grid_dependency_wait();
     __shared__ unsigned short mask_words[kMaskGroups][256];  // per-thread outlier masks of the dense pass
-    const MaskSlots ms{smem_u32(&mask_words[0][threadIdx.x]), 256u * 2u};
+    __shared__ __align__(16) uint8_t ring[dense_ring_bytes(C, 256)];  // ... and its ring of frame groups
+    const MaskSlots ms{smem_u32(&mask_words[0][threadIdx.x]), 256u * 2u, smem_u32(ring) + threadIdx.x * 16};
     const unsigned int mirrored = a.ghq_count[0], total = mirrored + a.gq_count[0];
     const int lane = threadIdx.x & 31;
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -2162,6 +2245,70 @@ __device__ __noinline__ void video_enqueue(const VideoArgs& v, VideoQueueEntry* 
     }
 }
 
+// Phase 2 of a chrono-video task, window by window over the per-(window, band) result words parked in shared memory:
+// certificate, then the background pixel -- or the exact-path queue.
+template <int C>
+__device__ __forceinline__ void video_phase2(const VideoArgs& v, const uint32_t* res, int rw, int i_lo, int i_hi, int blk, int tile, long long pix, bool owner,
+                                             int lane, VideoQueueEntry* queue, int& qcount) {
+    constexpr int kThreads = kVideoWarps * 32;
+    const OutlierArgs& a = v.o;
+    const int n = a.n;
+    // ---- phase 2, window by window: certificate, background pixel or exact-path queue
+#pragma unroll 1
+    for (int i = i_lo; i < i_hi; i++) {
+        const int win = blk * kVideoBlock + i - v.first_start;
+        uint32_t r0[C], r1[C];
+        float bound = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const uint32_t* r = res + ((i * C + c) * rw) * kThreads;
+            r0[c] = r[0];
+            r1[c] = rw > 1 ? r[kThreads] : 0u;
+            const float w = a.w[c];
+            if (w != 0.0f && !(w < 0.0f)) {
+                const float aw = a.absolute ? w : w * iqr_inv_of((int)(r1[c] >> 14));
+                const float t = aw * ((float)((r0[c] >> 9) & 0xffu) + 0.5f * (float)(r0[c] & 1u));
+                bound += t * t;
+            }
+        }
+        const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
+        if (owner && clean) {
+            uint8_t pixel[4] = {0, 0, 0, 0};
+            if (a.bg == 2) {
+#pragma unroll
+                for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf((float)(r1[c] & 0x3fffu) / (float)n));  // src/chrono.rs:297-306,335-337
+            } else if (a.bg == 3) {
+#pragma unroll
+                for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(0.5f * (float)(r0[c] & 0x1ffu)));  // :340-345
+            } else if (a.bg == 0) {
+#pragma unroll
+                for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((r0[c] >> 17) & 0xffu);  // :348-350: window position 0
+            } else {
+                const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)n);  // :357
+                const PixelSrc src{a.stack + (long long)tile * tile_bytes(C, a.NG), a.NG, C, lane};
+#pragma unroll
+                for (int c = 0; c < C; c++) pixel[c] = src.at(v.first_start + win + pos, c);
+            }
+            uint8_t* oi = v.out_images + (long long)win * v.out_stride + pix * C;
+#pragma unroll
+            for (int c = 0; c < C; c++) oi[c] = pixel[c];
+            if (v.out_masks) {
+                uint8_t* om = v.out_masks + (long long)win * v.out_stride + pix * C;
+#pragma unroll
+                for (int c = 0; c < C; c++) om[c] = (c < 3) ? 0 : 255;
+            }
+        }
+        const bool dirty = owner && !clean;
+        const unsigned db = __ballot_sync(0xffffffffu, dirty);
+        if (db) {
+            uint32_t w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < C; c++) { w0[c] = r0[c]; w1[c] = r1[c]; }
+            video_enqueue<C>(v, queue, qcount, lane, db, dirty, pix, win, w0[0], w0[1], w0[2], w0[3], w1[0], w1[1], w1[2], w1[3]);
+        }
+    }
+}
+
 // Result word 0 of a (window, band): bits 0-8 mlo + mhi (twice the median), 9-16 max |x - centre|, 17-24 the byte of
 // window position 0. Word 1 (when present): bits 0-13 band sum, 14-23 4 * IQR.
 template <int C, int NW>
@@ -2322,60 +2469,131 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
                 }
             }
         }
-        // ---- phase 2, window by window: certificate, background pixel or exact-path queue
+        video_phase2<C>(v, res, rw, i_lo, i_hi, blk, tile, pix, owner, lane, queue, qcount);
+    }
+    __syncwarp();
+    if (qcount > 0) drain_video_queue<C>(v, queue, qcount, lane);
+}
+
+// chrono-video runs with ABSOLUTE thresholds: same task shape and result words as video_kernel, but every window of the block is
+// evaluated from scratch out of the registers that hold the block's frame groups -- the window's words by funnel shifts, its
+// sum (IDP.4A), the straight-line five-value median window of K1 (band_window: 5 VABSDIFF4.ACC per word) and the exact byte-wise
+// maximum of |x - centre| for the certificate: about 9 instructions per window word, 110 per (window, band) at 25 frames,
+// against 300 for the sliding counts' bookkeeping (which only pays beyond ~150 frames per window; the sliding kernel is kept
+// for relative thresholds, whose quartiles it reads off the same counts). A median outside its window takes the whole warp
+// through the iterative solver, as in video_kernel.
+template <int C, int NW>
+__global__ void __launch_bounds__(kVideoWarps * 32, 4) video_direct_kernel(const __grid_constant__ VideoArgs v) {
+    constexpr int KG = (NW + 3) / 4 + 1;  // frame groups a block of 16 starts spans
+    constexpr int NWL = 4 * KG;           // words per lane
+    constexpr int kThreads = kVideoWarps * 32;
+    const OutlierArgs& a = v.o;
+    extern __shared__ __align__(16) uint8_t vsm[];
+    const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    VideoQueueEntry* const queue = reinterpret_cast<VideoQueueEntry*>(vsm) + warp_in_cta * kVideoQueueCap;
+    uint32_t* const res = reinterpret_cast<uint32_t*>(vsm + kVideoWarps * kVideoQueueCap * sizeof(VideoQueueEntry)) + threadIdx.x;
+    const int rw = v.res_words;
+    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n_tasks = (int)a.n_tiles * v.n_blocks;  // the host keeps this below 2^31
+    constexpr int cap = 4 * NW;
+    const int n = a.n;
+    const int pad = cap - n;
+    const int kp1 = a.rk[2] + pad, kp2 = a.rk[3] + pad;
+    int qcount = 0;
+    for (int task = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); task < n_tasks; task += n_warps) {
+        const int tile = task / v.n_blocks;
+        const int blk = v.blk0 + task % v.n_blocks;
+        const long long pix = (long long)tile * kTilePixels + lane;
+        const bool owner = pix < a.n_pixels;
+        const uint8_t* tb = a.stack + (long long)tile * tile_bytes(C, a.NG) + lane * kUnitBytes;
+        const int i_lo = max(0, v.first_start - blk * kVideoBlock);  // windows of this block that belong to the run
+        const int i_hi = min(kVideoBlock, v.first_start + v.n_windows - blk * kVideoBlock);
 #pragma unroll 1
-        for (int i = i_lo; i < i_hi; i++) {
-            const int win = blk * kVideoBlock + i - v.first_start;
-            uint32_t r0[C], r1[C];
-            float bound = 0.0f;
+        for (int c = 0; c < C; c++) {
+            uint32_t A[NWL + 1];
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                const uint32_t* r = res + ((i * C + c) * rw) * kThreads;
-                r0[c] = r[0];
-                r1[c] = rw > 1 ? r[kThreads] : 0u;
-                const float w = a.w[c];
-                if (w != 0.0f && !(w < 0.0f)) {
-                    const float aw = a.absolute ? w : w * iqr_inv_of((int)(r1[c] >> 14));
-                    const float t = aw * ((float)((r0[c] >> 9) & 0xffu) + 0.5f * (float)(r0[c] & 1u));
-                    bound += t * t;
-                }
+            for (int k = 0; k < KG; k++) {
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (blk + k < a.NG) u = ldg_stream(tb + ((long long)c * a.NG + (blk + k)) * (kTilePixels * kUnitBytes));
+                A[4 * k] = u.x; A[4 * k + 1] = u.y; A[4 * k + 2] = u.z; A[4 * k + 3] = u.w;
             }
-            const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
-            if (owner && clean) {
-                uint8_t pixel[4] = {0, 0, 0, 0};
-                if (a.bg == 2) {
+            A[NWL] = 0;
+            const float w = a.w[c];
+            const bool stats = (w != 0.0f);
+            int prev_med = 0;
+            bool have_prev = false;
+#pragma unroll 1
+            for (int wo = 0; wo < 4; wo++) {  // four windows per word offset; the words move down by one afterwards
+#pragma unroll 1
+                for (int bo = 0; bo < 4; bo++) {  // (one copy of the body: the shift amount is a register)
+                    const int i = 4 * wo + bo;
+                    if (i < i_lo || i >= i_hi) continue;  // uniform
+                    uint32_t X[NW];  // the window's words, positions >= n zeroed
 #pragma unroll
-                    for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf((float)(r1[c] & 0x3fffu) / (float)n));  // src/chrono.rs:297-306,335-337
-                } else if (a.bg == 3) {
+                    for (int q = 0; q < NW; q++) X[q] = __funnelshift_r(A[q], A[q + 1], 8 * bo);
+                    X[NW - 2] &= v.mask_a;
+                    X[NW - 1] &= v.mask_b;
+                    const uint32_t x_first = X[0] & 0xffu;
+                    uint32_t bsum = 0, odev = 0;
+                    int med2 = 0;
+                    if (a.bg == 2 || stats) {
+                        uint32_t s0 = 0, s1 = 0;
 #pragma unroll
-                    for (int c = 0; c < C; c++) pixel[c] = sat_u8(roundf(0.5f * (float)(r0[c] & 0x1ffu)));  // :340-345
-                } else if (a.bg == 0) {
+                        for (int q = 0; q < NW; q += 2) { s0 = __dp4a(X[q], 0x01010101u, s0); s1 = __dp4a(X[q + 1], 0x01010101u, s1); }
+                        bsum = s0 + s1;
+                    }
+                    if (stats) {
+                        // the previous window's median is the guess: one frame in, one out moves it to a neighbouring order statistic
+                        // at most, while the mean of 25 noisy samples misses the +-2 window for some lane of most warps
+                        const int guess = have_prev ? prev_med : __float2int_rn((float)bsum * a.inv_n_sub);
+                        // seven values around the guess resolve a median pair within +-2 of it; lanes it escaped get one more window
+                        // on the side the counts point to (+-3 .. +-7), and only then the whole warp runs the iterative solver
+                        int mlo, mhi, p0, cn[6];
+                        uint32_t fm;
+                        bool ok = band_window<NW, 1, 7>(X, guess, kp1, kp2, cap, mlo, mhi, false, fm, p0, cn);
+                        if (__any_sync(0xffffffffu, !ok && owner)) {
+                            const int g2 = cn[0] > kp1 ? guess - 5 : guess + 5;  // below the window : above it
+                            int mlo2, mhi2;
+                            const bool ok2 = band_window<NW, 1, 7>(X, min(max(g2, 0), 255), kp1, kp2, cap, mlo2, mhi2, false, fm, p0, cn);
+                            if (!ok) { mlo = mlo2; mhi = mhi2; ok = ok2; }
+                        }
+                        med2 = mlo + mhi;
+                        const unsigned nb = __ballot_sync(0xffffffffu, !ok && owner);
+                        if (nb) {  // iterative solver, the whole warp together
+                            if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(nb));
+                            uint32_t tmp[NW];
 #pragma unroll
-                    for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((r0[c] >> 17) & 0xffu);  // :348-350: window position 0
-                } else {
-                    const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)n);  // :357
-                    const PixelSrc src{a.stack + (long long)tile * tile_bytes(C, a.NG), a.NG, C, lane};
+                            for (int q = 0; q < NW; q++) tmp[q] = X[q];
+                            int m2 = 0, i4 = 0;
+                            video_solve<NW>(tmp, min(max(guess, 0), 254), a, pad, m2, i4);
+                            if (!ok) med2 = m2;
+                        }
+                        prev_med = med2 >> 1;
+                        have_prev = true;
+                        if (!(w < 0.0f)) {  // exact max |x - centre| (bytes beyond the window read as the centre)
+                            const uint32_t cc = rep4(med2 >> 1);
+                            X[NW - 2] |= cc & ~v.mask_a;
+                            X[NW - 1] |= cc & ~v.mask_b;
+                            uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-                    for (int c = 0; c < C; c++) pixel[c] = src.at(v.first_start + win + pos, c);
+                            for (int q = 0; q < NW; q += 2) {
+                                const uint32_t d0 = absdiff4(X[q], cc), d1 = absdiff4(X[q + 1], cc);
+                                m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);  // the high byte of each half is a byte-wise maximum
+                                m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
+                            }
+                            const uint32_t m = __vmaxu2(m0, m1);
+                            odev = max((m >> 8) & 0xffu, m >> 24);
+                        }
+                    }
+                    uint32_t* r = res + ((i * C + c) * rw) * kThreads;
+                    r[0] = (uint32_t)med2 | (odev << 9) | (x_first << 17);
+                    if (rw > 1) r[kThreads] = bsum;  // (4 * IQR stays 0: absolute thresholds)
                 }
-                uint8_t* oi = v.out_images + (long long)win * v.out_stride + pix * C;
 #pragma unroll
-                for (int c = 0; c < C; c++) oi[c] = pixel[c];
-                if (v.out_masks) {
-                    uint8_t* om = v.out_masks + (long long)win * v.out_stride + pix * C;
-#pragma unroll
-                    for (int c = 0; c < C; c++) om[c] = (c < 3) ? 0 : 255;
-                }
-            }
-            const bool dirty = owner && !clean;
-            const unsigned db = __ballot_sync(0xffffffffu, dirty);
-            if (db) {
-                uint32_t w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int c = 0; c < C; c++) { w0[c] = r0[c]; w1[c] = r1[c]; }
-                video_enqueue<C>(v, queue, qcount, lane, db, dirty, pix, win, w0[0], w0[1], w0[2], w0[3], w1[0], w1[1], w1[2], w1[3]);
+                for (int q = 0; q < NWL; q++) A[q] = A[q + 1];
             }
         }
+        video_phase2<C>(v, res, rw, i_lo, i_hi, blk, tile, pix, owner, lane, queue, qcount);
     }
     __syncwarp();
     if (qcount > 0) drain_video_queue<C>(v, queue, qcount, lane);

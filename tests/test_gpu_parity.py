@@ -184,12 +184,25 @@ def test_longest_series_one_launch_holds(ctx, n):
     check_outlier(ctx, st, (False, 3.0, 5.0), "median", "backward")
 
 
-def test_more_than_4096_frames_in_one_window_is_reported(ctx):
-    st = np.zeros((4097, 2, 4, 3), np.uint8)
+@pytest.mark.parametrize("n", [4097, 5000])
+def test_series_beyond_4096_frames_go_through_the_histogram_tier(ctx, n):
+    # more frames than the register-resident variants hold: every pixel takes outlier_hist_kernel (any length) and, where its
+    # certificate fails, the per-frame path -- slower, but the same composite, mask, statistics and warnings as the reference
+    rng = np.random.default_rng(n)
+    st = make_stack(rng, n, 3, 9, 3, noise=6, n_obj=4)
+    check_outlier(ctx, st, (True, 0.05, 0.2), "first", "extreme")
+    check_outlier(ctx, st, (False, 3.0, 5.0), "median", "backward")
+    check_outlier(ctx, st, (True, 0.05, 0.2), "average", "average")
+    check_outlier(ctx, st, (True, 0.05, 0.2), "random", "forward")
+
+
+def test_windows_of_a_series_beyond_4096_frames(ctx):
+    st = np.zeros((4200, 2, 4, 3), np.uint8)
     fs = upload(ctx, st)
+    # a window spanning more than 4096 frames is not a whole-stack launch: reported, not computed
     with pytest.raises(Exception) as ei:
-        cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG["first"], OM["extreme"]).process(fs)
-    assert "4096" in str(ei.value) or "holds at most" in str(ei.value)
+        cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG["first"], OM["extreme"]).process(fs, list(range(0, 4199)))
+    assert "whole-stack" in str(ei.value)
     # a window of the same stack that fits is fine, and so are darker / lighter (they stream, no capacity limit)
     img, _ = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG["first"], OM["extreme"]).process(fs, list(range(100, 400)))
     assert not img.any()

@@ -1,7 +1,9 @@
-// chrono_b200_cli -- CLI-compatible driver for the compositing path (mirrors src/cli.rs:19-243 and src/main.rs:21-429
-// for the hot-path flags). Frames are binary PPM (P6, maxval 255): this image has no JPEG/PNG codec library, the
-// reference's decode/encode (`image` crate) stays outside the path. Flags that only steer the reference's temp files
-// (--slice, --compression, --temp-dir) or its thread pools / JPEG quality are accepted and ignored.
+// chrono_b200_cli -- CLI-compatible driver for the compositing path (mirrors src/cli.rs:19-243 and src/main.rs:21-571
+// for the hot-path flags). Frames: JPEG (decoded on the GPU by nvJPEG: the compressed bytes cross PCIe), PNG (RGB8 / RGBA8,
+// zlib) or binary PPM; output by extension like save_image (src/main.rs:520-571): jpg/jpeg at --quality, png, tif/tiff, bmp,
+// ppm. --shake / --shake-anchors run the camera-shake analysis on the GPU (src/main.rs:61-77) and the Crop origins are applied
+// while the frames are uploaded. Flags that only steer the reference's temp files (--slice, --compression, --temp-dir) or its
+// thread pools are accepted and ignored.
 #include <glob.h>
 
 #include <algorithm>
@@ -12,45 +14,9 @@
 #include <map>
 
 #include "../include/chrono_b200.hpp"
+#include "../include/chrono_b200_imageio.hpp"
 
 using namespace chrono_b200;
-
-struct Image {
-    int w = 0, h = 0;
-    std::vector<uint8_t> px;
-};
-
-static Image read_ppm(const std::string& path) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) throw std::runtime_error("Unable to open image " + path);
-    std::string magic;
-    f >> magic;
-    if (magic != "P6") throw std::runtime_error("Unexpected format. Not a binary PPM (P6): " + path);
-    auto next_int = [&]() {
-        int v;
-        while (true) {
-            f >> std::ws;
-            if (f.peek() == '#') { std::string line; std::getline(f, line); continue; }
-            f >> v;
-            return v;
-        }
-    };
-    Image im;
-    im.w = next_int(); im.h = next_int();
-    int maxv = next_int();
-    if (maxv != 255) throw std::runtime_error("Unexpected format. Not an 8 bit image.");
-    f.get();
-    im.px.resize((size_t)im.w * im.h * 3);
-    f.read(reinterpret_cast<char*>(im.px.data()), (std::streamsize)im.px.size());
-    if (!f) throw std::runtime_error("Truncated PPM: " + path);
-    return im;
-}
-static void write_ppm(const std::string& path, int w, int h, const std::vector<uint8_t>& px) {
-    std::ofstream f(path, std::ios::binary);
-    if (!f) throw std::runtime_error("Unable to create output file " + path);
-    f << "P6\n" << w << " " << h << "\n255\n";
-    f.write(reinterpret_cast<const char*>(px.data()), (std::streamsize)px.size());
-}
 
 // Cli::from_str quote handling (src/cli.rs:245-266)
 static std::vector<std::string> split_option_string(const std::string& str) {
@@ -98,6 +64,7 @@ int main(int argc, char** argv) {
         }
         std::map<std::string, std::string> opt;
         std::vector<float> weights;
+        std::vector<std::string> anchor_args;
         const std::map<std::string, std::string> shorts = {{"-p", "--pattern"}, {"-f", "--frames"}, {"-o", "--output"}, {"-m", "--mode"}, {"-t", "--threshold"},
                                                            {"-b", "--background"}, {"-l", "--outlier"}, {"-c", "--compression"}, {"-q", "--quality"}, {"-s", "--slice"}};
         for (size_t i = 0; i < args.size(); i++) {
@@ -109,6 +76,12 @@ int main(int argc, char** argv) {
                     if (++i >= args.size()) throw ParseOptionError("--weights requires 4 values");
                     weights.push_back(parse_f32(args[i], "Can't parse weight " + args[i]));
                 }
+                continue;
+            }
+            if (a == "--shake-anchors") {  // one or more x/y values (src/cli.rs:125-127)
+                while (i + 1 < args.size() && args[i + 1].rfind("--", 0) != 0 && !(args[i + 1].size() == 2 && args[i + 1][0] == '-')) anchor_args.push_back(args[++i]);
+                if (anchor_args.empty()) throw ParseOptionError("The argument '--shake-anchors' requires a value");
+                opt[a] = "given";
                 continue;
             }
             if (a.rfind("--", 0) != 0) throw ParseOptionError("Found argument '" + a + "' which wasn't expected");
@@ -131,7 +104,8 @@ int main(int argc, char** argv) {
         if (opt.count("--video-in")) video_in = FrameRange::from_str(opt["--video-in"]);
         if (opt.count("--video-out")) video_out = FrameRange::from_str(opt["--video-out"]);
         if (opt.count("--shake") != opt.count("--shake-anchors")) throw ParseOptionError("Provide both options or none: `--shake` and `--shake-anchors`");
-        if (opt.count("--shake")) throw ParseOptionError("--shake: camera-shake analysis is outside this driver (SURVEY.md 8f); pass pre-cropped frames");
+        int quality = opt.count("--quality") ? parse_i32(opt["--quality"], "Can't parse --quality") : 95;  // src/cli.rs:197-200
+        if (quality < 1 || quality > 100) throw ParseOptionError("--quality must be in 1..100");
         if (mode != SelectionMode::Outlier) {  // src/cli.rs:141-167, :233-239
             std::vector<std::string> unused;
             for (const char* k : {"--output-blend", "--threshold", "--outlier", "--background", "--temp-dir", "--sample", "--slice", "--compression"})
@@ -160,27 +134,62 @@ int main(int argc, char** argv) {
         }
         if (files.empty()) throw std::runtime_error("Unable to process search pattern " + opt["--pattern"]);
 
-        // ---- upload (replaces to_time_slices, src/main.rs:574-602)
+        // ---- camera-shake analysis (src/main.rs:61-84: ShakeAnalyzer::analyze -> Crop::create), then the upload that replaces
+        // to_time_slices (src/main.rs:574-602): every frame lands in the HBM-resident stack at its Crop origin
         Context ctx;
-        Image first = read_ppm(files[0]);
-        GpuStack stack(ctx, first.w, first.h, 3, (int)files.size());
+        Image first = read_image(files[0], &ctx);
+        const int fw = first.w, fh = first.h, ch = first.c;
+        std::vector<int32_t> origins(2 * files.size(), 0);
+        int cw = fw, chh = fh;
+        if (opt.count("--shake")) {
+            const ShakeParams sp = ShakeParams::from_str(opt["--shake"]);
+            std::vector<ShakeAnchor> anchors;
+            for (const auto& s : anchor_args) anchors.push_back(ShakeAnchor::from_str(s));
+            std::cout << "Analyzing camera shake in " << files.size() << " images\n";
+            ShakeAnalyzer an(ctx, fw, fh, ch, anchors, sp, first.px.data(), (size_t)fw * ch);
+            std::vector<int32_t> offs(2 * files.size(), 0);  // the first frame is the reference: offset (0, 0) (src/shake.rs:284-286)
+            for (size_t i = 1; i < files.size(); i++) {
+                Image im = read_image(files[i], &ctx);
+                if (im.w != fw || im.h != fh || im.c != ch) throw std::runtime_error("Image layout does not fit!");
+                auto o = an.offset(im.px.data(), (size_t)im.w * im.c);
+                offs[2 * i] = o.first; offs[2 * i + 1] = o.second;
+            }
+            int32_t w2 = 0, h2 = 0;
+            if (chb_crop_create(offs.data(), (int)files.size(), fw, fh, origins.data(), &w2, &h2)) {
+                std::cout << "Camera shake detected. Images will be corrected.\n";
+                cw = w2; chh = h2;
+                if (cw < 1 || chh < 1) throw std::runtime_error("Camera shake larger than the image");
+            } else {
+                std::cout << "No camera shake detected. Images will not be corrected.\n";
+                std::fill(origins.begin(), origins.end(), 0);
+            }
+        }
+        GpuStack stack(ctx, cw, chh, ch, (int)files.size());
         for (size_t i = 0; i < files.size(); i++) {
-            Image im = i == 0 ? first : read_ppm(files[i]);
-            if (im.w != first.w || im.h != first.h) throw std::runtime_error("Image layout does not fit!");  // src/simple.rs:62-66
-            stack.upload((int)i, im.px.data(), (size_t)im.w * 3);
+            const int ox = origins[2 * i], oy = origins[2 * i + 1];
+            if (is_jpeg_path(files[i]) && ch == 3) {  // compressed bytes to the device, decoded there (chb_stack_upload_jpeg checks the layout)
+                const std::vector<uint8_t> bytes = read_file(files[i]);
+                check(chb_stack_upload_jpeg(stack.raw(), (int)i, bytes.data(), bytes.size(), ox, oy));
+            } else {
+                Image im = i == 0 ? first : read_image(files[i], &ctx);
+                if (im.w != fw || im.h != fh || im.c != ch) throw std::runtime_error("Image layout does not fit!");  // src/simple.rs:62-66
+                stack.upload((int)i, im.px.data(), (size_t)im.w * im.c, ox, oy);
+            }
         }
         stack.sync();
+        first.w = cw; first.h = chh;  // the composites have the cropped size
+        auto write_out = [&](const std::string& path, const uint8_t* px) { save_image(px, cw, chh, ch, path, quality, &ctx); };
 
         auto run_frame = [&](const std::vector<int32_t>* indices, const std::string& out, const std::optional<std::string>& out_blend) {
             if (mode == SelectionMode::Outlier) {
                 OutlierProcessor proc(threshold, background, outlier, w, fade, sample, /*seed=*/0x9E3779B97F4A7C15ULL);
                 auto res = proc.process(stack, indices);
                 if (proc.warnings() > 0) std::cout << "Warning: " << proc.warnings() << " pixels seem to consist of only outliers\n";
-                write_ppm(out, first.w, first.h, res.first);
-                if (out_blend) write_ppm(*out_blend, first.w, first.h, res.second);
+                write_out(out, res.first.data());
+                if (out_blend) write_out(*out_blend, res.second.data());
             } else {
                 SimpleProcessor proc(w, fade, mode == SelectionMode::Darker);
-                write_ppm(out, first.w, first.h, proc.process(stack, indices));
+                write_out(out, proc.process(stack, indices).data());
             }
         };
         std::optional<std::string> out_blend;
@@ -213,15 +222,12 @@ int main(int argc, char** argv) {
                     std::vector<uint8_t> bufs, masks;
                     std::vector<uint64_t> warns;
                     vproc.process_video_run(stack, ws[i], len, j - i, bufs, masks, warns);
-                    const size_t fb = (size_t)first.w * first.h * 3;
+                    const size_t fb = (size_t)cw * chh * ch;
                     for (int k = i; k < j; k++) {
                         std::cout << "Processing frame " << num[k] << " -> \n";
                         if (warns[k - i] > 0) std::cout << "Warning: " << warns[k - i] << " pixels seem to consist of only outliers\n";
-                        write_ppm(frame_name(opt["--output"], num[k]), first.w, first.h,
-                                  std::vector<uint8_t>(bufs.begin() + (k - i) * fb, bufs.begin() + (k - i + 1) * fb));
-                        if (out_blend)
-                            write_ppm(frame_name(*out_blend, num[k]), first.w, first.h,
-                                      std::vector<uint8_t>(masks.begin() + (k - i) * fb, masks.begin() + (k - i + 1) * fb));
+                        write_out(frame_name(opt["--output"], num[k]), bufs.data() + (k - i) * fb);
+                        if (out_blend) write_out(frame_name(*out_blend, num[k]), masks.data() + (k - i) * fb);
                     }
                     i = j;
                     continue;

@@ -1,0 +1,37 @@
+#!/bin/bash
+# A/B of the dense per-frame pass / solver changes against the previous build, inside one box.
+OUT=gpurun_out/r2j
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+show() { python -c "
+import sys,json
+d=json.loads(open('$1').read().strip().splitlines()[-1]); r=d['roofline']; v=d.get('verified') or {}
+print('$2', d['config']['workload'], 'ms %.3f'%d['ms_per_step'], 'call %.3f'%r['avg_launch_ms'], 'frac %.3f'%r['frac'], 'main %.3f'%(r.get('dominant_kernel') or {}).get('avg_launch_ms',0), 'verified', v.get('ok'), v.get('pixels_differing_from_oracle'))
+"; }
+timeout 900 python -m pytest tests/ -x -q -m gpu > $OUT/pytest_gpu.txt 2>&1; echo "exit $?" >> $OUT/pytest_gpu.txt
+tail -5 $OUT/pytest_gpu.txt
+for wl in a4-gauss-noise a1-iid-uniform c3-outlier-abs-extreme; do
+  CHB_LIB=$PWD/chrono_photo_b200/_variants/base.so timeout 300 python bench.py --workload $wl --no-cpu --no-e2e --no-verify --steps 10 --warmup 3 > $OUT/base_$wl.json 2> $OUT/base_$wl.err; show $OUT/base_$wl.json base
+  timeout 300 python bench.py --workload $wl --no-cpu --no-e2e --steps 10 --warmup 3 > $OUT/new_$wl.json 2> $OUT/new_$wl.err; show $OUT/new_$wl.json new
+done
+for pf in 0 1 3 4; do
+  CHB_DENSE_PF=$pf timeout 300 python bench.py --workload a4-gauss-noise --no-cpu --no-e2e --no-verify --steps 10 --warmup 3 > $OUT/pf${pf}_a4.json 2>/dev/null; show $OUT/pf${pf}_a4.json pf$pf
+done
+for co in 100 50; do
+  CHB_CARVEOUT=$co timeout 300 python bench.py --workload a4-gauss-noise --no-cpu --no-e2e --no-verify --steps 10 --warmup 3 > $OUT/co${co}_a4.json 2>/dev/null; show $OUT/co${co}_a4.json carveout$co
+  CHB_CARVEOUT=$co timeout 300 python bench.py --workload c3-outlier-abs-extreme --no-cpu --no-e2e --no-verify --steps 10 --warmup 3 > $OUT/co${co}_c3.json 2>/dev/null; show $OUT/co${co}_c3.json carveout$co
+done
+for im in 4 8 20; do
+  CHB_INLINE_MIN=$im timeout 300 python bench.py --workload a4-gauss-noise --no-cpu --no-e2e --no-verify --steps 10 --warmup 3 > $OUT/im${im}_a4.json 2>/dev/null; show $OUT/im${im}_a4.json inline_min$im
+done
+# an eighth of config 3 (what one of 8 GPUs sees under strong scaling)
+timeout 200 python tools/small_band.py > $OUT/small_band.txt 2>&1; tail -5 $OUT/small_band.txt
+# ncu: hard kernel on iid bytes, streaming kernel on a4
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:^outlier_hard_kernel -s 1 -c 1 -f -o $OUT/ncu_hard_a1 python tools/launch_times.py 2048 2048 200 0 3 > $OUT/ncu_hard_a1.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:^outlier_kernel -s 1 -c 1 -f -o $OUT/ncu_outlier_a4 python tools/launch_times.py 4000 6000 200 0 4 > $OUT/ncu_outlier_a4.log 2>&1
+for r in $OUT/*.ncu-rep; do
+  b=${r%.ncu-rep}
+  python tools/ncu_summary.py $r 30 > $b.summary.txt 2>&1
+  ncu -i $r --page source --csv --print-source cuda,sass 2>/dev/null | gzip -9 > $b.source.csv.gz
+  rm -f $r
+done
