@@ -254,8 +254,30 @@ def verify_photo(orc, np, mode, kind, n, H, W, image, mask):
     return rows_done, bad, where
 
 
+def bind_to_gpu_cpus(index):
+    """One rank per GPU: the process (and with it the first-touch placement of its pinned host frames) is bound to the CPUs NVML
+    reports as local to the GPU, so that every rank's H2D stream crosses its own root complex instead of the socket interconnect.
+    Returns the number of CPUs bound to, or None when NVML gives no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class Env:
     """torch / torch.distributed plumbing of one bench process."""
+    cpu_affinity = None
 
     def __init__(self, args):
         import torch
@@ -271,6 +293,7 @@ class Env:
             import torch.distributed as dist
             self.dist = dist
             torch.cuda.set_device(self.local_rank)
+            self.cpu_affinity = bind_to_gpu_cpus(self.local_rank)
             # stdout carries the one JSON line only: NCCL prints its version banner with a plain printf when the communicator is
             # created, so file descriptor 1 points at stderr until the first collective is through
             sys.stdout.flush()
@@ -585,7 +608,8 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
     cfg = config_of(wl)
     cfg_run = {"sharding": (f"{n_gpus} bands of {rows} rows: a {W}x{H} image, every GPU owns one full-size band of the workload" if weak
                             else f"{W}x{H_img} image cut into {n_gpus} band(s) of {rows} rows"),
-               "launcher": "torchrun" if env.multi_proc else "single-process", "stack_gb_per_gpu": stack.device_bytes(0) / 1e9}
+               "launcher": "torchrun" if env.multi_proc else "single-process", "stack_gb_per_gpu": stack.device_bytes(0) / 1e9,
+               "cpus_bound_per_rank": env.cpu_affinity}
     out = {"metric": "pixel-frames/s", "value": value, "unit": "pixel-frames/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (weak or n_gpus == 1) else "strong", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic", "config": cfg, "run": cfg_run,

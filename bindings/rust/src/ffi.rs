@@ -103,6 +103,7 @@ extern "C" {
     pub fn chb_ctx_create(device_ids: *const c_int, n_dev: c_int, out: *mut *mut ChbCtx) -> c_int;
     pub fn chb_ctx_destroy(ctx: *mut ChbCtx) -> c_int;
     pub fn chb_ctx_device_count(ctx: *const ChbCtx) -> c_int;
+    pub fn chb_ctx_mem_info(ctx: *mut ChbCtx, dev_slot: c_int, free_bytes: *mut usize, total_bytes: *mut usize) -> c_int;
     pub fn chb_stack_create(ctx: *mut ChbCtx, width: c_int, height: c_int, channels: c_int, n_frames: c_int, out: *mut *mut ChbStack) -> c_int;
     pub fn chb_stack_destroy(stack: *mut ChbStack) -> c_int;
     pub fn chb_stack_upload(stack: *mut ChbStack, frame_idx: c_int, host_pixels: *const u8, row_pitch: usize, crop_x: c_int, crop_y: c_int) -> c_int;

@@ -42,6 +42,7 @@ SYMBOLS = {
     "chb_ctx_create": (_i, [C.POINTER(C.c_int), _i, C.POINTER(_vp)]),
     "chb_ctx_destroy": (_i, [_vp]),
     "chb_ctx_device_count": (_i, [_vp]),
+    "chb_ctx_mem_info": (_i, [_vp, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "chb_ctx_set_stream": (_i, [_vp, _i, _vp]),
     "chb_stack_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "chb_stack_destroy": (_i, [_vp]),

@@ -48,12 +48,11 @@ struct Tuning {
     std::atomic<int> pdl{1};               // CHB_PDL: tier kernels as programmatic dependent launches
     std::atomic<int> video_queue_cap{-1};  // CHB_VIDEO_QUEUE_CAP: capacity of the video exact-path queue (tests the in-place fallback)
     std::atomic<int> inline_min{12};       // CHB_INLINE_MIN: uncertified pixels per tile from which the tile is finished inside K1 (0 = never)
-    std::atomic<int> video_direct{0};      // CHB_VIDEO_DIRECT: 0 = chrono-video runs with absolute thresholds use the sliding-count kernel too
     std::atomic<int> hard_inline_min{1};   // CHB_HARD_INLINE_MIN: same for a warp-full of the iterative tier (finished inside outlier_hard_kernel)
     Tuning() {
         auto env = [](const char* k, std::atomic<int>& v) { if (const char* e = getenv(k)) v.store(atoi(e)); };
         env("CHB_FORCE_VARIANT", force_variant); env("CHB_HIST", hist); env("CHB_PDL", pdl);
-        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min); env("CHB_HARD_INLINE_MIN", hard_inline_min); env("CHB_VIDEO_DIRECT", video_direct);
+        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min); env("CHB_HARD_INLINE_MIN", hard_inline_min);
     }
 };
 static Tuning g_tune;
@@ -66,7 +65,6 @@ extern "C" int chb_set_tuning(const char* key, int value) {
     else if (k == "video_queue_cap") g_tune.video_queue_cap.store(value);
     else if (k == "inline_min") g_tune.inline_min.store(value);
     else if (k == "hard_inline_min") g_tune.hard_inline_min.store(value);
-    else if (k == "video_direct") g_tune.video_direct.store(value);
     else return fail(CHB_ERR_INVALID, "chb_set_tuning: unknown key '%s'", key);
     return CHB_OK;
 }
@@ -228,6 +226,16 @@ extern "C" int chb_ctx_destroy(chb_ctx* ctx) {
 }
 
 extern "C" int chb_ctx_device_count(const chb_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+extern "C" int chb_ctx_mem_info(chb_ctx* ctx, int dev_slot, size_t* free_bytes, size_t* total_bytes) {
+    if (!ctx || dev_slot < 0 || dev_slot >= (int)ctx->devs.size()) return fail(CHB_ERR_INVALID, "chb_ctx_mem_info: bad device slot");
+    size_t f = 0, t = 0;
+    CU(cudaSetDevice(ctx->devs[dev_slot].id));
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return CHB_OK;
+}
 
 extern "C" int chb_ctx_set_stream(chb_ctx* ctx, int dev_slot, void* cuda_stream) {
     if (!ctx || dev_slot < 0 || dev_slot >= (int)ctx->devs.size()) return fail(CHB_ERR_INVALID, "chb_ctx_set_stream: bad device slot");
@@ -1167,19 +1175,6 @@ static VideoKernel video_kernel_for(int nw) {
         default: return video_kernel<C, 16>;
     }
 }
-template <int C>
-static VideoKernel video_direct_kernel_for(int nw) {
-    switch (nw) {
-        case 2: return video_direct_kernel<C, 2>;
-        case 4: return video_direct_kernel<C, 4>;
-        case 6: return video_direct_kernel<C, 6>;
-        case 8: return video_direct_kernel<C, 8>;
-        case 10: return video_direct_kernel<C, 10>;
-        case 12: return video_direct_kernel<C, 12>;
-        case 14: return video_direct_kernel<C, 14>;
-        default: return video_direct_kernel<C, 16>;
-    }
-}
 static constexpr int kMaxVideoWindow = 64;
 static constexpr unsigned int kVideoQueueEntries = 2u << 20;  // 128 MB; pixel-windows beyond it are finished inside video_kernel
 
@@ -1239,11 +1234,7 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
     va.mask_b = word_mask(nw - 1);
     va.res_words = (!prm->thr_absolute || prm->background == CHB_BG_AVERAGE) ? 2 : 1;
     const int smem = video_smem_bytes(st->C, va.res_words);
-    // absolute thresholds: every window recomputed from registers (video_direct_kernel); relative: the sliding counts, which also
-    // yield the quartiles (video_kernel). CHB_VIDEO_DIRECT=0 forces the sliding kernel (tests, A/B).
-    const bool direct = prm->thr_absolute && g_tune.video_direct.load() != 0;
-    VideoKernel kern = direct ? (st->C == 3 ? video_direct_kernel_for<3>(nw) : video_direct_kernel_for<4>(nw))
-                              : (st->C == 3 ? video_kernel_for<3>(nw) : video_kernel_for<4>(nw));
+    VideoKernel kern = st->C == 3 ? video_kernel_for<3>(nw) : video_kernel_for<4>(nw);
     if (!prm->fade.is_none) memcpy(st->slots[0].h_fade, prm->fade.values, sizeof(float) * (size_t)prm->fade.n_values);
     st->slots[0].last_tables.clear();  // the fade table on the devices no longer belongs to a single-window call
 

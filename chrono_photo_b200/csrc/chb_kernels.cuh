@@ -806,7 +806,10 @@ __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint
             }
         }
         uint32_t om16 = 0;
-        int gkey = INT_MIN;  // max over the group's frames of 16 * (q - t) + (15 - j)
+        // max over the group's frames of 19 * (q - t) + (15 - j): the first maximum of the distance wins. (19, not 16: a multiplier
+        // that is no power of two plus or minus one keeps the per-frame key ONE IMAD on the FMA pipe; the ALU pipe -- PRMT,
+        // VABSDIFF4, SHF at half rate -- is the pass's bottleneck.)
+        int gkey = INT_MIN;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             uint32_t xw[4] = {0u, 0u, 0u, 0u};
@@ -822,14 +825,16 @@ __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint
                 // dm = q - t with 4 dist_sq = 4 q + k2 (see IntMedians): negative <=> not an outlier
                 const int dm = dp4a_us(pfw[kk], negd, (int)__dp4a(L, L, (uint32_t)c0));
                 om16 = __funnelshift_l((uint32_t)dm, om16, 1);  // collects the NON-outlier bits, frame j at bit 15 - j
-                gkey = max(gkey, dm * 16 + (15 - j));
+                gkey = max(gkey, dm * 19 + (15 - j));
             }
         }
         om16 = (~__brev(om16)) >> 16;
         ms.put(g - gA, om16);
         k += __popc(om16);
-        const int s = sg + 15 - (gkey & 15);
-        maxkey = max(maxkey, ((uint32_t)(4 * ((gkey >> 4) + im.t) + im.k2) << 12) | (uint32_t)(4095 - s));
+        const uint32_t gq = (uint32_t)(gkey + 19 * im.t);  // 19 q + (15 - j) >= 0
+        const uint32_t qv = gq / 19u;
+        const int s = sg + 15 - (int)(gq - 19u * qv);
+        maxkey = max(maxkey, ((4u * qv + (uint32_t)im.k2) << 12) | (uint32_t)(4095 - s));
     }
     k_out = k;
     maxkey_out = maxkey;
@@ -1320,8 +1325,14 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center,
     p_out = p;
     if (want_f) f_mid = group_sum<G>(f[kHalf]);  // F(p + NP/2): spread estimate for the quartile guesses (relative thresholds)
     v1 = p; v2 = p;
+    if (kp1 == kp2) {  // (uniform) odd sample counts: the median pair is one rank
 #pragma unroll
-    for (int k = 0; k < NP - 1; k++) { v1 += (cn[k] <= kp1); v2 += (cn[k] <= kp2); }
+        for (int k = 0; k < NP - 1; k++) v1 += (cn[k] <= kp1);
+        v2 = v1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NP - 1; k++) { v1 += (cn[k] <= kp1); v2 += (cn[k] <= kp2); }
+    }
     return ((cn[0] <= kp1) || p == 0) && ((kp2 < cn[NP - 2]) || p == 256 - NP);
 }
 
@@ -1574,7 +1585,30 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         o |= o >> 8;
         o = group_or<G>(o & 0xffu);  // >= max over frames of |x - centre| (OR dominates max)
         const float aw = a.absolute ? w : w * iqi;
-        const float t = aw * ((float)o + halfw);
+        float t = aw * ((float)o + halfw);
+        // The OR overshoots the maximum by up to 2x (4 | 3 = 7, 8 | 7 = 15). Where that alone costs a pixel its certificate --
+        // the bound fails with the OR but would hold with the highest set bit of the OR, which the maximum is at least -- the
+        // warp takes a second pass for the exact byte-wise maximum (VIMNMX.U16x2: the high byte of each half is a byte maximum).
+        // Series whose noise stays below the OR's next power of two (the S2 series at abs/0.05) never take it.
+        {
+            const bool fails = !((acc.bound + t * t) * 1.0001f < a.thr_sq);
+            const float t_lo = aw * ((float)(o ? (1u << (31 - __clz(o))) : 0u) + halfw);
+            const bool could = (acc.bound + t_lo * t_lo) * 1.0001f < a.thr_sq;
+            if (__any_sync(0xffffffffu, fails && could)) {
+                uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+                for (int q = 0; q < W4; q += 2) {
+                    const uint32_t d0 = absdiff4(A[q], cc), d1 = absdiff4(A[q + 1], cc);
+                    m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);
+                    m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
+                }
+                const uint32_t m = __vmaxu2(m0, m1);
+                uint32_t mx = max((m >> 8) & 0xffu, m >> 24);
+#pragma unroll
+                for (int sh = 32 / G; sh < 32; sh <<= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+                t = aw * ((float)mx + halfw);
+            }
+        }
         acc.bound += t * t;
     }
 }
@@ -2467,130 +2501,6 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
                         A[NWL - 1] = 0;
                     }
                 }
-            }
-        }
-        video_phase2<C>(v, res, rw, i_lo, i_hi, blk, tile, pix, owner, lane, queue, qcount);
-    }
-    __syncwarp();
-    if (qcount > 0) drain_video_queue<C>(v, queue, qcount, lane);
-}
-
-// chrono-video runs with ABSOLUTE thresholds: same task shape and result words as video_kernel, but every window of the block is
-// evaluated from scratch out of the registers that hold the block's frame groups -- the window's words by funnel shifts, its
-// sum (IDP.4A), the straight-line five-value median window of K1 (band_window: 5 VABSDIFF4.ACC per word) and the exact byte-wise
-// maximum of |x - centre| for the certificate: about 9 instructions per window word, 110 per (window, band) at 25 frames,
-// against 300 for the sliding counts' bookkeeping (which only pays beyond ~150 frames per window; the sliding kernel is kept
-// for relative thresholds, whose quartiles it reads off the same counts). A median outside its window takes the whole warp
-// through the iterative solver, as in video_kernel.
-template <int C, int NW>
-__global__ void __launch_bounds__(kVideoWarps * 32, 4) video_direct_kernel(const __grid_constant__ VideoArgs v) {
-    constexpr int KG = (NW + 3) / 4 + 1;  // frame groups a block of 16 starts spans
-    constexpr int NWL = 4 * KG;           // words per lane
-    constexpr int kThreads = kVideoWarps * 32;
-    const OutlierArgs& a = v.o;
-    extern __shared__ __align__(16) uint8_t vsm[];
-    const int lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
-    VideoQueueEntry* const queue = reinterpret_cast<VideoQueueEntry*>(vsm) + warp_in_cta * kVideoQueueCap;
-    uint32_t* const res = reinterpret_cast<uint32_t*>(vsm + kVideoWarps * kVideoQueueCap * sizeof(VideoQueueEntry)) + threadIdx.x;
-    const int rw = v.res_words;
-    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
-    const int n_tasks = (int)a.n_tiles * v.n_blocks;  // the host keeps this below 2^31
-    constexpr int cap = 4 * NW;
-    const int n = a.n;
-    const int pad = cap - n;
-    const int kp1 = a.rk[2] + pad, kp2 = a.rk[3] + pad;
-    int qcount = 0;
-    for (int task = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); task < n_tasks; task += n_warps) {
-        const int tile = task / v.n_blocks;
-        const int blk = v.blk0 + task % v.n_blocks;
-        const long long pix = (long long)tile * kTilePixels + lane;
-        const bool owner = pix < a.n_pixels;
-        const uint8_t* tb = a.stack + (long long)tile * tile_bytes(C, a.NG) + lane * kUnitBytes;
-        const int i_lo = max(0, v.first_start - blk * kVideoBlock);  // windows of this block that belong to the run
-        const int i_hi = min(kVideoBlock, v.first_start + v.n_windows - blk * kVideoBlock);
-#pragma unroll 1
-        for (int c = 0; c < C; c++) {
-            uint32_t A[NWL + 1];
-#pragma unroll
-            for (int k = 0; k < KG; k++) {
-                uint4 u = make_uint4(0, 0, 0, 0);
-                if (blk + k < a.NG) u = ldg_stream(tb + ((long long)c * a.NG + (blk + k)) * (kTilePixels * kUnitBytes));
-                A[4 * k] = u.x; A[4 * k + 1] = u.y; A[4 * k + 2] = u.z; A[4 * k + 3] = u.w;
-            }
-            A[NWL] = 0;
-            const float w = a.w[c];
-            const bool stats = (w != 0.0f);
-            int prev_med = 0;
-            bool have_prev = false;
-#pragma unroll 1
-            for (int wo = 0; wo < 4; wo++) {  // four windows per word offset; the words move down by one afterwards
-#pragma unroll 1
-                for (int bo = 0; bo < 4; bo++) {  // (one copy of the body: the shift amount is a register)
-                    const int i = 4 * wo + bo;
-                    if (i < i_lo || i >= i_hi) continue;  // uniform
-                    uint32_t X[NW];  // the window's words, positions >= n zeroed
-#pragma unroll
-                    for (int q = 0; q < NW; q++) X[q] = __funnelshift_r(A[q], A[q + 1], 8 * bo);
-                    X[NW - 2] &= v.mask_a;
-                    X[NW - 1] &= v.mask_b;
-                    const uint32_t x_first = X[0] & 0xffu;
-                    uint32_t bsum = 0, odev = 0;
-                    int med2 = 0;
-                    if (a.bg == 2 || stats) {
-                        uint32_t s0 = 0, s1 = 0;
-#pragma unroll
-                        for (int q = 0; q < NW; q += 2) { s0 = __dp4a(X[q], 0x01010101u, s0); s1 = __dp4a(X[q + 1], 0x01010101u, s1); }
-                        bsum = s0 + s1;
-                    }
-                    if (stats) {
-                        // the previous window's median is the guess: one frame in, one out moves it to a neighbouring order statistic
-                        // at most, while the mean of 25 noisy samples misses the +-2 window for some lane of most warps
-                        const int guess = have_prev ? prev_med : __float2int_rn((float)bsum * a.inv_n_sub);
-                        // seven values around the guess resolve a median pair within +-2 of it; lanes it escaped get one more window
-                        // on the side the counts point to (+-3 .. +-7), and only then the whole warp runs the iterative solver
-                        int mlo, mhi, p0, cn[6];
-                        uint32_t fm;
-                        bool ok = band_window<NW, 1, 7>(X, guess, kp1, kp2, cap, mlo, mhi, false, fm, p0, cn);
-                        if (__any_sync(0xffffffffu, !ok && owner)) {
-                            const int g2 = cn[0] > kp1 ? guess - 5 : guess + 5;  // below the window : above it
-                            int mlo2, mhi2;
-                            const bool ok2 = band_window<NW, 1, 7>(X, min(max(g2, 0), 255), kp1, kp2, cap, mlo2, mhi2, false, fm, p0, cn);
-                            if (!ok) { mlo = mlo2; mhi = mhi2; ok = ok2; }
-                        }
-                        med2 = mlo + mhi;
-                        const unsigned nb = __ballot_sync(0xffffffffu, !ok && owner);
-                        if (nb) {  // iterative solver, the whole warp together
-                            if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(nb));
-                            uint32_t tmp[NW];
-#pragma unroll
-                            for (int q = 0; q < NW; q++) tmp[q] = X[q];
-                            int m2 = 0, i4 = 0;
-                            video_solve<NW>(tmp, min(max(guess, 0), 254), a, pad, m2, i4);
-                            if (!ok) med2 = m2;
-                        }
-                        prev_med = med2 >> 1;
-                        have_prev = true;
-                        if (!(w < 0.0f)) {  // exact max |x - centre| (bytes beyond the window read as the centre)
-                            const uint32_t cc = rep4(med2 >> 1);
-                            X[NW - 2] |= cc & ~v.mask_a;
-                            X[NW - 1] |= cc & ~v.mask_b;
-                            uint32_t m0 = 0, m1 = 0;
-#pragma unroll
-                            for (int q = 0; q < NW; q += 2) {
-                                const uint32_t d0 = absdiff4(X[q], cc), d1 = absdiff4(X[q + 1], cc);
-                                m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);  // the high byte of each half is a byte-wise maximum
-                                m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
-                            }
-                            const uint32_t m = __vmaxu2(m0, m1);
-                            odev = max((m >> 8) & 0xffu, m >> 24);
-                        }
-                    }
-                    uint32_t* r = res + ((i * C + c) * rw) * kThreads;
-                    r[0] = (uint32_t)med2 | (odev << 9) | (x_first << 17);
-                    if (rw > 1) r[kThreads] = bsum;  // (4 * IQR stays 0: absolute thresholds)
-                }
-#pragma unroll
-                for (int q = 0; q < NWL; q++) A[q] = A[q + 1];
             }
         }
         video_phase2<C>(v, res, rw, i_lo, i_hi, blk, tile, pix, owner, lane, queue, qcount);

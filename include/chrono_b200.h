@@ -100,6 +100,11 @@ int chb_version(void);
 int chb_ctx_create(const int *device_ids, int n_dev, chb_ctx **out);
 int chb_ctx_destroy(chb_ctx *ctx);
 int chb_ctx_device_count(const chb_ctx *ctx);
+/* Free / total HBM of device slot dev_slot: what a caller sizes its row bands by when a frame series does not fit at once (the
+ * reference is out-of-core by construction, SliceLength::bytes, src/slicer.rs:19-41; here the caller composites the image in
+ * row bands, each band a stack of its own: chb_stack_upload's crop origin selects the band's rows, pixel_offset keeps the
+ * per-pixel RNG aligned). */
+int chb_ctx_mem_info(chb_ctx *ctx, int dev_slot, size_t *free_bytes, size_t *total_bytes);
 /* Use the caller's CUDA stream (cudaStream_t as void*) for device `dev_slot`'s compute work, so the caller can
  * bracket launches with its own events (torch.cuda.Event only sees torch's current stream). NULL = internal stream. */
 int chb_ctx_set_stream(chb_ctx *ctx, int dev_slot, void *cuda_stream);

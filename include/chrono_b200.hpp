@@ -191,6 +191,11 @@ public:
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     chb_ctx* raw() const { return h_; }
+    size_t free_bytes(int dev_slot = 0) const {
+        size_t f = 0, t = 0;
+        check(chb_ctx_mem_info(h_, dev_slot, &f, &t));
+        return f;
+    }
 
 private:
     chb_ctx* h_ = nullptr;
@@ -238,6 +243,9 @@ public:
         return {std::move(buffer), std::move(is_outlier)};
     }
     uint64_t warnings() const { return warnings_; }  // "pixels seem to consist of only outliers", src/chrono.rs:198-203
+    // global index of the stack's first pixel when the stack is one row band of a larger image (keeps the per-pixel RNG of
+    // --background random / --sample aligned with the whole-image result)
+    void set_pixel_offset(uint64_t offset) { pixel_offset_ = offset; }
 
     // chrono-video: n_windows windows of window_len consecutive frames, window i starting at frame first_start + i -- the
     // per-frame loop of create_video (src/main.rs:254-331) in one call (chb_outlier_video). Planes are [n_windows][H*W*C].
@@ -263,6 +271,7 @@ private:
         p.fade = fade_.to_c();
         p.sample_count = sample_ ? (int32_t)*sample_ : -1;
         p.seed = seed_;
+        p.pixel_offset = pixel_offset_;
         return p;
     }
     Threshold threshold_;
@@ -271,7 +280,7 @@ private:
     float w_[4];
     Fade fade_;
     std::optional<size_t> sample_;
-    uint64_t seed_, warnings_ = 0;
+    uint64_t seed_, warnings_ = 0, pixel_offset_ = 0;
 };
 
 // src/simple.rs:11-168

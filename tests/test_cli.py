@@ -183,3 +183,33 @@ def test_cli_shake_png_frames_jpeg_output(tmp_path):
     decoded = np.stack([np.asarray(Image.open(tmp_path / f"j-{i:03d}.jpg").convert("RGB")) for i in range(5)])
     lj = np.asarray(Image.open(tmp_path / "light.png")).astype(int)
     assert np.abs(lj - orc.simple(decoded, False).astype(int)).max() <= 3  # decoders differ in the last bits (IDCT rounding)
+
+
+@pytest.mark.gpu
+def test_cli_row_bands_equal_the_whole_image(tmp_path):
+    """Out of core (the reference's time slices, src/slicer.rs:19-41): a series that does not fit the device is composited in row
+    bands, each a stack of its own. Forced here with CHRONO_B200_BAND_ROWS: same files as the one-stack run, including
+    --background random, whose per-pixel draws are keyed by the global pixel index (pixel_offset)."""
+    build_cli()
+    rng = np.random.default_rng(23)
+    st = make_stack(rng, 21, 29, 44, 3, n_obj=30)
+    for i, fr in enumerate(st):
+        write_ppm(tmp_path / f"image-{i:05d}.ppm", fr)
+    pat = str(tmp_path / "image-*.ppm")
+    for extra in (["-b", "random", "-l", "extreme"], ["-b", "first", "-l", "backward", "-t", "rel/2/4"], ["--mode", "lighter"]):
+        whole, banded = str(tmp_path / "whole.ppm"), str(tmp_path / "banded.ppm")
+        wb, bb = str(tmp_path / "whole_b.ppm"), str(tmp_path / "banded_b.ppm")
+        blend = [] if "--mode" in extra else ["--output-blend"]
+        p = run("--pattern", pat, "--output", whole, *(blend + [wb] if blend else []), *extra)
+        assert p.returncode == 0, p.stderr
+        env = dict(os.environ, CHRONO_B200_BAND_ROWS="7")
+        p = subprocess.run([CLI, "--pattern", pat, "--output", banded, *(blend + [bb] if blend else []), *extra], capture_output=True, text=True, timeout=120, env=env)
+        assert p.returncode == 0, p.stderr
+        assert "row bands of 7 rows" in p.stdout
+        assert np.array_equal(read_ppm(whole), read_ppm(banded)), extra
+        if blend:
+            assert np.array_equal(read_ppm(wb), read_ppm(bb)), extra
+    # a video needs the whole clip resident
+    env = dict(os.environ, CHRONO_B200_BAND_ROWS="7")
+    p = subprocess.run([CLI, "--pattern", pat, "--output", str(tmp_path / "v.ppm"), "--video-in", "0/5/1"], capture_output=True, text=True, timeout=120, env=env)
+    assert p.returncode == 1 and "whole clip resident" in p.stderr

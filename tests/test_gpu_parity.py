@@ -682,6 +682,25 @@ def test_shake_analysis_feeds_crop_and_video(ctx):
     fs.close()
 
 
+def test_certificate_uses_the_exact_maximum_where_the_or_bound_overshoots(ctx):
+    # deviations 8 and 7 from the median in one band: their OR is 15 (15^2 = 225 > thr^2 = 162.6), their maximum 8 (64 < 162.6).
+    # The second pass for the exact byte-wise maximum keeps such pixels on the certified tier: no pixel takes the per-frame path.
+    from chrono_photo_b200 import _lib
+    n, h, w = 40, 8, 64
+    st = np.full((n, h, w, 3), 100, np.uint8)
+    st[7, :, :, 0] = 108
+    st[23, :, :, 0] = 93
+    st[11, 0, :5, :] = 30  # a few real outliers, so that the per-frame path is not empty by construction
+    fs = upload(ctx, st)
+    proc = cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), BG["first"], OM["extreme"])
+    proc.process_device(fs)
+    assert int(_lib.lib().chb_last_slow_pixels()) == 5
+    img, msk = proc.process(fs)
+    oimg, omsk, _ = orc.outlier(st, orc.threshold(True, 0.05, 0.2), BG["first"], OM["extreme"])
+    assert np.array_equal(img, oimg) and np.array_equal(msk, omsk)
+    fs.close()
+
+
 def test_concurrent_callers_like_the_rayon_video_pool(ctx):
     # create_video calls one processor per output frame from a rayon pool (src/main.rs:260-261); decode threads upload
     # distinct frames concurrently. The library must give every caller its own correct result.
@@ -704,6 +723,53 @@ def test_concurrent_callers_like_the_rayon_video_pool(ctx):
     for idx, (img, msk) in zip(wins, got):
         oimg, omsk, _ = orc.outlier(st, t_orc, BG["median"], OM["extreme"], indices=idx)
         assert np.array_equal(img, oimg) and np.array_equal(msk, omsk)
+    fs.close()
+
+
+def test_concurrent_callers_overlap_on_call_slots(ctx):
+    """chb_outlier entered from several host threads (the rayon pool of create_video, src/main.rs:260-261) runs on separate call
+    slots: streams, output planes and queues of their own, so launches, tier kernels and D2H copies of different callers overlap.
+    Same results as serial calls, and more frames per second than one caller gets (1080p, 12-frame windows)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    n, h, w = 40, 1080, 1920
+    fs = cp.FrameStack(ctx, w, h, 3, n)
+    fs.fill_synthetic(2, seed=7)
+    wins = [list(range(s0, s0 + 12)) for s0 in range(0, 24)]
+    thr = cp.Threshold.abs(0.05, 0.2)
+    try:  # pinned result buffers (what a caller that cares about throughput hands over): D2H copies of different callers overlap
+        import torch
+        keep = [torch.empty((2, h, w, 3), dtype=torch.uint8, pin_memory=True) for _ in wins]
+        outs = [(t[0].numpy(), t[1].numpy()) for t in keep]
+    except Exception:
+        outs = [(np.empty((h, w, 3), np.uint8), np.empty((h, w, 3), np.uint8)) for _ in wins]
+
+    def one(k):
+        p = cp.OutlierProcessor(thr, BG["first"], OM["extreme"])
+        p.process(fs, wins[k], out=outs[k][0], mask_out=outs[k][1])
+        return p.warnings
+
+    serial = []
+    for k in range(len(wins)):  # warm-up + the serial reference results
+        one(k)
+        serial.append((outs[k][0].copy(), outs[k][1].copy()))
+    t0 = time.perf_counter()
+    for k in range(len(wins)):
+        one(k)
+    t_serial = time.perf_counter() - t0
+    with ThreadPoolExecutor(6) as pool:
+        list(pool.map(one, range(len(wins))))  # allocates the other call slots
+        t0 = time.perf_counter()
+        list(pool.map(one, range(len(wins))))
+        t_pool = time.perf_counter() - t0
+    for k in range(len(wins)):
+        assert np.array_equal(outs[k][0], serial[k][0]) and np.array_equal(outs[k][1], serial[k][1]), k
+    # a band of the first window against the oracle, so that "equal to serial" is anchored
+    st = np.stack([fs.download(f)[500:516] for f in wins[0]])
+    oimg, omsk, _ = orc.outlier(st, orc.threshold(True, 0.05, 0.2), BG["first"], OM["extreme"])
+    assert np.array_equal(serial[0][0][500:516], oimg) and np.array_equal(serial[0][1][500:516], omsk)
+    print(f"serial {t_serial * 1e3:.1f} ms, 6 threads {t_pool * 1e3:.1f} ms for {len(wins)} windows: x{t_serial / t_pool:.2f}")
+    assert t_pool < t_serial / 1.3, (t_serial, t_pool)
     fs.close()
 
 

@@ -164,22 +164,68 @@ int main(int argc, char** argv) {
                 std::fill(origins.begin(), origins.end(), 0);
             }
         }
-        GpuStack stack(ctx, cw, chh, ch, (int)files.size());
-        for (size_t i = 0; i < files.size(); i++) {
-            const int ox = origins[2 * i], oy = origins[2 * i + 1];
-            if (is_jpeg_path(files[i]) && ch == 3) {  // compressed bytes to the device, decoded there (chb_stack_upload_jpeg checks the layout)
-                const std::vector<uint8_t> bytes = read_file(files[i]);
-                check(chb_stack_upload_jpeg(stack.raw(), (int)i, bytes.data(), bytes.size(), ox, oy));
-            } else {
-                Image im = i == 0 ? first : read_image(files[i], &ctx);
-                if (im.w != fw || im.h != fh || im.c != ch) throw std::runtime_error("Image layout does not fit!");  // src/simple.rs:62-66
-                stack.upload((int)i, im.px.data(), (size_t)im.w * im.c, ox, oy);
+        // Fills a stack of `rows` rows with rows [row0, row0 + rows) of every (cropped) frame
+        auto fill_stack = [&](GpuStack& stack, int row0) {
+            for (size_t i = 0; i < files.size(); i++) {
+                const int ox = origins[2 * i], oy = origins[2 * i + 1] + row0;
+                if (is_jpeg_path(files[i]) && ch == 3) {  // compressed bytes to the device, decoded there (chb_stack_upload_jpeg checks the layout)
+                    const std::vector<uint8_t> bytes = read_file(files[i]);
+                    check(chb_stack_upload_jpeg(stack.raw(), (int)i, bytes.data(), bytes.size(), ox, oy));
+                } else {
+                    Image im = i == 0 ? first : read_image(files[i], &ctx);
+                    if (im.w != fw || im.h != fh || im.c != ch) throw std::runtime_error("Image layout does not fit!");  // src/simple.rs:62-66
+                    stack.upload((int)i, im.px.data(), (size_t)im.w * im.c, ox, oy);
+                }
             }
-        }
-        stack.sync();
-        first.w = cw; first.h = chh;  // the composites have the cropped size
+            stack.sync();
+        };
         auto write_out = [&](const std::string& path, const uint8_t* px) { save_image(px, cw, chh, ch, path, quality, &ctx); };
+        std::optional<std::string> out_blend;
+        if (opt.count("--output-blend")) out_blend = opt["--output-blend"];
+        const bool is_video = video_in || video_out;
 
+        // Out of core, like the reference's time slices (SliceLength::bytes, src/slicer.rs:19-41): when the series does not fit the
+        // device, the image is composited in row bands, each band a stack of its own (the frames are read once per band).
+        // CHRONO_B200_BAND_ROWS forces a band height (tests).
+        const int n_groups = ((int)files.size() + 15) / 16;
+        const size_t bytes_per_row = (size_t)cw * ((size_t)ch * n_groups * 16 + 34 * (size_t)ch + 80);  // stack + staging + planes + queues
+        int band_rows = chh;
+        {
+            const size_t budget = (size_t)(0.85 * (double)ctx.free_bytes());
+            if (bytes_per_row * (size_t)chh > budget) band_rows = (int)std::max<size_t>(1, budget / bytes_per_row);
+            if (const char* e = getenv("CHRONO_B200_BAND_ROWS")) band_rows = std::max(1, std::min(chh, atoi(e)));
+        }
+        if (band_rows < chh) {
+            if (is_video) throw std::runtime_error("The frame series does not fit the device; video output needs the whole clip resident");
+            std::cout << "Processing in row bands of " << band_rows << " rows\n";
+            const size_t row_bytes = (size_t)cw * ch;
+            std::vector<uint8_t> image(row_bytes * chh), blend(mode == SelectionMode::Outlier ? row_bytes * chh : 0);
+            uint64_t warnings = 0;
+            for (int row0 = 0; row0 < chh; row0 += band_rows) {
+                const int rows = std::min(band_rows, chh - row0);
+                GpuStack band(ctx, cw, rows, ch, (int)files.size());
+                fill_stack(band, row0);
+                if (mode == SelectionMode::Outlier) {
+                    OutlierProcessor proc(threshold, background, outlier, w, fade, sample, /*seed=*/0x9E3779B97F4A7C15ULL);
+                    proc.set_pixel_offset((uint64_t)row0 * cw);
+                    auto res = proc.process(band, nullptr);
+                    warnings += proc.warnings();
+                    std::memcpy(&image[row_bytes * row0], res.first.data(), row_bytes * rows);
+                    std::memcpy(&blend[row_bytes * row0], res.second.data(), row_bytes * rows);
+                } else {
+                    SimpleProcessor proc(w, fade, mode == SelectionMode::Darker);
+                    auto res = proc.process(band, nullptr);
+                    std::memcpy(&image[row_bytes * row0], res.data(), row_bytes * rows);
+                }
+            }
+            if (warnings > 0) std::cout << "Warning: " << warnings << " pixels seem to consist of only outliers\n";
+            write_out(opt["--output"], image.data());
+            if (out_blend && mode == SelectionMode::Outlier) write_out(*out_blend, blend.data());
+            return 0;
+        }
+
+        GpuStack stack(ctx, cw, chh, ch, (int)files.size());
+        fill_stack(stack, 0);
         auto run_frame = [&](const std::vector<int32_t>* indices, const std::string& out, const std::optional<std::string>& out_blend) {
             if (mode == SelectionMode::Outlier) {
                 OutlierProcessor proc(threshold, background, outlier, w, fade, sample, /*seed=*/0x9E3779B97F4A7C15ULL);
@@ -192,10 +238,7 @@ int main(int argc, char** argv) {
                 write_out(out, proc.process(stack, indices).data());
             }
         };
-        std::optional<std::string> out_blend;
-        if (opt.count("--output-blend")) out_blend = opt["--output-blend"];
-
-        if (video_in || video_out) {  // create_video / create_video_simple (src/main.rs:214-429)
+        if (is_video) {  // create_video / create_video_simple (src/main.rs:214-429)
             FrameRange vin = video_in.value_or(FrameRange::empty()), vout = video_out.value_or(FrameRange::empty());
             const int cap = 4 * (int)files.size() + 16;
             std::vector<int32_t> ws(cap), we(cap), num(cap);
