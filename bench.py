@@ -594,6 +594,29 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
                 e2e["pageable"] = {"value": e_pf / dt, "unit": "pixel-frames/s", "ms_per_step": dt * 1e3, "uploader_threads": n_thr,
                                    "h2d_gbs": n * fb / dt / 1e9, "path": "pageable host frames -> chb_stack_upload from 8 threads -> kernels -> D2H"}
                 del pageable
+                # JPEG in: the frames cross PCIe compressed and are decoded on the device (chb_stack_upload_jpeg: nvJPEG, Huffman
+                # stage in the calling thread) -- 32 frames (two frame groups) from 8 decode threads, encoded outside the timed region
+                try:
+                    n_j = min(32, n)
+                    jpegs = [cp.encode_jpeg(ctx, host[f].numpy(), quality=90) for f in range(n_j)]
+                    stack3 = cp.FrameStack(ctx, W, e_rows, 3, n_j)
+
+                    def jpeg_step():
+                        with ThreadPoolExecutor(n_thr) as ex:
+                            list(ex.map(lambda f: stack3.upload_jpeg(f, jpegs[f]), range(n_j)))
+                        stack3.sync()
+
+                    jpeg_step()
+                    t0 = time.perf_counter()
+                    jpeg_step()
+                    dt = time.perf_counter() - t0
+                    e2e["jpeg_ingest"] = {"value": float(n_j) * e_rows * W / dt, "unit": "pixel-frames/s", "frames": n_j, "decode_threads": n_thr,
+                                          "ms_per_frame": dt * 1e3 / n_j, "compressed_mb_per_frame": sum(len(j) for j in jpegs) / n_j / 1e6,
+                                          "path": "JPEG bytes (quality 90, 4:2:0) -> chb_stack_upload_jpeg from 8 threads (nvJPEG decode on the device) -> re-layout"}
+                    stack3.close()
+                    del jpegs
+                except Exception as ex:  # the JPEG leg must not take the line with it
+                    e2e["jpeg_ingest"] = {"error": f"{type(ex).__name__}: {ex}"}
             if e_note:
                 e2e["note"] = e_note
             stack2.close()

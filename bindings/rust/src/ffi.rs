@@ -45,6 +45,9 @@ pub struct ChbOutlierParams {
     pub sample_count: i32,
     pub seed: u64,
     pub pixel_offset: u64,
+    /// interleaved row-block shards: pixels per block and pixels between the ends and starts of consecutive owned blocks (0 / 0: one band)
+    pub block_pixels: u64,
+    pub block_skip: u64,
 }
 
 /// chb_simple_params (arguments of SimpleProcessor::new, src/simple.rs:18)
@@ -75,7 +78,7 @@ macro_rules! offset_of {
     }};
 }
 const _: () = assert!(size_of::<ChbFade>() == 24);
-const _: () = assert!(size_of::<ChbOutlierParams>() == 80);
+const _: () = assert!(size_of::<ChbOutlierParams>() == 96);
 const _: () = assert!(size_of::<ChbSimpleParams>() == 48);
 const _: () = assert!(size_of::<ChbDebugPlanes>() == 32);
 #[cfg(test)]
@@ -92,6 +95,8 @@ mod layout {
         assert_eq!(offset_of!(ChbOutlierParams, sample_count), 56);
         assert_eq!(offset_of!(ChbOutlierParams, seed), 64);
         assert_eq!(offset_of!(ChbOutlierParams, pixel_offset), 72);
+        assert_eq!(offset_of!(ChbOutlierParams, block_pixels), 80);
+        assert_eq!(offset_of!(ChbOutlierParams, block_skip), 88);
         assert_eq!(offset_of!(ChbSimpleParams, weights), 4);
         assert_eq!(offset_of!(ChbSimpleParams, fade), 24);
     }

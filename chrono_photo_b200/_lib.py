@@ -22,7 +22,7 @@ class OutlierParams(C.Structure):
     _fields_ = [("thr_absolute", C.c_uint8), ("background", C.c_uint8), ("outlier", C.c_uint8), ("_pad", C.c_uint8),
                 ("thr_min", C.c_float), ("thr_max", C.c_float), ("thr_scale", C.c_float),
                 ("weights", C.c_float * 4), ("fade", Fade), ("sample_count", C.c_int32),
-                ("seed", C.c_uint64), ("pixel_offset", C.c_uint64)]
+                ("seed", C.c_uint64), ("pixel_offset", C.c_uint64), ("block_pixels", C.c_uint64), ("block_skip", C.c_uint64)]
 
 
 class SimpleParams(C.Structure):

@@ -806,6 +806,8 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
                         const chb_debug_planes* dbg, float* kernel_ms, bool enqueue_only = false) {
     if (!st || !prm) return fail(CHB_ERR_INVALID, "chb_outlier: null argument");
     if (prm->background > CHB_BG_MEDIAN || prm->outlier > CHB_OUT_BACKWARD) return fail(CHB_ERR_INVALID, "chb_outlier: unknown background / outlier mode");
+    if ((prm->block_pixels != 0 || prm->block_skip != 0) && (st->bands.size() > 1 || prm->block_pixels == 0))
+        return fail(CHB_ERR_INVALID, "chb_outlier: interleaved row blocks need block_pixels > 0 and a single-device stack (one process per GPU)");
     // the caller owns call slot `slot`: launch and fetch form one critical section per slot
     CallSlot& cs = st->slots[slot];
     Window win;
@@ -957,6 +959,7 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
         ab.wmask = cb.d_wmask; ab.smask = sub ? cb.d_smask : nullptr; ab.win_frames = cb.d_win;
         ab.fade.values = cb.d_fade;
         ab.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
+        ab.block_pixels = prm->block_pixels; ab.block_skip = prm->block_skip;
         ab.out_image = cb.d_out;
         ab.out_mask = want_mask ? cb.d_mask : nullptr;
         ab.counters = reinterpret_cast<unsigned long long*>(cb.d_qcount + 8);
@@ -1297,6 +1300,7 @@ static int video_impl(chb_stack* st, const chb_outlier_params* prm, int first_st
             vb.o.n_pixels = b.n_pixels; vb.o.n_tiles = b.n_tiles;
             vb.o.fade.values = b.call[0].d_fade;
             vb.o.pixel_offset = prm->pixel_offset + (unsigned long long)b.row0 * st->W;
+            vb.o.block_pixels = prm->block_pixels; vb.o.block_skip = prm->block_skip;
             vb.o.counters = b.call[0].d_counters;
             vb.first_start = s_lo; vb.n_windows = cw;
             vb.blk0 = cb0; vb.n_blocks = cb1 - cb0 + 1;

@@ -127,6 +127,7 @@ struct OutlierArgs {
     int hard_inline_min;     // > 0 (G == 1 kernels): same for a warp-full of the iterative tier, finished inside outlier_hard_kernel
     int hist_all;            // 1: outlier_hist_kernel takes every pixel of the band (series beyond the register-resident variants), not a queue
     unsigned long long seed, pixel_offset;
+    unsigned long long block_pixels, block_skip;  // interleaved row-block shards (see chrono_b200.h); 0 / 0: one contiguous band
     uint8_t* out_image;
     uint8_t* out_mask;  // may be null
     unsigned long long* counters;  // [0] warnings (all-outlier pixels), [1] pixels on the exact path, [2] pixels on the iterative (hard) path
@@ -141,6 +142,13 @@ struct OutlierArgs {
     uint32_t* hflags;              // [n_tiles] bit p: pixel p of the tile goes to the iterative tier (zeroed by the host)
     float* dbg_median; float* dbg_q1; float* dbg_q3; int* dbg_nout;
 };
+
+// Global index of local pixel `pix`: what keys the per-pixel random draws, so that a shard draws what the whole image would.
+__device__ __forceinline__ unsigned long long pixel_gid(const OutlierArgs& a, long long pix) {
+    unsigned long long g = pixel_gid(a, pix);
+    if (a.block_pixels) g += ((unsigned long long)pix / a.block_pixels) * a.block_skip;
+    return g;
+}
 
 // ------------------------------------------------------------------------------------------------ exact order statistics
 // A pixel-band's samples sit in registers as packed bytes (4 frames per word), split over G lanes. For a candidate
@@ -1401,7 +1409,7 @@ __device__ __forceinline__ unsigned dense_pixels(const OutlierArgs& a, const uin
     uint32_t maxkey = 0;
     dense_masks_int<C>(a, colbase, bstride, a.contig_f0, a.n, im, ms, k, maxkey);
     uint8_t pixel[4] = {0, 0, 0, 0};
-    const uint8_t mask = finish_masks<C>(a, colbase, bstride, a.pixel_offset + (unsigned long long)pix, median, band_sum, im, ms, a.contig_f0, a.n,
+    const uint8_t mask = finish_masks<C>(a, colbase, bstride, pixel_gid(a, pix), median, band_sum, im, ms, a.contig_f0, a.n,
                                          a.frame_offset, k, maxkey, pixel, warn);
     if (active) {
         store_pixel<C>(a, pix, pixel, mask);
@@ -1434,7 +1442,7 @@ __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry*
         const PixelSrc src{tile_base, a.NG, C, (int)(pix & 31)};
         uint8_t pixel[4] = {0, 0, 0, 0};
         int n_out = 0, warn = 0;
-        const uint8_t mask = exact_pixel<C, true>(a, src, a.pixel_offset + (unsigned long long)pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn, a.contig_f0, a.frame_offset);
+        const uint8_t mask = exact_pixel<C, true>(a, src, pixel_gid(a, pix), e.median, e.iqr_inv, e.sum, pixel, n_out, warn, a.contig_f0, a.frame_offset);
         if (active) {
             store_pixel<C>(a, pix, pixel, mask);
             if (a.dbg_nout) a.dbg_nout[pix] = n_out;
@@ -1590,23 +1598,26 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         // the bound fails with the OR but would hold with the highest set bit of the OR, which the maximum is at least -- the
         // warp takes a second pass for the exact byte-wise maximum (VIMNMX.U16x2: the high byte of each half is a byte maximum).
         // Series whose noise stays below the OR's next power of two (the S2 series at abs/0.05) never take it.
-        {
+        // (absolute thresholds only: with relative ones the term also carries the IQR bound's slack and the pass rarely pays)
+        if (MODE == 1 || (MODE == 0 && a.absolute)) {
             const bool fails = !((acc.bound + t * t) * 1.0001f < a.thr_sq);
-            const float t_lo = aw * ((float)(o ? (1u << (31 - __clz(o))) : 0u) + halfw);
-            const bool could = (acc.bound + t_lo * t_lo) * 1.0001f < a.thr_sq;
-            if (__any_sync(0xffffffffu, fails && could)) {
-                uint32_t m0 = 0, m1 = 0;
+            if (__any_sync(0xffffffffu, fails)) {  // (rare: a tile that touches an object or heavy noise)
+                const float t_lo = aw * ((float)(o ? (1u << (31 - __clz(o))) : 0u) + halfw);
+                const bool could = fails && (acc.bound + t_lo * t_lo) * 1.0001f < a.thr_sq;
+                if (__any_sync(0xffffffffu, could)) {
+                    uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-                for (int q = 0; q < W4; q += 2) {
-                    const uint32_t d0 = absdiff4(A[q], cc), d1 = absdiff4(A[q + 1], cc);
-                    m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);
-                    m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
+                    for (int q = 0; q < W4; q += 2) {
+                        const uint32_t d0 = absdiff4(A[q], cc), d1 = absdiff4(A[q + 1], cc);
+                        m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);
+                        m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
+                    }
+                    const uint32_t m = __vmaxu2(m0, m1);
+                    uint32_t mx = max((m >> 8) & 0xffu, m >> 24);
+#pragma unroll
+                    for (int sh = 32 / G; sh < 32; sh <<= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+                    t = aw * ((float)mx + halfw);
                 }
-                const uint32_t m = __vmaxu2(m0, m1);
-                uint32_t mx = max((m >> 8) & 0xffu, m >> 24);
-#pragma unroll
-                for (int sh = 32 / G; sh < 32; sh <<= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
-                t = aw * ((float)mx + halfw);
             }
         }
         acc.bound += t * t;
@@ -1630,7 +1641,7 @@ __device__ __forceinline__ void finish_pixel(const OutlierArgs& a, const PixelAc
 #pragma unroll
             for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((acc.first_px >> (8 * c)) & 0xffu);  // :348-350
         } else {
-            const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)a.n);  // :357
+            const int pos = (int)rng_range(a.seed, pixel_gid(a, pix), 0, (uint32_t)a.n);  // :357
             const int f = __ldg(a.win_frames + pos);
             const PixelSrc src{a.stack + (pix >> 5) * tile_bytes(C, a.NG), a.NG, C, p_in_tile};
 #pragma unroll
@@ -2226,7 +2237,7 @@ __device__ __noinline__ void drain_video_queue(const VideoArgs& v, const VideoQu
     const int f0 = v.first_start + e.win;  // frame of window position 0 = the window's frame_offset (src/chrono.rs:102-103)
     uint8_t pixel[4] = {0, 0, 0, 0};
     int n_out = 0, warn = 0;
-    const uint8_t mask = exact_pixel(a, src, a.pixel_offset + (unsigned long long)e.pix, e.median, e.iqr_inv, e.sum, pixel, n_out, warn, f0, f0);
+    const uint8_t mask = exact_pixel(a, src, pixel_gid(a, e.pix), e.median, e.iqr_inv, e.sum, pixel, n_out, warn, f0, f0);
     if (active) {
         uint8_t* oi = v.out_images + (long long)e.win * v.out_stride + e.pix * C;
 #pragma unroll
@@ -2318,7 +2329,7 @@ __device__ __forceinline__ void video_phase2(const VideoArgs& v, const uint32_t*
 #pragma unroll
                 for (int c = 0; c < C; c++) pixel[c] = (uint8_t)((r0[c] >> 17) & 0xffu);  // :348-350: window position 0
             } else {
-                const int pos = (int)rng_range(a.seed, a.pixel_offset + (unsigned long long)pix, 0, (uint32_t)n);  // :357
+                const int pos = (int)rng_range(a.seed, pixel_gid(a, pix), 0, (uint32_t)n);  // :357
                 const PixelSrc src{a.stack + (long long)tile * tile_bytes(C, a.NG), a.NG, C, lane};
 #pragma unroll
                 for (int c = 0; c < C; c++) pixel[c] = src.at(v.first_start + win + pos, c);

@@ -153,7 +153,7 @@ class OutlierProcessor:
     """OutlierProcessor::new (src/chrono.rs:46-54). `compression` is accepted and ignored (there are no temp files)."""
 
     def __init__(self, threshold, bg_mode, outlier_mode, weights=(1.0, 1.0, 1.0, 1.0), fade=None, compression=None,
-                 sample_count=None, seed=0, pixel_offset=0):
+                 sample_count=None, seed=0, pixel_offset=0, block_pixels=0, block_skip=0):
         if not isinstance(threshold, Threshold):
             raise TypeError("threshold must be a Threshold")
         self.threshold = threshold
@@ -164,6 +164,7 @@ class OutlierProcessor:
         self.sample_count = sample_count
         self.seed = int(seed)
         self.pixel_offset = int(pixel_offset)
+        self.block_pixels, self.block_skip = int(block_pixels), int(block_skip)  # interleaved row-block shards (chrono_b200.h)
         self.warnings = 0
         self.kernel_ms = None
 
@@ -179,6 +180,7 @@ class OutlierProcessor:
         p.sample_count = -1 if self.sample_count is None else int(self.sample_count)
         p.seed = self.seed
         p.pixel_offset = self.pixel_offset
+        p.block_pixels, p.block_skip = self.block_pixels, self.block_skip
         return p
 
     def process(self, stack, image_indices=None, want_mask=True, debug=False, out=None, mask_out=None):

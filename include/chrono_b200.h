@@ -15,7 +15,12 @@
  * failing call on the calling thread. The caller owns every host buffer; the library owns device memory.
  * There is no CPU fallback: without a CUDA device chb_ctx_create fails with CHB_ERR_CUDA.
  * chb_outlier / chb_simple may be entered concurrently from several host threads on one stack (the
- * reference's video path calls the processors from a rayon pool, src/main.rs:260-261, :378-379).
+ * reference's video path calls the processors from a rayon pool, src/main.rs:260-261, :378-379): a stack
+ * owns four call slots (stream, output planes, tables, queues), so up to four such calls overlap their
+ * launches, tier kernels and D2H copies; further callers wait for a slot. The device-side entry points
+ * (chb_*_device, chb_outlier_enqueue, chb_stack_wait, chb_fetch_last*, chb_outlier_video*) are defined on
+ * "the last call" of the stack and serialise on slot 0. Compositing launches order themselves after the
+ * uploads issued before them (no chb_stack_sync needed in between).
  */
 #ifndef CHRONO_B200_H
 #define CHRONO_B200_H
@@ -27,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CHB_VERSION 100 /* 0.1.0 */
+#define CHB_VERSION 200 /* 0.2.0 */
 
 enum chb_status {
     CHB_OK = 0,
@@ -71,6 +76,12 @@ typedef struct chb_outlier_params {
     int32_t sample_count; /* --sample: median/IQR on this many randomly chosen frames of the window; <0 = all */
     uint64_t seed;        /* counter-based RNG seed for --background random and --sample (the reference uses thread_rng) */
     uint64_t pixel_offset; /* global index of this stack's pixel 0; lets row shards in separate processes draw the same numbers */
+    /* Interleaved row-block shards (GPU g of G owns the blocks of B rows with index = g mod G, so that objects spread evenly over
+     * the GPUs): the stack then holds blocks of block_pixels = B * image_width pixels that lie block_pixels + block_skip apart
+     * in the whole image (block_skip = (G - 1) * block_pixels) and pixel_offset = g * block_pixels. The global index of local
+     * pixel p is pixel_offset + p + (p / block_pixels) * block_skip. 0 / 0 = one contiguous band (single-device stacks only). */
+    uint64_t block_pixels;
+    uint64_t block_skip;
 } chb_outlier_params;
 
 /* Arguments of SimpleProcessor::new (src/simple.rs:18). */
@@ -213,7 +224,7 @@ int chb_decode_jpeg(chb_ctx *ctx, const uint8_t *jpeg, size_t n_bytes, uint8_t *
                     int *out_width, int *out_height);
 
 /* Tuning / test knobs (not needed for normal use; initial values come from the environment variables CHB_<KEY> read once at
- * load time): "force_variant", "hist", "pdl", "video_queue_cap", "inline_min"; value -1 = automatic. */
+ * load time): "force_variant", "hist", "pdl", "video_queue_cap", "inline_min", "hard_inline_min"; value -1 = automatic. */
 int chb_set_tuning(const char *key, int value);
 
 /* The --sample subset the library draws for (seed, window length n, cnt): cnt ascending positions in [0, n).

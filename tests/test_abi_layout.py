@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STRUCTS = {
     "chb_fade": (_lib.Fade, "ChbFade", ["is_none", "mode", "absolute", "offset", "n_values", "values"]),
     "chb_outlier_params": (_lib.OutlierParams, "ChbOutlierParams",
-                           ["thr_absolute", "background", "outlier", "thr_min", "thr_max", "thr_scale", "weights", "fade", "sample_count", "seed", "pixel_offset"]),
+                           ["thr_absolute", "background", "outlier", "thr_min", "thr_max", "thr_scale", "weights", "fade", "sample_count", "seed", "pixel_offset", "block_pixels", "block_skip"]),
     "chb_simple_params": (_lib.SimpleParams, "ChbSimpleParams", ["darker", "weights", "fade"]),
     "chb_debug_planes": (_lib.DebugPlanes, "ChbDebugPlanes", ["median", "q1", "q3", "n_outliers"]),
 }

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(l, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
-    assert l.chb_version() == 100
+    assert l.chb_version() == 200
 
 
 def test_no_cpu_fallback():

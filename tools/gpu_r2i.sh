@@ -10,7 +10,7 @@ stamp() { echo "[$(( $(date +%s) - t0 )) s] $*" | tee -a $OUT/timeline.txt; }
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt; nproc >> $OUT/gpu.txt
 
 stamp "pytest -m gpu"
-timeout 1200 python -m pytest tests/ -x -q -m gpu > $OUT/pytest_gpu.txt 2>&1; echo "exit $?" >> $OUT/pytest_gpu.txt
+timeout 1200 python -m pytest tests/ -x -q -m gpu -s > $OUT/pytest_gpu.txt 2>&1; echo "exit $?" >> $OUT/pytest_gpu.txt
 tail -4 $OUT/pytest_gpu.txt
 stamp "smoke"
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.txt 2>&1; echo "exit $?" >> $OUT/smoke.txt
@@ -50,6 +50,12 @@ stamp "ncu launch lists a4 / c4"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_a4.csv python tools/launch_times.py 4000 6000 200 0 4 > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_c4.csv python tools/launch_times.py 2160 3840 1000 1 > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_a1.csv python tools/launch_times.py 2048 2048 200 0 3 > /dev/null 2>&1
+stamp "ncu full a1 outlier_hard_kernel"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:^outlier_hard_kernel -s 1 -c 1 -f -o $OUT/ncu_hard_a1 \
+  python tools/launch_times.py 2048 2048 200 0 3 > $OUT/ncu_hard_a1.log 2>&1
+stamp "band of 500 rows (one eighth of c3): launch list + per-band times"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/launches_band500.csv python tools/small_band_once.py > $OUT/band500.log 2>&1
+timeout 200 python tools/small_band.py > $OUT/small_band.txt 2>&1; tail -8 $OUT/small_band.txt
 stamp "ncu full c5 video_kernel"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:^video_kernel -s 1 -c 1 -f -o $OUT/ncu_video_c5 \
   python tools/prof_c5_ncu.py > $OUT/ncu_video_c5.log 2>&1
