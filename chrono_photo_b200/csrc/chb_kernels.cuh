@@ -145,7 +145,7 @@ struct OutlierArgs {
 
 // Global index of local pixel `pix`: what keys the per-pixel random draws, so that a shard draws what the whole image would.
 __device__ __forceinline__ unsigned long long pixel_gid(const OutlierArgs& a, long long pix) {
-    unsigned long long g = pixel_gid(a, pix);
+    unsigned long long g = a.pixel_offset + (unsigned long long)pix;
     if (a.block_pixels) g += ((unsigned long long)pix / a.block_pixels) * a.block_skip;
     return g;
 }
