@@ -216,11 +216,13 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA side
-def make_processor(cp, mode, seed=42, pixel_offset=0):
+def make_processor(cp, mode, seed=42, pixel_offset=0, **shard_args):
     if mode in ("outlier", "outlier-c1", "video"):
-        return cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), cp.BackgroundMode.FIRST, cp.OutlierSelectionMode.EXTREME, seed=seed, pixel_offset=pixel_offset)
+        return cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), cp.BackgroundMode.FIRST, cp.OutlierSelectionMode.EXTREME, seed=seed, pixel_offset=pixel_offset,
+                                   **shard_args)
     if mode == "outlier-rel":
-        return cp.OutlierProcessor(cp.Threshold.rel(3.0, 5.0), cp.BackgroundMode.FIRST, cp.OutlierSelectionMode.ALL_FORWARD, seed=seed, pixel_offset=pixel_offset)
+        return cp.OutlierProcessor(cp.Threshold.rel(3.0, 5.0), cp.BackgroundMode.FIRST, cp.OutlierSelectionMode.ALL_FORWARD, seed=seed, pixel_offset=pixel_offset,
+                                   **shard_args)
     return cp.SimpleProcessor(darker=(mode == "darker"))
 
 
@@ -340,7 +342,7 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
     import numpy as np
     import chrono_photo_b200 as cp
     from chrono_photo_b200 import _lib
-    from chrono_photo_b200.sharding import shard_rows
+    from chrono_photo_b200.sharding import InterleavedShard, deinterleave, interleave_block_rows, shard_rows
     torch, dist = env.torch, env.dist
     mode, n, H_img, W, kind, desc = WORKLOADS[wl]
     is_outlier = mode.startswith("outlier")
@@ -348,7 +350,17 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
     weak = scaling == "weak" and env.shard_world > 1
     H = H_img * env.shard_world if weak else H_img
     row0, rows = (env.shard_rank * H_img, H_img) if weak else shard_rows(H_img, env.shard_rank, env.shard_world)
-    key = (kind, n, rows, W, row0, H)
+    # strong scaling: GPU g owns the row blocks with index = g mod G (objects are compact in the image: contiguous bands leave the
+    # GPU whose band holds the most object pixels defining the step); contiguous bands when the image does not divide
+    def strong_shard():
+        b = interleave_block_rows(H_img, env.shard_world) if (env.shard_world > 1 and os.environ.get("CHB_BENCH_CONTIGUOUS", "0") != "1") else None
+        return InterleavedShard(H_img, W, env.shard_rank, env.shard_world, b) if b else None
+    ishard = None if weak else strong_shard()
+    if ishard:
+        row0, rows = ishard.row0, ishard.rows
+    fill_args = ishard.fill_args() if ishard else dict(row0_global=row0, full_height=H)
+    proc_args = ishard.processor_args() if ishard else dict(pixel_offset=row0 * W)
+    key = (kind, n, rows, W, row0, H, ishard.block_rows if ishard else 0)
     ctx = shared.get("ctx") if shared else None
     own_ctx = ctx is None
     if own_ctx:
@@ -368,10 +380,10 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
         if weak:  # every band is its own full-size series of the workload's recipe, seeds 42 + rank
             stack.fill_synthetic(kind, seed=42 + env.shard_rank, row0_global=0, full_height=H_img)
         else:
-            stack.fill_synthetic(kind, seed=42, row0_global=row0, full_height=H)
+            stack.fill_synthetic(kind, seed=42, **fill_args)
         if shared is not None:
             shared[("stack", key)] = stack
-    proc = make_processor(cp, mode, pixel_offset=row0 * W)
+    proc = make_processor(cp, mode, **(proc_args if is_outlier else {}))
 
     def timed_steps(st, pr):
         for _ in range(warmup):
@@ -431,12 +443,14 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
     other_scaling = None
     if env.shard_world > 1 and primary:
         if weak:  # the workload's own image cut into N bands
-            o_row0, o_rows = shard_rows(H_img, env.shard_rank, env.shard_world)
+            o_sh = strong_shard()
+            o_row0, o_rows = (o_sh.row0, o_sh.rows) if o_sh else shard_rows(H_img, env.shard_rank, env.shard_world)
             o_stack = cp.FrameStack(ctx, W, o_rows, 3, n)
-            o_stack.fill_synthetic(kind, seed=42, row0_global=o_row0, full_height=H_img)
-            o_ms, _ = timed_steps(o_stack, make_processor(cp, mode, pixel_offset=o_row0 * W))
+            o_stack.fill_synthetic(kind, seed=42, **(o_sh.fill_args() if o_sh else dict(row0_global=o_row0, full_height=H_img)))
+            o_pargs = (o_sh.processor_args() if o_sh else dict(pixel_offset=o_row0 * W)) if is_outlier else {}
+            o_ms, _ = timed_steps(o_stack, make_processor(cp, mode, **o_pargs))
             other_scaling = ("strong_scaling", {"value": float(n) * H_img * W / (o_ms / 1e3), "unit": "pixel-frames/s", "ms_per_step": o_ms,
-                                                "image": f"{W}x{H_img} cut into {n_gpus} bands of {o_rows} rows"})
+                                                "image": f"{W}x{H_img} cut into {n_gpus} shards of {o_rows} rows" + (f" (interleaved blocks of {o_sh.block_rows} rows)" if o_sh else "")})
         else:  # every rank a full-size band of an N-times taller image
             o_stack = cp.FrameStack(ctx, W, H_img, 3, n)
             o_stack.fill_synthetic(kind, seed=42 + env.shard_rank, row0_global=0, full_height=H_img)
@@ -448,7 +462,11 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
     # ---- gather helpers (N > 1 under torchrun): device bands -> rank 0 over NCCL -> pinned host image
     frame_bytes = rows * W * 3
     d_img = d_msk = g_img = g_msk = None
-    equal_bands = all(shard_rows(H_img, r, env.shard_world)[1] == rows for r in range(env.shard_world))
+    equal_bands = ishard is not None or all(shard_rows(H_img, r, env.shard_world)[1] == rows for r in range(env.shard_world))
+
+    def assemble(parts):  # rank 0: the gathered shards in rank order -> the image
+        return deinterleave(torch.stack(parts), ishard.block_rows) if ishard else torch.cat(parts)
+
     if env.multi_proc and not weak and equal_bands:
         d_img = torch.empty((rows, W, 3), dtype=torch.uint8, device="cuda")
         d_msk = torch.empty((rows, W, 3), dtype=torch.uint8, device="cuda") if is_outlier else None
@@ -479,8 +497,8 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
             gms = env.max_over_ranks(gather_last(stack))
             vinfo["gather_ms"] = gms
             if env.rank == 0:
-                full_img = torch.cat(g_img).cpu().numpy()
-                full_msk = torch.cat(g_msk).cpu().numpy() if g_msk is not None else None
+                full_img = assemble(g_img).cpu().numpy()
+                full_msk = assemble(g_msk).cpu().numpy() if g_msk is not None else None
                 # rank 0's own single-GPU result of the whole image
                 s1 = cp.FrameStack(ctx, W, H_img, 3, n)
                 s1.fill_synthetic(kind, seed=42, row0_global=0, full_height=H_img)
@@ -546,9 +564,9 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
                         proc.process_device(stack2)
                     gather_ms.append(gather_last(stack2))
                     if env.rank == 0:
-                        out_t.copy_(torch.cat(g_img), non_blocking=True)
+                        out_t.copy_(assemble(g_img), non_blocking=True)
                         if g_msk is not None:
-                            msk_t.copy_(torch.cat(g_msk), non_blocking=True)
+                            msk_t.copy_(assemble(g_msk), non_blocking=True)
                         torch.cuda.synchronize()
                 elif is_outlier:
                     proc.process(stack2, out=out_np, mask_out=msk_np)
@@ -630,7 +648,8 @@ def run_photo(env, wl, steps, warmup, e2e_steps, do_e2e, do_cpu, cpu_target_s, d
 
     cfg = config_of(wl)
     cfg_run = {"sharding": (f"{n_gpus} bands of {rows} rows: a {W}x{H} image, every GPU owns one full-size band of the workload" if weak
-                            else f"{W}x{H_img} image cut into {n_gpus} band(s) of {rows} rows"),
+                            else (f"{W}x{H_img} image cut into {n_gpus} shards of {rows} rows: GPU g owns the blocks of {ishard.block_rows} rows with index = g mod {n_gpus}"
+                                  if ishard else f"{W}x{H_img} image cut into {n_gpus} band(s) of {rows} rows")),
                "launcher": "torchrun" if env.multi_proc else "single-process", "stack_gb_per_gpu": stack.device_bytes(0) / 1e9,
                "cpus_bound_per_rank": env.cpu_affinity}
     out = {"metric": "pixel-frames/s", "value": value, "unit": "pixel-frames/s", "n_gpus": n_gpus, "steps": steps, "warmup": warmup,

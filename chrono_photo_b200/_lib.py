@@ -52,6 +52,7 @@ SYMBOLS = {
     "chb_stack_download": (_i, [_vp, _i, _vp, C.c_size_t]),
     "chb_stack_sync": (_i, [_vp]),
     "chb_stack_fill_synthetic": (_i, [_vp, _i, C.c_uint64, _i, _i]),
+    "chb_stack_fill_synthetic_blocks": (_i, [_vp, _i, C.c_uint64, _i, _i, _i, _i]),
     "chb_synth_frame_host": (_i, [_i, C.c_uint64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "chb_outlier": (_i, [_vp, C.POINTER(OutlierParams), _i32p, _i, _vp, _vp, _u64p]),
     "chb_outlier_debug": (_i, [_vp, C.POINTER(OutlierParams), _i32p, _i, _vp, _vp, _u64p, C.POINTER(DebugPlanes)]),

@@ -49,10 +49,11 @@ struct Tuning {
     std::atomic<int> video_queue_cap{-1};  // CHB_VIDEO_QUEUE_CAP: capacity of the video exact-path queue (tests the in-place fallback)
     std::atomic<int> inline_min{12};       // CHB_INLINE_MIN: uncertified pixels per tile from which the tile is finished inside K1 (0 = never)
     std::atomic<int> hard_inline_min{1};   // CHB_HARD_INLINE_MIN: same for a warp-full of the iterative tier (finished inside outlier_hard_kernel)
+    std::atomic<int> hard_drains{1};       // CHB_HARD_DRAINS: outlier_hard_kernel also drains the streaming kernel's own queue (no exact-path launch)
     Tuning() {
         auto env = [](const char* k, std::atomic<int>& v) { if (const char* e = getenv(k)) v.store(atoi(e)); };
         env("CHB_FORCE_VARIANT", force_variant); env("CHB_HIST", hist); env("CHB_PDL", pdl);
-        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min); env("CHB_HARD_INLINE_MIN", hard_inline_min);
+        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min); env("CHB_HARD_INLINE_MIN", hard_inline_min); env("CHB_HARD_DRAINS", hard_drains);
     }
 };
 static Tuning g_tune;
@@ -65,6 +66,7 @@ extern "C" int chb_set_tuning(const char* key, int value) {
     else if (k == "video_queue_cap") g_tune.video_queue_cap.store(value);
     else if (k == "inline_min") g_tune.inline_min.store(value);
     else if (k == "hard_inline_min") g_tune.hard_inline_min.store(value);
+    else if (k == "hard_drains") g_tune.hard_drains.store(value);
     else return fail(CHB_ERR_INVALID, "chb_set_tuning: unknown key '%s'", key);
     return CHB_OK;
 }
@@ -642,15 +644,25 @@ extern "C" int chb_stack_sync(chb_stack* st) {
 }
 
 extern "C" int chb_stack_fill_synthetic(chb_stack* st, int kind, uint64_t seed, int row0_global, int full_height) {
+    return chb_stack_fill_synthetic_blocks(st, kind, seed, row0_global, full_height, 0, 0);
+}
+
+// Same series for an interleaved row-block shard (chb_outlier_params.block_pixels): local row r of the stack is row
+// row0_global + r + (r / block_rows) * block_skip_rows of the whole image.
+extern "C" int chb_stack_fill_synthetic_blocks(chb_stack* st, int kind, uint64_t seed, int row0_global, int full_height, int block_rows,
+                                               int block_skip_rows) {
     if (!st) return fail(CHB_ERR_INVALID, "chb_stack_fill_synthetic: null stack");
     if (kind < 1 || kind > 4) return fail(CHB_ERR_INVALID, "chb_stack_fill_synthetic: unknown kind %d", kind);
+    if (block_rows < 0 || block_skip_rows < 0 || (block_rows > 0 && st->bands.size() > 1))
+        return fail(CHB_ERR_INVALID, "chb_stack_fill_synthetic_blocks: interleaved row blocks need a single-device stack");
     std::lock_guard<std::mutex> lk(st->upload_mu);
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CU(cudaSetDevice(d.id));
         const long long units = b.n_tiles * st->C * st->NG * kTilePixels;
         synth_fill_kernel<<<grid_for(units, 256, d.sm_count, 16), 256, 0, d.pack>>>(b.d_stack, b.n_pixels, b.n_tiles, st->C, st->NG, st->N, kind,
-                                                                                   (unsigned long long)seed, st->W, row0_global + b.row0, full_height);
+                                                                                   (unsigned long long)seed, st->W, row0_global + b.row0, full_height,
+                                                                                   block_rows, block_skip_rows);
         g_launches++;
         CU(cudaGetLastError());
     }
@@ -1011,6 +1023,9 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
         compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(cb.d_hflags, b.n_tiles, cb.d_hqueue, cb.d_qcount + 1);
         bool use_hist = kmode == 2 && n >= 256;
         if (g_tune.hist.load() >= 0) use_hist = kmode != 0 && n >= 256 && g_tune.hist.load() != 0;
+        // with the dense per-frame pass in the iterative tier's kernel (every uncertified pixel of its warp-fulls finished in place)
+        // that kernel also takes the streaming kernel's own queue and the exact-path launch is dropped
+        ab.hard_drains_all = (!use_hist && ab.mask_path && var.g == 1 && kmode != 2 && ab.hard_inline_min == 1 && g_tune.hard_drains.load() != 0) ? 1 : 0;
         // the two tier kernels are programmatic dependent launches: their CTAs become resident while the previous kernel's
         // last CTAs drain and wait (griddepcontrol.wait) for its results, which hides two launch latencies per call
         const bool use_pdl = g_tune.pdl.load() != 0;
@@ -1032,8 +1047,8 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
             }
             CU(launch_dep(hard_kern, blocks, kWarpsPerCta * 32, smem));
         }
-        CU(launch_dep(st->C == 3 ? outlier_exact_kernel<3> : outlier_exact_kernel<4>, d.sm_count * 4, 256, 0));
-        g_launches += 4;
+        if (!ab.hard_drains_all) CU(launch_dep(st->C == 3 ? outlier_exact_kernel<3> : outlier_exact_kernel<4>, d.sm_count * 4, 256, 0));
+        g_launches += ab.hard_drains_all ? 3 : 4;
         CU(cudaGetLastError());
         CU(cudaEventRecord(cb.ev1, s));
         CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, cb.d_qcount + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));

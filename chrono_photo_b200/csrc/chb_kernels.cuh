@@ -126,6 +126,7 @@ struct OutlierArgs {
     int inline_min;          // > 0 (G == 1 kernels): a tile with at least this many uncertified pixels is finished inside the streaming kernel
     int hard_inline_min;     // > 0 (G == 1 kernels): same for a warp-full of the iterative tier, finished inside outlier_hard_kernel
     int hist_all;            // 1: outlier_hist_kernel takes every pixel of the band (series beyond the register-resident variants), not a queue
+    int hard_drains_all;     // 1: outlier_hard_kernel also finishes the pixels the streaming kernel queued itself (dense pass): no outlier_exact_kernel launch
     unsigned long long seed, pixel_offset;
     unsigned long long block_pixels, block_skip;  // interleaved row-block shards (see chrono_b200.h); 0 / 0: one contiguous band
     uint8_t* out_image;
@@ -1418,7 +1419,7 @@ __device__ __forceinline__ unsigned dense_pixels(const OutlierArgs& a, const uin
     return __ballot_sync(0xffffffffu, active && warn);
 }
 
-template <int C>
+template <int C, bool MASK_ONLY = false>
 __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry* slot, bool in_range, int lane, const MaskSlots ms) {
     long long pix = in_range ? slot->pix : -1;
     const bool active = pix >= 0;
@@ -1431,13 +1432,13 @@ __device__ __noinline__ void drain_queue(const OutlierArgs& a, const QueueEntry*
     const long long tile = pix >> 5;
     const uint8_t* tile_base = a.stack + tile * tile_bytes(C, a.NG);
     unsigned wb;
-    if (a.mask_path) {
+    if (MASK_ONLY || a.mask_path) {
         float median[4];
         uint32_t sum[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) { median[c] = slot->median[c]; sum[c] = slot->sum[c]; }
         wb = dense_pixels<C>(a, tile_base + (pix & 31) * kUnitBytes, pix, active, median, sum, ms);
-    } else {
+    } else if (!MASK_ONLY) {
         const QueueEntry e = *slot;
         const PixelSrc src{tile_base, a.NG, C, (int)(pix & 31)};
         uint8_t pixel[4] = {0, 0, 0, 0};
@@ -1904,6 +1905,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, CHB_HARD_MINB) outlier_hard
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PPW; base < total; base += n_warps * PPW)
         drain_hard<C, WPL, G, MODE>(a, base, (int)min((unsigned int)PPW, total - base), lane, cap, pad, acc_slot, ms);
+    // The pixels the streaming kernel queued itself (certificate failed, median inside its window) sit at the far end of the
+    // exact-path queue. With the dense per-frame pass available (mask_path; every pixel of this tier's own warp-fulls is then
+    // finished in drain_hard) this kernel takes them as well -- starting with the warps that got no or few iterative-tier
+    // pixels -- and the call needs no outlier_exact_kernel launch: one launch latency less per call.
+    if (G == 1 && MODE != 2 && a.hard_drains_all) {
+        const unsigned int extra = a.gq_count[0];
+        const unsigned int w = n_warps - 1u - ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+        for (unsigned int base = w * 32u; base < extra; base += n_warps * 32u) {
+            const unsigned int v = base + lane;
+            const bool in_range = v < extra;
+            drain_queue<C, true>(a, a.gq + (a.n_pixels - 1 - (long long)(in_range ? v : base)), in_range, lane, ms);
+        }
+    }
 }
 
 // Iterative tier for long whole-stack series (hundreds of frames): instead of the solver's repeated passes over the pixel's
@@ -2228,6 +2242,75 @@ __device__ __noinline__ VideoCounts video_recount(const uint32_t* xl, int center
     return r;
 }
 
+// 4 * IQR of the window from its counts (quartiles, src/chrono.rs:559-579, are multiples of 1/4)
+__device__ __forceinline__ int video_iq4(const OutlierArgs& a, const VideoCounts& cn) {
+    const int q1a = stat_at(cn, rep4(127 - a.rk[0])), q3a = stat_at(cn, rep4(127 - a.rk[4]));
+    const int q1b = (a.rk[0] == a.rk[1]) ? q1a : stat_at(cn, rep4(127 - a.rk[1]));
+    const int q3b = (a.rk[4] == a.rk[5]) ? q3a : stat_at(cn, rep4(127 - a.rk[5]));
+    const float q1 = (a.rk[0] == a.rk[1]) ? (float)q1a : (1.0f - a.q1_frac) * (float)q1a + a.q1_frac * (float)q1b;
+    const float q3 = (a.rk[4] == a.rk[5]) ? (float)q3a : (1.0f - a.q3_frac) * (float)q3a + a.q3_frac * (float)q3b;
+    return __float2int_rn((q3 - q1) * 4.0f);
+}
+
+// The uncommon cases of one (window, band), the whole warp together: a rank outside the counted values -> iterative solver,
+// then counts around the exact median; samples beyond the counted values -> the window is scanned for the exact maximum
+// deviation (or, for one or two such pixels, they get the pessimistic bound and take the exact path: most of them hold an
+// outlier anyway). X: the window's words, positions >= n zeroed.
+struct VideoSlowIO {  // (lives in local memory, and only on the uncommon path: the caller copies in and out)
+    VideoCounts cn;
+    int med2, iq4;
+    uint32_t odev;
+};
+template <int NW>
+__device__ __noinline__ void video_window_slow(const VideoArgs& v, const uint32_t* X, float w, bool live, int lane, int pad, VideoSlowIO* io) {
+    const OutlierArgs& a = v.o;
+    const int n = a.n;
+    VideoCounts cn = io->cn;
+    const int r_lo = a.absolute ? a.rk[2] : a.rk[0], r_hi = a.absolute ? a.rk[3] : a.rk[5];  // smallest / largest rank a band needs
+    const bool ok = ((int)(cn.c0 & 0xffu) <= r_lo || cn.p == 0) && ((int)(cn.c3 >> 24) > r_hi);
+    int med2 = 0, iq4 = 0;
+    uint32_t odev = 0;
+    bool solved = false;
+    const unsigned nb = __ballot_sync(0xffffffffu, !ok && live);
+    if (nb) {
+        if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(nb));
+        int m2 = 0, i4 = 0;
+        video_solve<NW>(X, min(cn.p + 8, 254), a, pad, m2, i4);
+        const VideoCounts rc = video_recount<NW>(X, m2 >> 1, n);
+        if (!ok) { cn = rc; med2 = m2; iq4 = i4; solved = true; }
+    }
+    if (!solved) {
+        const int mlo = stat_at(cn, rep4(127 - a.rk[2]));
+        const int mhi = (a.rk[2] == a.rk[3]) ? mlo : stat_at(cn, rep4(127 - a.rk[3]));
+        med2 = mlo + mhi;
+        if (!a.absolute) iq4 = video_iq4(a, cn);
+    }
+    if (!(w < 0.0f)) {
+        const int center = med2 >> 1;
+        const bool in_range = ((cn.c0 & 0xffu) == 0u || cn.p == 0) && ((int)(cn.c3 >> 24) == n);
+        const int minv = stat_at(cn, rep4(127)), maxv = stat_at(cn, rep4(127 - (n - 1)));
+        odev = (uint32_t)max(center - minv, maxv - center);
+        const unsigned ob = __ballot_sync(0xffffffffu, !in_range && live);
+        if (__popc(ob) >= 3) {  // many pixels with samples beyond the counted values: scan the window
+            const uint32_t cc = rep4(center);
+            uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+            for (int q = 0; q < NW; q += 2) {
+                uint32_t x0 = X[q], x1 = X[q + 1];
+                if (q == NW - 2) { x0 |= cc & ~v.mask_a; x1 |= cc & ~v.mask_b; }
+                const uint32_t d0 = absdiff4(x0, cc), d1 = absdiff4(x1, cc);
+                m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);  // the high byte of each half is a byte-wise maximum
+                m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
+            }
+            const uint32_t m = __vmaxu2(m0, m1);
+            if (!in_range) odev = max((m >> 8) & 0xffu, m >> 24);
+        } else if (!in_range) {
+            odev = 255;
+        }
+    }
+    io->cn = cn; io->med2 = med2; io->iq4 = iq4; io->odev = odev;
+}
+
 template <int C>
 __device__ __noinline__ void drain_video_queue(const VideoArgs& v, const VideoQueueEntry* q, int count, int lane) {
     const OutlierArgs& a = v.o;
@@ -2375,9 +2458,10 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
     const bool rel = !a.absolute;
     // rank constants of stat_at(): median pair, quartile pairs, smallest and largest sample
     const uint32_t kk_m1 = rep4(127 - a.rk[2]), kk_m2 = rep4(127 - a.rk[3]);
-    const uint32_t kk_q1a = rep4(127 - a.rk[0]), kk_q1b = rep4(127 - a.rk[1]), kk_q3a = rep4(127 - a.rk[4]), kk_q3b = rep4(127 - a.rk[5]);
     const uint32_t kk_min = rep4(127), kk_max = rep4(127 - (n - 1));
     const int r_lo = rel ? a.rk[0] : a.rk[2], r_hi = rel ? a.rk[5] : a.rk[3];  // smallest / largest rank a band needs
+    const bool one_rank = a.rk[2] == a.rk[3];
+    const int n_word = n >> 2, n_shift = 8 * (n & 3);  // window position n: word NW-2 .. NW of the window's words, and its byte
     int qcount = 0;
     for (int task = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); task < n_tasks; task += n_warps) {
         const int tile = task / v.n_blocks;
@@ -2387,7 +2471,13 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
         const uint8_t* tb = a.stack + (long long)tile * tile_bytes(C, a.NG) + lane * kUnitBytes;
         const int i_lo = max(0, v.first_start - blk * kVideoBlock);                            // windows of this block that belong to the run
         const int i_hi = min(kVideoBlock, v.first_start + v.n_windows - blk * kVideoBlock);
-        // ---- phase 1, band by band: the band's bytes in registers, the window slides over them
+        // windows of the run (bit i), none for lanes beyond the band's last pixel: only those vote for the uncommon path
+        const uint32_t live_mask = (owner && i_hi > i_lo) ? (((1u << i_hi) - 1u) & ~((1u << i_lo) - 1u)) : 0u;  // 0 <= i_lo < i_hi <= 16
+        // ---- phase 1, band by band: the band's bytes in registers, the window slides over them. All 16 windows of the block
+        // are evaluated (phase 2 only reads those of the run), four at a time with the window's byte offset inside A[0] a
+        // compile-time constant; the words rotate once per four windows. The common case -- every rank and the smallest /
+        // largest sample inside the counted values -- is straight-line code behind ONE warp vote; everything else (solver,
+        // re-centred counts, window scan) lives in video_window_slow.
 #pragma unroll 1
         for (int c = 0; c < C; c++) {
             uint32_t A[NWL];
@@ -2397,108 +2487,70 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
                 if (blk + k < a.NG) u = ldg_stream(tb + ((long long)c * a.NG + (blk + k)) * (kTilePixels * kUnitBytes));
                 A[4 * k] = u.x; A[4 * k + 1] = u.y; A[4 * k + 2] = u.z; A[4 * k + 3] = u.w;
             }
-            for (int r = 0; r < (i_lo >> 2); r++) {  // skip the words in front of the first window of the run
-#pragma unroll
-                for (int q = 0; q < NWL - 1; q++) A[q] = A[q + 1];
-                A[NWL - 1] = 0;
-            }
             const float w = a.w[c];
             const bool stats = (w != 0.0f);
+            const bool want_dev = stats && !(w < 0.0f);
             VideoCounts cn = {0, 0, 0, 0, 0};
             uint32_t bsum = 0;
-            bool fresh = true;
+            if (a.bg == 2 || stats) {  // window 0 of the block: sum and counts from scratch
+                uint32_t X[NW];
+#pragma unroll
+                for (int q = 0; q < NW; q++) X[q] = A[q];
+                X[NW - 2] &= v.mask_a;
+                X[NW - 1] &= v.mask_b;
+                uint32_t s0 = 0, s1 = 0;
+#pragma unroll
+                for (int q = 0; q < NW; q += 2) { s0 = __dp4a(X[q], 0x01010101u, s0); s1 = __dp4a(X[q + 1], 0x01010101u, s1); }
+                bsum = s0 + s1;
+                if (stats) cn = video_recount<NW>(X, __float2int_rn((float)bsum * a.inv_n_sub), n);
+            }
 #pragma unroll 1
-            for (int i = i_lo; i < i_hi; i++) {
-                const int bo = i & 3;  // byte of A[0] the window starts at
-                auto build_x = [&](uint32_t (&X)[NW]) {  // the window's words, positions >= n zeroed
+            for (int quad = 0; quad < kVideoBlock / 4; quad++) {
+                // the four samples that enter during this quad (window positions n .. n + 3 of its first window) and the four that leave
+                const uint32_t wlo = n_word == NW - 2 ? A[NW - 2] : (n_word == NW - 1 ? A[NW - 1] : A[NW]);
+                const uint32_t whi = n_word == NW - 2 ? A[NW - 1] : (n_word == NW - 1 ? A[NW] : A[NW + 1]);
+                const uint32_t in4 = __funnelshift_r(wlo, whi, n_shift);
+                const uint32_t out4 = A[0];
+                const uint32_t live_quad = live_mask >> (4 * quad);
 #pragma unroll
-                    for (int q = 0; q < NW; q++) X[q] = __funnelshift_r(A[q], A[q + 1], 8 * bo);
-                    X[NW - 2] &= v.mask_a;
-                    X[NW - 1] &= v.mask_b;
-                };
-                const uint32_t x_first = __byte_perm(A[0], 0, 0x4440 + bo);
-                if (fresh) {  // first window of the block: sum and counts from scratch
-                    fresh = false;
-                    if (a.bg == 2 || stats) {
-                        uint32_t X[NW];
-                        build_x(X);
-                        uint32_t s0 = 0, s1 = 0;
+                for (int bo = 0; bo < 4; bo++) {  // bo: byte of A[0] the window starts at
+                    const int i = 4 * quad + bo;
+                    const uint32_t x_first = __byte_perm(out4, 0, 0x4440 + bo);
+                    int med2 = 0, iq4 = 0;
+                    uint32_t odev = 0;
+                    if (stats) {
+                        const int cn_lo = (int)(cn.c0 & 0xffu), cn_hi = (int)(cn.c3 >> 24);
+                        // every rank the band needs must resolve inside the counted values (the byte-range ends count as known),
+                        // and so must the smallest and the largest sample for the exact certificate term -- which implies the former
+                        const bool fine = want_dev ? ((cn_lo == 0 || cn.p == 0) && cn_hi == n) : ((cn_lo <= r_lo || cn.p == 0) && cn_hi > r_hi);
+                        const bool live = (live_quad >> bo) & 1u;
+                        if (__any_sync(0xffffffffu, live && !fine)) {
+                            uint32_t X[NW];
 #pragma unroll
-                        for (int q = 0; q < NW; q += 2) { s0 = __dp4a(X[q], 0x01010101u, s0); s1 = __dp4a(X[q + 1], 0x01010101u, s1); }
-                        bsum = s0 + s1;
-                        if (stats) {
-                            uint32_t tmp[NW];
-#pragma unroll
-                            for (int q = 0; q < NW; q++) tmp[q] = X[q];
-                            cn = video_recount<NW>(tmp, __float2int_rn((float)bsum * a.inv_n_sub), n);
-                        }
-                    }
-                }
-                int med2 = 0, iq4 = 0;
-                uint32_t odev = 0;
-                if (stats) {
-                    // every rank the band needs must resolve inside the counted values (the byte-range ends count as known)
-                    bool ok = ((int)(cn.c0 & 0xffu) <= r_lo || cn.p == 0) && ((int)(cn.c3 >> 24) > r_hi);
-                    bool solved = false;
-                    const unsigned nb = __ballot_sync(0xffffffffu, !ok && owner);
-                    if (nb) {  // iterative solver, then counts around the exact median; the whole warp together
-                        if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(nb));
-                        uint32_t tmp[NW];
-                        build_x(tmp);
-                        int m2 = 0, i4 = 0;
-                        video_solve<NW>(tmp, min(cn.p + 8, 254), a, pad, m2, i4);
-                        const VideoCounts rc = video_recount<NW>(tmp, m2 >> 1, n);
-                        if (!ok) { cn = rc; med2 = m2; iq4 = i4; solved = true; }
-                    }
-                    if (!solved) {
-                        const int mlo = stat_at(cn, kk_m1);
-                        const int mhi = (a.rk[2] == a.rk[3]) ? mlo : stat_at(cn, kk_m2);
-                        med2 = mlo + mhi;
-                        if (rel) {  // quartiles (src/chrono.rs:559-579)
-                            const int q1a = stat_at(cn, kk_q1a), q3a = stat_at(cn, kk_q3a);
-                            const int q1b = (a.rk[0] == a.rk[1]) ? q1a : stat_at(cn, kk_q1b);
-                            const int q3b = (a.rk[4] == a.rk[5]) ? q3a : stat_at(cn, kk_q3b);
-                            const float q1 = (a.rk[0] == a.rk[1]) ? (float)q1a : (1.0f - a.q1_frac) * (float)q1a + a.q1_frac * (float)q1b;
-                            const float q3 = (a.rk[4] == a.rk[5]) ? (float)q3a : (1.0f - a.q3_frac) * (float)q3a + a.q3_frac * (float)q3b;
-                            iq4 = __float2int_rn((q3 - q1) * 4.0f);
-                        }
-                    }
-                    if (!(w < 0.0f)) {  // max |x - centre| from the smallest and largest sample
-                        const int center = med2 >> 1;
-                        const bool in_range = ((cn.c0 & 0xffu) == 0u || cn.p == 0) && ((int)(cn.c3 >> 24) == n);
-                        const int minv = stat_at(cn, kk_min), maxv = stat_at(cn, kk_max);
-                        odev = (uint32_t)max(center - minv, maxv - center);
-                        const unsigned ob = __ballot_sync(0xffffffffu, !in_range && owner);
-                        if (ob) {
-                            if (__popc(ob) >= 3) {  // many pixels with samples beyond the counted values: scan the window
-                                uint32_t X[NW];
-                                build_x(X);
-                                const uint32_t cc = rep4(center);
-                                X[NW - 2] |= cc & ~v.mask_a;
-                                X[NW - 1] |= cc & ~v.mask_b;
-                                uint32_t m0 = 0, m1 = 0;
-#pragma unroll
-                                for (int q = 0; q < NW; q += 2) {
-                                    const uint32_t d0 = absdiff4(X[q], cc), d1 = absdiff4(X[q + 1], cc);
-                                    m0 = __vmaxu2(m0, d0); m0 = __vmaxu2(m0, d0 << 8);  // the high byte of each half is a byte-wise maximum
-                                    m1 = __vmaxu2(m1, d1); m1 = __vmaxu2(m1, d1 << 8);
-                                }
-                                const uint32_t m = __vmaxu2(m0, m1);
-                                if (!in_range) odev = max((m >> 8) & 0xffu, m >> 24);
-                            } else if (!in_range) {
-                                odev = 255;  // a few such pixels: they take the exact path (most of them hold an outlier anyway)
+                            for (int q = 0; q < NW; q++) X[q] = bo == 0 ? A[q] : __funnelshift_r(A[q], A[q + 1], 8 * bo);
+                            X[NW - 2] &= v.mask_a;
+                            X[NW - 1] &= v.mask_b;
+                            VideoSlowIO io;
+                            io.cn = cn;
+                            video_window_slow<NW>(v, X, w, live, lane, pad, &io);
+                            cn = io.cn; med2 = io.med2; iq4 = io.iq4; odev = io.odev;
+                        } else {
+                            const int mlo = stat_at(cn, kk_m1);
+                            const int mhi = one_rank ? mlo : stat_at(cn, kk_m2);
+                            med2 = mlo + mhi;
+                            if (rel) iq4 = video_iq4(a, cn);
+                            if (want_dev) {  // max |x - centre| from the smallest and largest sample
+                                const int center = med2 >> 1;
+                                const int minv = stat_at(cn, kk_min), maxv = stat_at(cn, kk_max);
+                                odev = (uint32_t)max(center - minv, maxv - center);
                             }
                         }
                     }
-                }
-                uint32_t* r = res + ((i * C + c) * rw) * kThreads;
-                r[0] = (uint32_t)med2 | (odev << 9) | (x_first << 17);
-                if (rw > 1) r[kThreads] = bsum | ((uint32_t)iq4 << 14);
-                // ---- slide by one frame: the sample at window position n enters, position 0 leaves
-                if (i + 1 < i_hi) {
-                    const int pos = bo + n, wi = pos >> 2;  // NW - 2 <= wi <= NW
-                    const uint32_t wv = wi == NW - 2 ? A[NW - 2] : (wi == NW - 1 ? A[NW - 1] : A[NW]);
-                    const uint32_t x_in = __byte_perm(wv, 0, 0x4440 + (pos & 3));
+                    uint32_t* r = res + ((i * C + c) * rw) * kThreads;
+                    r[0] = (uint32_t)med2 | (odev << 9) | (x_first << 17);
+                    if (rw > 1) r[kThreads] = bsum | ((uint32_t)iq4 << 14);
+                    // ---- slide by one frame: the sample at window position n enters, position 0 leaves
+                    const uint32_t x_in = __byte_perm(in4, 0, 0x4440 + bo);
                     bsum += x_in - x_first;
                     if (stats) {
                         uint32_t mi[4], mo[4];
@@ -2506,12 +2558,10 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
                         le_masks((int)x_first, cn.p, mo);
                         cn.c0 += mi[0] - mo[0]; cn.c1 += mi[1] - mo[1]; cn.c2 += mi[2] - mo[2]; cn.c3 += mi[3] - mo[3];
                     }
-                    if (bo == 3) {
-#pragma unroll
-                        for (int q = 0; q < NWL - 1; q++) A[q] = A[q + 1];
-                        A[NWL - 1] = 0;
-                    }
                 }
+#pragma unroll
+                for (int q = 0; q < NWL - 1; q++) A[q] = A[q + 1];
+                A[NWL - 1] = 0;
             }
         }
         video_phase2<C>(v, res, rw, i_lo, i_hi, blk, tile, pix, owner, lane, queue, qcount);
@@ -2831,7 +2881,7 @@ __global__ void __launch_bounds__(256) pack_group_kernel(const PackGroupArgs src
 // One thread per 16-byte unit.
 __global__ void __launch_bounds__(256) synth_fill_kernel(uint8_t* __restrict__ stack, long long n_pixels, long long n_tiles, int C,
                                                          int NG, int n_frames, int kind, unsigned long long seed, int width,
-                                                         int row0_global, int full_height) {
+                                                         int row0_global, int full_height, int block_rows, int block_skip_rows) {
     const long long n_units = n_tiles * C * NG * kTilePixels;
     const long long n_threads = (long long)gridDim.x * blockDim.x;
     for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += n_threads) {
@@ -2843,7 +2893,8 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(uint8_t* __restrict__ s
         const long long pix = tile * kTilePixels + p;
         uint32_t wd[4] = {0, 0, 0, 0};
         if (pix < n_pixels) {
-            const int y = row0_global + (int)(pix / width), xx = (int)(pix % width);
+            const int yl = (int)(pix / width), xx = (int)(pix % width);
+            const int y = row0_global + yl + (block_rows > 0 ? (yl / block_rows) * block_skip_rows : 0);  // interleaved row-block shards
 #pragma unroll 1
             for (int k = 0; k < 16; k++) {
                 const int f = g * 16 + k;

@@ -115,9 +115,11 @@ class FrameStack:
         _lib.check(_lib.lib().chb_stack_wait(self._h, C.byref(ms), C.byref(warn)))
         return ms.value, warn.value
 
-    def fill_synthetic(self, kind, seed=42, row0_global=0, full_height=None):
-        _lib.check(_lib.lib().chb_stack_fill_synthetic(self._h, int(kind), int(seed), int(row0_global),
-                                                      int(self.height if full_height is None else full_height)))
+    def fill_synthetic(self, kind, seed=42, row0_global=0, full_height=None, block_rows=0, block_skip_rows=0):
+        """block_rows / block_skip_rows: the stack is an interleaved row-block shard (sharding.InterleavedShard)."""
+        _lib.check(_lib.lib().chb_stack_fill_synthetic_blocks(self._h, int(kind), int(seed), int(row0_global),
+                                                             int(self.height if full_height is None else full_height),
+                                                             int(block_rows), int(block_skip_rows)))
 
     def device_bytes(self, dev_slot=0):
         return _lib.lib().chb_stack_device_bytes(self._h, dev_slot)

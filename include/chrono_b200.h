@@ -145,6 +145,10 @@ int chb_stack_sync(chb_stack *stack);
  * identical bytes to chb_synth_frame_host). row0_global: image row of this stack's first row (for shards that
  * live in separate processes); full_height: height of the whole image. */
 int chb_stack_fill_synthetic(chb_stack *stack, int kind, uint64_t seed, int row0_global, int full_height);
+/* Same for an interleaved row-block shard (chb_outlier_params.block_pixels; single-device stacks): local row r of the stack
+ * is row row0_global + r + (r / block_rows) * block_skip_rows of the whole image. 0 / 0 = one contiguous band. */
+int chb_stack_fill_synthetic_blocks(chb_stack *stack, int kind, uint64_t seed, int row0_global, int full_height, int block_rows,
+                                    int block_skip_rows);
 /* Host twin of the generator: writes frame `frame_idx` rows [row0, row0+rows) of a width x full_height image. */
 int chb_synth_frame_host(int kind, uint64_t seed, int frame_idx, int n_frames, int width, int full_height, int channels,
                          int row0, int rows, uint8_t *out_pixels);

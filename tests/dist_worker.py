@@ -35,6 +35,32 @@ def main():
         ref_img, ref_msk, _ = orc.outlier(st, thr, 1, 2, seed=11)
         assert np.array_equal(full_img, ref_img) and np.array_equal(full_msk, ref_msk)
         assert np.array_equal(full_dark, orc.simple(st, True))
+    # ---- strong-scaling shards: interleaved row blocks (rank g owns the blocks with index = g mod G). The oracle composites a
+    # shard block by block (pixel_offset = the block's first global pixel), which is what block_pixels / block_skip make the CUDA
+    # path do in one call; the gathered shards are de-interleaved on rank 0.
+    from chrono_photo_b200.sharding import InterleavedShard, deinterleave, interleave_block_rows
+    H2 = 36
+    B = interleave_block_rows(H2, world, 4)
+    sh = InterleavedShard(H2, W, rank, world, B)
+    rows_g = sh.global_rows()
+    assert sh.processor_args()["pixel_offset"] == rows_g[0] * W and len(rows_g) == H2 // world
+    full2 = np.stack([synth_frame_host(1, 7, f, n, W, H2, 3) for f in range(n)])
+    mine = full2[:, rows_g]
+    parts_i, parts_m = [], []
+    for b0 in range(0, sh.rows, B):
+        bi, bm, _ = orc.outlier(np.ascontiguousarray(mine[:, b0:b0 + B]), thr, 1, 2, seed=11, pixel_offset=int(rows_g[b0]) * W)
+        parts_i.append(bi); parts_m.append(bm)
+    import torch
+    mine_img = torch.from_numpy(np.concatenate(parts_i))
+    mine_msk = torch.from_numpy(np.concatenate(parts_m))
+    g_i = [torch.empty_like(mine_img) for _ in range(world)] if rank == 0 else None
+    g_m = [torch.empty_like(mine_msk) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine_img, g_i, dst=0)
+    dist.gather(mine_msk, g_m, dst=0)
+    if rank == 0:
+        ref_img, ref_msk, _ = orc.outlier(full2, thr, 1, 2, seed=11)
+        assert np.array_equal(deinterleave(torch.stack(g_i), B).numpy(), ref_img)
+        assert np.array_equal(deinterleave(torch.stack(g_m), B).numpy(), ref_msk)
         print("DIST_OK", world)
     dist.destroy_process_group()
 

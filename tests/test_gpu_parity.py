@@ -868,3 +868,40 @@ def test_multi_gpu_row_shards_match_single_gpu(ctx):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert np.array_equal(cp.SimpleProcessor(darker=True).process(fs1), cp.SimpleProcessor(darker=True).process(fs2))
     fs1.close(); fs2.close(); ctx2.close()
+
+
+def test_interleaved_row_block_shards_match_the_whole_image(ctx):
+    """Strong-scaling shards (sharding.InterleavedShard): GPU g of G owns the row blocks with index = g mod G. Every shard is
+    composited on its own (here: one after the other on one device) and the de-interleaved result must equal the whole image
+    bit for bit -- including `--background random`, whose draws are keyed by the global pixel index -- and the oracle's."""
+    from chrono_photo_b200.sharding import InterleavedShard, deinterleave, interleave_block_rows
+    rng = np.random.default_rng(72)
+    n, H, W = 40, 48, 50
+    st = make_stack(rng, n, H, W, 3, n_obj=40)
+    fs = upload(ctx, st)
+    thr = cp.Threshold.abs(0.05, 0.2)
+    for G, target in ((2, 4), (4, 3), (3, 8)):
+        B = interleave_block_rows(H, G, target)
+        assert B is not None and H % (B * G) == 0
+        for bg, om in (("random", "extreme"), ("first", "forward")):
+            want = cp.OutlierProcessor(thr, BG[bg], OM[om], seed=9).process(fs)
+            oimg, omsk, _ = orc.outlier(st, orc.threshold(True, 0.05, 0.2), BG[bg], OM[om], seed=9)
+            assert np.array_equal(want[0], oimg) and np.array_equal(want[1], omsk)
+            imgs, msks = [], []
+            for g in range(G):
+                sh = InterleavedShard(H, W, g, G, B)
+                fsg = upload(ctx, np.ascontiguousarray(st[:, sh.global_rows()]))
+                img, msk = cp.OutlierProcessor(thr, BG[bg], OM[om], seed=9, **sh.processor_args()).process(fsg)
+                imgs.append(img); msks.append(msk)
+                fsg.close()
+            assert np.array_equal(deinterleave(np.stack(imgs), B), want[0]), (G, B, bg, om)
+            assert np.array_equal(deinterleave(np.stack(msks), B), want[1]), (G, B, bg, om)
+    # the synthetic series generated in place for a shard equals the shard's rows of the whole series
+    sh = InterleavedShard(H, W, 1, 2, 4)
+    whole = cp.FrameStack(ctx, W, H, 3, 5)
+    whole.fill_synthetic(2, seed=3)
+    part = cp.FrameStack(ctx, W, sh.rows, 3, 5)
+    part.fill_synthetic(2, seed=3, **sh.fill_args())
+    for f in range(5):
+        assert np.array_equal(part.download(f), whole.download(f)[sh.global_rows()])
+    whole.close(); part.close(); fs.close()
