@@ -126,6 +126,7 @@ struct OutlierArgs {
     int inline_min;          // > 0 (G == 1 kernels): a tile with at least this many uncertified pixels is finished inside the streaming kernel
     int hard_inline_min;     // > 0 (G == 1 kernels): same for a warp-full of the iterative tier, finished inside outlier_hard_kernel
     int hist_all;            // 1: outlier_hist_kernel takes every pixel of the band (series beyond the register-resident variants), not a queue
+    int window_retry;        // 1 (G == 1 kernels, absolute thresholds): a second median window at the mean of the samples on the median's side before a pixel goes to the iterative tier
     int hard_drains_all;     // 1: outlier_hard_kernel also finishes the pixels the streaming kernel queued itself (dense pass): no outlier_exact_kernel launch
     unsigned long long seed, pixel_offset;
     unsigned long long block_pixels, block_skip;  // interleaved row-block shards (see chrono_b200.h); 0 / 0: one contiguous band
@@ -1345,6 +1346,22 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center,
     return ((cn[0] <= kp1) || p == 0) && ((kp2 < cn[NP - 2]) || p == 256 - NP);
 }
 
+// Second try of the straight-line median pair, for the warps of the streaming kernel that hold a pixel whose pair fell outside
+// the window around its mean: an object rests on such a pixel for part of the series, its mean is no guess for its median --
+// but the mean of the samples on the median's side of the first guess (background, mostly) is, and F(g), #{x <= g} and the
+// band sum give it for free (the iterative solver's first re-jump, see band_solve). Out of line and on a copy of the band's
+// words, so that the streaming kernel's loop neither grows nor loses its registers. Returns mlo | mhi << 8 | ok << 16.
+template <int W4>
+__device__ __noinline__ uint32_t band_window_retry(const uint32_t* xl, int g2, int kp1, int kp2, int cap) {
+    uint32_t x[W4];
+#pragma unroll
+    for (int q = 0; q < W4; q++) x[q] = xl[q];
+    int mlo, mhi, p0, cn[4];
+    uint32_t fm;
+    const bool ok = band_window<W4, 1, 5>(x, g2, kp1, kp2, cap, mlo, mhi, false, fm, p0, cn);
+    return (uint32_t)mlo | ((uint32_t)mhi << 8) | (ok ? 0x10000u : 0u);
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 // One warp = one tile slice: 32/G pixels x G lanes per pixel. A pixel-band's whole time series (WPL 16-frame units per
 // lane; slot i of lane j holds frame group g0 + i*G + j) is held in registers while its order statistics and its
@@ -1533,7 +1550,28 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         bool ok;
         if (!rel) {
             int cn[4];
-            ok = band_window<W4, G, 5>(A, guess, a.rk[2] + pad, a.rk[3] + pad, cap, mlo, mhi, false, fm, p0, cn);
+            const int kp1 = a.rk[2] + pad, kp2 = a.rk[3] + pad;
+            ok = band_window<W4, G, 5>(A, guess, kp1, kp2, cap, mlo, mhi, G == 1, fm, p0, cn);
+            if (G == 1 && a.window_retry && __any_sync(0xffffffffu, !ok)) {
+                // g = p0 + 2 is the value the window was centred on: F(g) = fm, #{x <= g} = cn[2], F(g + 1) = F(g) + 2 #{x <= g} - cap
+                const int g = p0 + 2, nj = cn[2];
+                int g2;
+                if (kp1 >= nj) {  // the pair lies above g: mean of the samples above g
+                    const int above = cap - nj;  // > 0
+                    const int up = ((int)fm + 2 * nj - cap + (int)bsum - cap * (g + 1)) >> 1;  // sum of (x - g - 1) over x > g
+                    g2 = g + 1 + __float2int_rn(__fdividef((float)up, (float)above));
+                } else {  // below: mean of the real samples <= g (the pad zeros taken out)
+                    const int below = nj - pad;
+                    const int dn = (((int)fm - (int)bsum + cap * g) >> 1) - pad * g;  // sum of (g - x) over real x <= g
+                    g2 = g - __float2int_rn(__fdividef((float)dn, (float)max(below, 1)));
+                }
+                g2 = g2 < 0 ? 0 : (g2 > 255 ? 255 : g2);
+                uint32_t X[W4];
+#pragma unroll
+                for (int q = 0; q < W4; q++) X[q] = A[q];
+                const uint32_t r2 = band_window_retry<W4>(X, g2, kp1, kp2, cap);
+                if (!ok && (r2 & 0x10000u)) { mlo = (int)(r2 & 0xffu); mhi = (int)((r2 >> 8) & 0xffu); ok = true; }
+            }
         } else {
             // The certificate only needs an UPPER bound of 1/IQR, i.e. a lower bound of the IQR, and the counts of a
             // 7-value window give one: Q1 <= d[hi rank of the Q1 pair] <= p + #{counts <= that rank} (valid when the rank is
@@ -2274,10 +2312,20 @@ __device__ __noinline__ void video_window_slow(const VideoArgs& v, const uint32_
     const unsigned nb = __ballot_sync(0xffffffffu, !ok && live);
     if (nb) {
         if (lane == 0) atomicAdd(a.counters + 2, (unsigned long long)__popc(nb));
-        int m2 = 0, i4 = 0;
-        video_solve<NW>(X, min(cn.p + 8, 254), a, pad, m2, i4);
-        const VideoCounts rc = video_recount<NW>(X, m2 >> 1, n);
-        if (!ok) { cn = rc; med2 = m2; iq4 = i4; solved = true; }
+        // A median leaves the counted values when an object has come to cover (or has just uncovered) more than half of the
+        // window: the newest sample then belongs to the cluster that now holds the median. Counts around it usually resolve
+        // every rank (they are exact wherever they are centred); only if they do not, the iterative solver runs.
+        const uint32_t newest = (X[(n - 1) >> 2] >> (8 * ((n - 1) & 3))) & 0xffu;
+        VideoCounts rc = video_recount<NW>(X, (int)newest, n);
+        const bool ok2 = ((int)(rc.c0 & 0xffu) <= r_lo || rc.p == 0) && ((int)(rc.c3 >> 24) > r_hi);
+        if (__any_sync(0xffffffffu, !ok && live && !ok2)) {
+            int m2 = 0, i4 = 0;
+            video_solve<NW>(X, min(cn.p + 8, 254), a, pad, m2, i4);
+            rc = video_recount<NW>(X, m2 >> 1, n);
+            if (!ok) { cn = rc; med2 = m2; iq4 = i4; solved = true; }
+        } else if (!ok) {
+            cn = rc;
+        }
     }
     if (!solved) {
         const int mlo = stat_at(cn, rep4(127 - a.rk[2]));
@@ -2386,20 +2434,36 @@ __device__ __forceinline__ void video_phase2(const VideoArgs& v, const uint32_t*
     for (int i = i_lo; i < i_hi; i++) {
         const int win = blk * kVideoBlock + i - v.first_start;
         uint32_t r0[C], r1[C];
-        float bound = 0.0f;
+        bool clean;
+        if (a.int_dist) {
+            // absolute thresholds, weights 0 / 1: |2 x - 2 median| <= 2 max|x - centre| + (median - centre) * 2 in integers, and
+            // 4 dist_sq < thr4 <=> dist_sq < thr_sq exactly (see IntDist), so the certificate is an integer comparison
+            uint32_t acc = 0;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const uint32_t* r = res + ((i * C + c) * rw) * kThreads;
-            r0[c] = r[0];
-            r1[c] = rw > 1 ? r[kThreads] : 0u;
-            const float w = a.w[c];
-            if (w != 0.0f && !(w < 0.0f)) {
-                const float aw = a.absolute ? w : w * iqr_inv_of((int)(r1[c] >> 14));
-                const float t = aw * ((float)((r0[c] >> 9) & 0xffu) + 0.5f * (float)(r0[c] & 1u));
-                bound += t * t;
+            for (int c = 0; c < C; c++) {
+                const uint32_t* r = res + ((i * C + c) * rw) * kThreads;
+                r0[c] = r[0];
+                r1[c] = rw > 1 ? r[kThreads] : 0u;
+                const uint32_t t = a.w[c] != 0.0f ? 2u * ((r0[c] >> 9) & 0xffu) + (r0[c] & 1u) : 0u;
+                acc += t * t;
             }
+            clean = (int)acc < a.thr4;
+        } else {
+            float bound = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const uint32_t* r = res + ((i * C + c) * rw) * kThreads;
+                r0[c] = r[0];
+                r1[c] = rw > 1 ? r[kThreads] : 0u;
+                const float w = a.w[c];
+                if (w != 0.0f && !(w < 0.0f)) {
+                    const float aw = a.absolute ? w : w * iqr_inv_of((int)(r1[c] >> 14));
+                    const float t = aw * ((float)((r0[c] >> 9) & 0xffu) + 0.5f * (float)(r0[c] & 1u));
+                    bound += t * t;
+                }
+            }
+            clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
         }
-        const bool clean = bound * 1.0001f < a.thr_sq;  // margin covers the f32 roundings of the reference's sum
         if (owner && clean) {
             uint8_t pixel[4] = {0, 0, 0, 0};
             if (a.bg == 2) {
@@ -2474,10 +2538,9 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
         // windows of the run (bit i), none for lanes beyond the band's last pixel: only those vote for the uncommon path
         const uint32_t live_mask = (owner && i_hi > i_lo) ? (((1u << i_hi) - 1u) & ~((1u << i_lo) - 1u)) : 0u;  // 0 <= i_lo < i_hi <= 16
         // ---- phase 1, band by band: the band's bytes in registers, the window slides over them. All 16 windows of the block
-        // are evaluated (phase 2 only reads those of the run), four at a time with the window's byte offset inside A[0] a
-        // compile-time constant; the words rotate once per four windows. The common case -- every rank and the smallest /
-        // largest sample inside the counted values -- is straight-line code behind ONE warp vote; everything else (solver,
-        // re-centred counts, window scan) lives in video_window_slow.
+        // are evaluated (phase 2 only reads those of the run); the words rotate once per four windows. The common case -- every
+        // rank and the smallest / largest sample inside the counted values -- is straight-line code behind ONE warp vote;
+        // everything else (solver, re-centred counts, window scan) lives in video_window_slow.
 #pragma unroll 1
         for (int c = 0; c < C; c++) {
             uint32_t A[NWL];
@@ -2504,60 +2567,62 @@ __global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid
                 bsum = s0 + s1;
                 if (stats) cn = video_recount<NW>(X, __float2int_rn((float)bsum * a.inv_n_sub), n);
             }
+            // ONE copy of the window body in the instruction stream (the four-fold unrolled version, with the window's byte offset a
+            // compile-time constant, was 18 KB of loop and spent 59 % of its stall samples waiting for instructions): two nested
+            // loops, the words rotate in the outer one
 #pragma unroll 1
             for (int quad = 0; quad < kVideoBlock / 4; quad++) {
-                // the four samples that enter during this quad (window positions n .. n + 3 of its first window) and the four that leave
+                // the four samples that enter during this quad's slides (window positions n .. n + 3 of its first window)
                 const uint32_t wlo = n_word == NW - 2 ? A[NW - 2] : (n_word == NW - 1 ? A[NW - 1] : A[NW]);
                 const uint32_t whi = n_word == NW - 2 ? A[NW - 1] : (n_word == NW - 1 ? A[NW] : A[NW + 1]);
                 const uint32_t in4 = __funnelshift_r(wlo, whi, n_shift);
-                const uint32_t out4 = A[0];
                 const uint32_t live_quad = live_mask >> (4 * quad);
-#pragma unroll
+                uint32_t* const res_quad = res + (4 * quad * C + c) * rw * kThreads;
+#pragma unroll 1
                 for (int bo = 0; bo < 4; bo++) {  // bo: byte of A[0] the window starts at
-                    const int i = 4 * quad + bo;
-                    const uint32_t x_first = __byte_perm(out4, 0, 0x4440 + bo);
-                    int med2 = 0, iq4 = 0;
-                    uint32_t odev = 0;
-                    if (stats) {
-                        const int cn_lo = (int)(cn.c0 & 0xffu), cn_hi = (int)(cn.c3 >> 24);
-                        // every rank the band needs must resolve inside the counted values (the byte-range ends count as known),
-                        // and so must the smallest and the largest sample for the exact certificate term -- which implies the former
-                        const bool fine = want_dev ? ((cn_lo == 0 || cn.p == 0) && cn_hi == n) : ((cn_lo <= r_lo || cn.p == 0) && cn_hi > r_hi);
-                        const bool live = (live_quad >> bo) & 1u;
-                        if (__any_sync(0xffffffffu, live && !fine)) {
-                            uint32_t X[NW];
+                const uint32_t x_first = __byte_perm(A[0], 0, 0x4440 + bo);
+                int med2 = 0, iq4 = 0;
+                uint32_t odev = 0;
+                if (stats) {
+                    const int cn_lo = (int)(cn.c0 & 0xffu), cn_hi = (int)(cn.c3 >> 24);
+                    // every rank the band needs must resolve inside the counted values (the byte-range ends count as known),
+                    // and so must the smallest and the largest sample for the exact certificate term -- which implies the former
+                    const bool fine = want_dev ? ((cn_lo == 0 || cn.p == 0) && cn_hi == n) : ((cn_lo <= r_lo || cn.p == 0) && cn_hi > r_hi);
+                    const bool live = (live_quad >> bo) & 1u;
+                    if (__any_sync(0xffffffffu, live && !fine)) {
+                        uint32_t X[NW];
 #pragma unroll
-                            for (int q = 0; q < NW; q++) X[q] = bo == 0 ? A[q] : __funnelshift_r(A[q], A[q + 1], 8 * bo);
-                            X[NW - 2] &= v.mask_a;
-                            X[NW - 1] &= v.mask_b;
-                            VideoSlowIO io;
-                            io.cn = cn;
-                            video_window_slow<NW>(v, X, w, live, lane, pad, &io);
-                            cn = io.cn; med2 = io.med2; iq4 = io.iq4; odev = io.odev;
-                        } else {
-                            const int mlo = stat_at(cn, kk_m1);
-                            const int mhi = one_rank ? mlo : stat_at(cn, kk_m2);
-                            med2 = mlo + mhi;
-                            if (rel) iq4 = video_iq4(a, cn);
-                            if (want_dev) {  // max |x - centre| from the smallest and largest sample
-                                const int center = med2 >> 1;
-                                const int minv = stat_at(cn, kk_min), maxv = stat_at(cn, kk_max);
-                                odev = (uint32_t)max(center - minv, maxv - center);
-                            }
+                        for (int q = 0; q < NW; q++) X[q] = __funnelshift_r(A[q], A[q + 1], 8 * bo);
+                        X[NW - 2] &= v.mask_a;
+                        X[NW - 1] &= v.mask_b;
+                        VideoSlowIO io;
+                        io.cn = cn;
+                        video_window_slow<NW>(v, X, w, live, lane, pad, &io);
+                        cn = io.cn; med2 = io.med2; iq4 = io.iq4; odev = io.odev;
+                    } else {
+                        const int mlo = stat_at(cn, kk_m1);
+                        const int mhi = one_rank ? mlo : stat_at(cn, kk_m2);
+                        med2 = mlo + mhi;
+                        if (rel) iq4 = video_iq4(a, cn);
+                        if (want_dev) {  // max |x - centre| from the smallest and largest sample
+                            const int center = med2 >> 1;
+                            const int minv = stat_at(cn, kk_min), maxv = stat_at(cn, kk_max);
+                            odev = (uint32_t)max(center - minv, maxv - center);
                         }
                     }
-                    uint32_t* r = res + ((i * C + c) * rw) * kThreads;
-                    r[0] = (uint32_t)med2 | (odev << 9) | (x_first << 17);
-                    if (rw > 1) r[kThreads] = bsum | ((uint32_t)iq4 << 14);
-                    // ---- slide by one frame: the sample at window position n enters, position 0 leaves
-                    const uint32_t x_in = __byte_perm(in4, 0, 0x4440 + bo);
-                    bsum += x_in - x_first;
-                    if (stats) {
-                        uint32_t mi[4], mo[4];
-                        le_masks((int)x_in, cn.p, mi);
-                        le_masks((int)x_first, cn.p, mo);
-                        cn.c0 += mi[0] - mo[0]; cn.c1 += mi[1] - mo[1]; cn.c2 += mi[2] - mo[2]; cn.c3 += mi[3] - mo[3];
-                    }
+                }
+                uint32_t* r = res_quad + bo * (C * rw * kThreads);
+                r[0] = (uint32_t)med2 | (odev << 9) | (x_first << 17);
+                if (rw > 1) r[kThreads] = bsum | ((uint32_t)iq4 << 14);
+                // ---- slide by one frame: the sample at window position n enters, position 0 leaves
+                const uint32_t x_in = __byte_perm(in4, 0, 0x4440 + bo);
+                bsum += x_in - x_first;
+                if (stats) {
+                    uint32_t mi[4], mo[4];
+                    le_masks((int)x_in, cn.p, mi);
+                    le_masks((int)x_first, cn.p, mo);
+                    cn.c0 += mi[0] - mo[0]; cn.c1 += mi[1] - mo[1]; cn.c2 += mi[2] - mo[2]; cn.c3 += mi[3] - mo[3];
+                }
                 }
 #pragma unroll
                 for (int q = 0; q < NWL - 1; q++) A[q] = A[q + 1];
