@@ -49,12 +49,12 @@ struct Tuning {
     std::atomic<int> video_queue_cap{-1};  // CHB_VIDEO_QUEUE_CAP: capacity of the video exact-path queue (tests the in-place fallback)
     std::atomic<int> inline_min{12};       // CHB_INLINE_MIN: uncertified pixels per tile from which the tile is finished inside K1 (0 = never)
     std::atomic<int> hard_inline_min{1};   // CHB_HARD_INLINE_MIN: same for a warp-full of the iterative tier (finished inside outlier_hard_kernel)
-    std::atomic<int> window_retry{1};      // CHB_WINDOW_RETRY: second median window in the streaming kernel before the iterative tier
+    std::atomic<int> hard_window{1};       // CHB_HARD_WINDOW: the iterative tier tries the two straight-line windows before the solver
     std::atomic<int> hard_drains{1};       // CHB_HARD_DRAINS: outlier_hard_kernel also drains the streaming kernel's own queue (no exact-path launch)
     Tuning() {
         auto env = [](const char* k, std::atomic<int>& v) { if (const char* e = getenv(k)) v.store(atoi(e)); };
         env("CHB_FORCE_VARIANT", force_variant); env("CHB_HIST", hist); env("CHB_PDL", pdl);
-        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min); env("CHB_HARD_INLINE_MIN", hard_inline_min); env("CHB_HARD_DRAINS", hard_drains); env("CHB_WINDOW_RETRY", window_retry);
+        env("CHB_VIDEO_QUEUE_CAP", video_queue_cap); env("CHB_INLINE_MIN", inline_min); env("CHB_HARD_INLINE_MIN", hard_inline_min); env("CHB_HARD_DRAINS", hard_drains); env("CHB_HARD_WINDOW", hard_window);
     }
 };
 static Tuning g_tune;
@@ -68,7 +68,7 @@ extern "C" int chb_set_tuning(const char* key, int value) {
     else if (k == "inline_min") g_tune.inline_min.store(value);
     else if (k == "hard_inline_min") g_tune.hard_inline_min.store(value);
     else if (k == "hard_drains") g_tune.hard_drains.store(value);
-    else if (k == "window_retry") g_tune.window_retry.store(value);
+    else if (k == "hard_window") g_tune.hard_window.store(value);
     else return fail(CHB_ERR_INVALID, "chb_set_tuning: unknown key '%s'", key);
     return CHB_OK;
 }
@@ -892,7 +892,7 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
     // ... run inside the streaming kernel (lane = pixel: the G == 1 variants) for tiles with at least this many uncertified pixels
     a.inline_min = (a.mask_path && var.g == 1) ? g_tune.inline_min.load() : 0;
     a.hard_inline_min = (a.mask_path && var.g == 1) ? g_tune.hard_inline_min.load() : 0;
-    a.window_retry = (var.g == 1 && g_tune.window_retry.load() != 0) ? 1 : 0;
+    a.hard_window = (var.g == 1 && !sub && g_tune.hard_window.load() != 0) ? 1 : 0;
 
     // host tables
     if (!long_series) byte_masks(win.frames, win.g0, cap_groups, cs.h_wmask);

@@ -126,7 +126,7 @@ struct OutlierArgs {
     int inline_min;          // > 0 (G == 1 kernels): a tile with at least this many uncertified pixels is finished inside the streaming kernel
     int hard_inline_min;     // > 0 (G == 1 kernels): same for a warp-full of the iterative tier, finished inside outlier_hard_kernel
     int hist_all;            // 1: outlier_hist_kernel takes every pixel of the band (series beyond the register-resident variants), not a queue
-    int window_retry;        // 1 (G == 1 kernels, absolute thresholds): a second median window at the mean of the samples on the median's side before a pixel goes to the iterative tier
+    int hard_window;         // 1 (G == 1 kernels, absolute thresholds): the iterative tier tries the two straight-line windows before the solver
     int hard_drains_all;     // 1: outlier_hard_kernel also finishes the pixels the streaming kernel queued itself (dense pass): no outlier_exact_kernel launch
     unsigned long long seed, pixel_offset;
     unsigned long long block_pixels, block_skip;  // interleaved row-block shards (see chrono_b200.h); 0 / 0: one contiguous band
@@ -373,22 +373,36 @@ struct PixelSrc {
     }
 };
 
-// Reads a pixel's samples frame by frame, keeping the current 16-frame unit of every band in registers.
+// Reads a pixel's samples frame by frame, keeping the current 16-frame unit of every band in registers -- and the unit of the
+// group the walk enters next (one group on in the direction of the last move), requested when the current one is entered, so
+// that its L2 / HBM latency is covered by the sixteen frames in between instead of being exposed once per group.
 struct ColumnReader {
     const uint8_t* base;  // address of unit (c = 0, g = 0) of this pixel
     long long band_stride;  // NG * 512
-    int C, cur_g;
-    uint4 u[4];
+    int C, NG, cur_g, nxt_g;
+    uint4 u[4], nxt[4];
     __device__ __forceinline__ ColumnReader(const PixelSrc& s)
-        : base(s.tile + (long long)s.p * kUnitBytes), band_stride((long long)s.NG * kTilePixels * kUnitBytes), C(s.C), cur_g(-1) {}
+        : base(s.tile + (long long)s.p * kUnitBytes), band_stride((long long)s.NG * kTilePixels * kUnitBytes), C(s.C), NG(s.NG), cur_g(-1), nxt_g(-1) {}
+    __device__ __forceinline__ void load_group(int g, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (c < C) dst[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
+    }
+    __device__ __forceinline__ void enter(int g) {  // (uniform across the lanes of a single-window batch: every lane walks the same window)
+        const int ahead = g + (g >= cur_g ? 1 : -1);
+        if (g == nxt_g) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) u[c] = nxt[c];
+        } else {
+            load_group(g, u);
+        }
+        cur_g = g;
+        nxt_g = -1;
+        if (ahead >= 0 && ahead < NG) { load_group(ahead, nxt); nxt_g = ahead; }
+    }
     __device__ __forceinline__ void fetch(int frame, uint8_t (&px)[4]) {
         const int g = frame >> 4;
-        if (g != cur_g) {  // uniform across the lanes of a batch: every lane walks the same window
-            cur_g = g;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (c < C) u[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
-        }
+        if (g != cur_g) enter(g);
         const int wsel = (frame >> 2) & 3, sh = (frame & 3) * 8;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -401,12 +415,7 @@ struct ColumnReader {
     // the 4-frame word (frames frame .. frame+3, frame a multiple of 4) of every band
     __device__ __forceinline__ void fetch_word(int frame, uint32_t (&xw)[4]) {
         const int g = frame >> 4;
-        if (g != cur_g) {
-            cur_g = g;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (c < C) u[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
-        }
+        if (g != cur_g) enter(g);
         const int wsel = (frame >> 2) & 3;
 #pragma unroll
         for (int c = 0; c < 4; c++) xw[c] = (c < C) ? (wsel == 0 ? u[c].x : (wsel == 1 ? u[c].y : (wsel == 2 ? u[c].z : u[c].w))) : 0u;
@@ -1346,20 +1355,66 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center,
     return ((cn[0] <= kp1) || p == 0) && ((kp2 < cn[NP - 2]) || p == 256 - NP);
 }
 
-// Second try of the straight-line median pair, for the warps of the streaming kernel that hold a pixel whose pair fell outside
-// the window around its mean: an object rests on such a pixel for part of the series, its mean is no guess for its median --
-// but the mean of the samples on the median's side of the first guess (background, mostly) is, and F(g), #{x <= g} and the
-// band sum give it for free (the iterative solver's first re-jump, see band_solve). Out of line and on a copy of the band's
-// words, so that the streaming kernel's loop neither grows nor loses its registers. Returns mlo | mhi << 8 | ok << 16.
+// Median pair of one pixel-band (lane = pixel, G == 1) by at most four straight-line windows: five F values per window give
+// four exact counts for 260 VABSDIFF4 and a few bookkeeping instructions, where an iteration of band_solve gives one or two
+// for 104 and a long state machine. Window 1 sits on the band mean (it resolves the bands that were not the reason the pixel
+// came to this tier). Window 2 sits where band_solve's first re-jump would go: the mean of the samples on the median's side of
+// the first guess (an object rests on the pixel: two clusters) or, when those samples spread far beyond the rank (iid bytes,
+// wide noise), the first guess moved by the samples still to be passed over the density the mean absolute deviation implies.
+// From then on every window leaves exact counts on both sides of the pair -- (xl, cl): the largest value known to have
+// #{x <= xl} <= kp1, (xh, ch): the smallest with #{x <= xh} > kp2 -- and the next window is placed where a uniform spread
+// of the ch - cl samples between them puts the rank, kept adjacent to a known count so that it always resolves three new
+// values. Returns true when every lane of the warp is resolved (warp-uniform); otherwise the caller runs band_solve.
 template <int W4>
-__device__ __noinline__ uint32_t band_window_retry(const uint32_t* xl, int g2, int kp1, int kp2, int cap) {
-    uint32_t x[W4];
+__device__ __forceinline__ bool band_solve_windows(const uint32_t (&x)[W4], uint32_t bsum, const OutlierArgs& a, int pad, int cap, int& mlo, int& mhi) {
+    const int kp1 = a.rk[2] + pad, kp2 = a.rk[3] + pad;
+    int g = __float2int_rn((float)bsum * a.inv_n_sub);
+    int xl = -1, cl = 0, xh = 255, ch = cap;
+    bool ok = false;
+    mlo = mhi = 0;
+#pragma unroll 1
+    for (int it = 0; it < 4; it++) {
+        int v1, v2, p0, cn[4];
+        uint32_t fm;
+        const bool okw = band_window<W4, 1, 5>(x, g, kp1, kp2, cap, v1, v2, true, fm, p0, cn);
+        if (!ok && okw) { mlo = v1; mhi = v2; ok = true; }
+        if (!__any_sync(0xffffffffu, !ok)) return true;
 #pragma unroll
-    for (int q = 0; q < W4; q++) x[q] = xl[q];
-    int mlo, mhi, p0, cn[4];
-    uint32_t fm;
-    const bool ok = band_window<W4, 1, 5>(x, g2, kp1, kp2, cap, mlo, mhi, false, fm, p0, cn);
-    return (uint32_t)mlo | ((uint32_t)mhi << 8) | (ok ? 0x10000u : 0u);
+        for (int k = 0; k < 4; k++)
+            if (cn[k] <= kp1 && p0 + k > xl) { xl = p0 + k; cl = cn[k]; }
+#pragma unroll
+        for (int k = 3; k >= 0; k--)
+            if (cn[k] > kp2 && p0 + k < xh) { xh = p0 + k; ch = cn[k]; }
+        int g2;
+        if (it == 0) {
+            const int gc = p0 + 2, nj = cn[2];  // F(gc) = fm, #{x <= gc} = nj, F(gc + 1) = F(gc) + 2 nj - cap
+            const bool up = kp1 >= nj;
+            int side, far;
+            float fside;
+            if (up) {  // mean of the samples above gc
+                const int sum_up = ((int)fm + 2 * nj - cap + (int)bsum - cap * (gc + 1)) >> 1;  // sum of (x - gc - 1) over x > gc
+                side = gc + 1 + __float2int_rn(__fdividef((float)sum_up, (float)max(cap - nj, 1)));
+                far = kp1 + 1 - nj;
+                fside = (float)((int)fm + 2 * nj - cap) - (float)pad * (float)(gc + 1);
+            } else {   // mean of the real samples <= gc (the pad zeros taken out)
+                const int sum_dn = (((int)fm - (int)bsum + cap * gc) >> 1) - pad * gc;  // sum of (gc - x) over real x <= gc
+                side = gc - __float2int_rn(__fdividef((float)sum_dn, (float)max(nj - pad, 1)));
+                far = nj - kp1;
+                fside = (float)fm - (float)pad * (float)gc;
+            }
+            const int step = __float2int_rn((float)far * 3.5f * fside * a.inv_n_sub * a.inv_n_sub);
+            const int dside = up ? side - gc : gc - side;
+            g2 = (4 * step < dside) ? (up ? gc + step : gc - step) : side;
+        } else {
+            g2 = xl + __float2int_rn(__fdividef((float)(kp1 + 1 - cl) * (float)(xh - xl), (float)max(ch - cl, 1)));
+        }
+        // p0 = g - 2 in [xl, xh - 3]: count 0 of the window is then a known "<= kp1" count (or the range end), count 3 a known
+        // "> kp2" one once the bracket is narrow; an unresolved lane's bracket shrinks by at least three values per window
+        const int g_lo = xl + 2, g_hi = max(xl + 2, xh - 1);
+        g2 = g2 < g_lo ? g_lo : (g2 > g_hi ? g_hi : g2);
+        if (!ok) g = g2;
+    }
+    return !__any_sync(0xffffffffu, !ok);
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -1385,7 +1440,7 @@ __device__ __noinline__ uint32_t band_window_retry(const uint32_t* xl, int g2, i
 #define CHB_HARD_MINB 2
 #endif
 #ifndef CHB_EXACT_MINB
-#define CHB_EXACT_MINB 4
+#define CHB_EXACT_MINB 3
 #endif
 constexpr int kWarpsPerCta = CHB_WARPS;
 constexpr int kQueueCap = 64;  // per warp
@@ -1551,27 +1606,7 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         if (!rel) {
             int cn[4];
             const int kp1 = a.rk[2] + pad, kp2 = a.rk[3] + pad;
-            ok = band_window<W4, G, 5>(A, guess, kp1, kp2, cap, mlo, mhi, G == 1, fm, p0, cn);
-            if (G == 1 && a.window_retry && __any_sync(0xffffffffu, !ok)) {
-                // g = p0 + 2 is the value the window was centred on: F(g) = fm, #{x <= g} = cn[2], F(g + 1) = F(g) + 2 #{x <= g} - cap
-                const int g = p0 + 2, nj = cn[2];
-                int g2;
-                if (kp1 >= nj) {  // the pair lies above g: mean of the samples above g
-                    const int above = cap - nj;  // > 0
-                    const int up = ((int)fm + 2 * nj - cap + (int)bsum - cap * (g + 1)) >> 1;  // sum of (x - g - 1) over x > g
-                    g2 = g + 1 + __float2int_rn(__fdividef((float)up, (float)above));
-                } else {  // below: mean of the real samples <= g (the pad zeros taken out)
-                    const int below = nj - pad;
-                    const int dn = (((int)fm - (int)bsum + cap * g) >> 1) - pad * g;  // sum of (g - x) over real x <= g
-                    g2 = g - __float2int_rn(__fdividef((float)dn, (float)max(below, 1)));
-                }
-                g2 = g2 < 0 ? 0 : (g2 > 255 ? 255 : g2);
-                uint32_t X[W4];
-#pragma unroll
-                for (int q = 0; q < W4; q++) X[q] = A[q];
-                const uint32_t r2 = band_window_retry<W4>(X, g2, kp1, kp2, cap);
-                if (!ok && (r2 & 0x10000u)) { mlo = (int)(r2 & 0xffu); mhi = (int)((r2 >> 8) & 0xffu); ok = true; }
-            }
+            ok = band_window<W4, G, 5>(A, guess, kp1, kp2, cap, mlo, mhi, false, fm, p0, cn);
         } else {
             // The certificate only needs an UPPER bound of 1/IQR, i.e. a lower bound of the IQR, and the counts of a
             // 7-value window give one: Q1 <= d[hi rank of the Q1 pair] <= p + #{counts <= that rank} (valid when the rank is
@@ -1594,6 +1629,17 @@ __device__ __forceinline__ void process_band(const OutlierArgs& a, uint32_t (&A)
         halfw = med - (float)center;
         acc.hard = acc.hard || !ok;
         solved = true;
+    }
+    if (!solved && !FAST && G == 1 && (MODE == 1 || (MODE == 0 && a.absolute)) && a.hard_window) {
+        // Iterative tier, absolute thresholds (one rank pair per band): a short iteration of straight-line windows before the
+        // solver's general loop (see band_solve_windows); only a warp-full that still holds an unresolved pair runs the solver.
+        int mlo, mhi;
+        if (band_solve_windows<W4>(A, bsum, a, pad, cap, mlo, mhi)) {
+            med = (mlo == mhi) ? (float)mlo : 0.5f * ((float)mlo + (float)mhi);  // src/chrono.rs:582-591
+            center = (mlo + mhi) >> 1;
+            halfw = med - (float)center;
+            solved = true;
+        }
     }
     if (!solved) band_stats<W4, G>(cap, A, bsum, a.inv_n_sub, a, pad, med, q1, q3, iqi, center, halfw);
     acc.set_median(c, med);

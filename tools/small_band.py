@@ -20,10 +20,10 @@ def run(rows, row0, shard=None, tag=""):
     fs.wait(); dt = (time.perf_counter() - t0) / 20 * 1e3
     print(f"{tag}rows {rows} at {row0}: call ms {min(ms[1:]):.4f} main {min(main[1:]):.4f} tiers {min(ms[1:]) - min(main[1:]):.4f} (ideal call {2.455*rows/4000:.4f})  enqueue-loop ms/step {dt:.4f}  slow {int(_lib.lib().chb_last_slow_pixels())}", flush=True)
     fs.close()
-for hd, wr in ((1, 1), (1, 0), (0, 0)):
+for hd, wr in ((1, 1), (1, 0)):
     _lib.lib().chb_set_tuning(b"hard_drains", hd)
-    _lib.lib().chb_set_tuning(b"window_retry", wr)
-    print(f"== hard_drains {hd} window_retry {wr}")
+    _lib.lib().chb_set_tuning(b"hard_window", wr)
+    print(f"== hard_drains {hd} hard_window {wr}")
     for rows in (4000, 2000, 1000):
         run(rows, 0)
     for k in (3, 6, 7):
