@@ -373,36 +373,22 @@ struct PixelSrc {
     }
 };
 
-// Reads a pixel's samples frame by frame, keeping the current 16-frame unit of every band in registers -- and the unit of the
-// group the walk enters next (one group on in the direction of the last move), requested when the current one is entered, so
-// that its L2 / HBM latency is covered by the sixteen frames in between instead of being exposed once per group.
+// Reads a pixel's samples frame by frame, keeping the current 16-frame unit of every band in registers.
 struct ColumnReader {
     const uint8_t* base;  // address of unit (c = 0, g = 0) of this pixel
     long long band_stride;  // NG * 512
-    int C, NG, cur_g, nxt_g;
-    uint4 u[4], nxt[4];
+    int C, cur_g;
+    uint4 u[4];
     __device__ __forceinline__ ColumnReader(const PixelSrc& s)
-        : base(s.tile + (long long)s.p * kUnitBytes), band_stride((long long)s.NG * kTilePixels * kUnitBytes), C(s.C), NG(s.NG), cur_g(-1), nxt_g(-1) {}
-    __device__ __forceinline__ void load_group(int g, uint4 (&dst)[4]) {
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (c < C) dst[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
-    }
-    __device__ __forceinline__ void enter(int g) {  // (uniform across the lanes of a single-window batch: every lane walks the same window)
-        const int ahead = g + (g >= cur_g ? 1 : -1);
-        if (g == nxt_g) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) u[c] = nxt[c];
-        } else {
-            load_group(g, u);
-        }
-        cur_g = g;
-        nxt_g = -1;
-        if (ahead >= 0 && ahead < NG) { load_group(ahead, nxt); nxt_g = ahead; }
-    }
+        : base(s.tile + (long long)s.p * kUnitBytes), band_stride((long long)s.NG * kTilePixels * kUnitBytes), C(s.C), cur_g(-1) {}
     __device__ __forceinline__ void fetch(int frame, uint8_t (&px)[4]) {
         const int g = frame >> 4;
-        if (g != cur_g) enter(g);
+        if (g != cur_g) {  // uniform across the lanes of a batch: every lane walks the same window
+            cur_g = g;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c < C) u[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
+        }
         const int wsel = (frame >> 2) & 3, sh = (frame & 3) * 8;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -415,7 +401,12 @@ struct ColumnReader {
     // the 4-frame word (frames frame .. frame+3, frame a multiple of 4) of every band
     __device__ __forceinline__ void fetch_word(int frame, uint32_t (&xw)[4]) {
         const int g = frame >> 4;
-        if (g != cur_g) enter(g);
+        if (g != cur_g) {
+            cur_g = g;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c < C) u[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
+        }
         const int wsel = (frame >> 2) & 3;
 #pragma unroll
         for (int c = 0; c < 4; c++) xw[c] = (c < C) ? (wsel == 0 ? u[c].x : (wsel == 1 ? u[c].y : (wsel == 2 ? u[c].z : u[c].w))) : 0u;
@@ -1355,36 +1346,44 @@ __device__ __forceinline__ bool band_window(const uint32_t (&x)[W4], int center,
     return ((cn[0] <= kp1) || p == 0) && ((kp2 < cn[NP - 2]) || p == 256 - NP);
 }
 
-// Median pair of one pixel-band (lane = pixel, G == 1) by at most four straight-line windows: five F values per window give
+// Median pair of one pixel-band (lane = pixel, G == 1) by a few straight-line windows: five F values per window give
 // four exact counts for 260 VABSDIFF4 and a few bookkeeping instructions, where an iteration of band_solve gives one or two
 // for 104 and a long state machine. Window 1 sits on the band mean (it resolves the bands that were not the reason the pixel
 // came to this tier). Window 2 sits where band_solve's first re-jump would go: the mean of the samples on the median's side of
 // the first guess (an object rests on the pixel: two clusters) or, when those samples spread far beyond the rank (iid bytes,
 // wide noise), the first guess moved by the samples still to be passed over the density the mean absolute deviation implies.
-// From then on every window leaves exact counts on both sides of the pair -- (xl, cl): the largest value known to have
-// #{x <= xl} <= kp1, (xh, ch): the smallest with #{x <= xh} > kp2 -- and the next window is placed where a uniform spread
-// of the ch - cl samples between them puts the rank, kept adjacent to a known count so that it always resolves three new
-// values. Returns true when every lane of the warp is resolved (warp-uniform); otherwise the caller runs band_solve.
+// From then on every window leaves exact counts on both sides of the rank that is still open and the next window is placed
+// where a uniform spread of the samples between them puts the rank, kept adjacent to a known count so that it always covers
+// three new values. Returns true when every lane of the warp is resolved (warp-uniform); otherwise the caller runs band_solve.
 template <int W4>
 __device__ __forceinline__ bool band_solve_windows(const uint32_t (&x)[W4], uint32_t bsum, const OutlierArgs& a, int pad, int cap, int& mlo, int& mhi) {
+    constexpr int kMaxWindows = 8;  // iid bytes: 4.2 windows for the slowest of 32 lanes; two far-apart clusters: 5.1 (simulated)
     const int kp1 = a.rk[2] + pad, kp2 = a.rk[3] + pad;
     int g = __float2int_rn((float)bsum * a.inv_n_sub);
-    int xl = -1, cl = 0, xh = 255, ch = cap;
-    bool ok = false;
+    // the two ranks of the pair are resolved separately (their values may lie far apart); the bracket belongs to the rank kt
+    // that is still open: (xl, cl) the largest value known to have #{x <= xl} <= kt, (xh, ch) the smallest with #{x <= xh} > kt
+    int kt = kp1, xl = -1, cl = 0, xh = 255, ch = cap;
+    bool have1 = false, have2 = false;
     mlo = mhi = 0;
 #pragma unroll 1
-    for (int it = 0; it < 4; it++) {
-        int v1, v2, p0, cn[4];
+    for (int it = 0; it < kMaxWindows; it++) {
+        int w1, w2, p0, cn[4];
         uint32_t fm;
-        const bool okw = band_window<W4, 1, 5>(x, g, kp1, kp2, cap, v1, v2, true, fm, p0, cn);
-        if (!ok && okw) { mlo = v1; mhi = v2; ok = true; }
-        if (!__any_sync(0xffffffffu, !ok)) return true;
+        band_window<W4, 1, 5>(x, g, kp1, kp2, cap, w1, w2, true, fm, p0, cn);
+        const bool lo_end = p0 == 0, hi_end = p0 == 256 - 5;  // the ends of the byte range count as known
+        if (!have1 && (cn[0] <= kp1 || lo_end) && (kp1 < cn[3] || hi_end)) {
+            mlo = w1; have1 = true;
+            if (kp2 != kp1 && !have2) { kt = kp2; xh = 255; ch = cap; }  // (xl, cl) stays valid for the larger rank
+        }
+        if (!have2 && (cn[0] <= kp2 || lo_end) && (kp2 < cn[3] || hi_end)) { mhi = w2; have2 = true; }
+        const bool open = !(have1 && have2);
+        if (!__any_sync(0xffffffffu, open)) return true;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            if (cn[k] <= kp1 && p0 + k > xl) { xl = p0 + k; cl = cn[k]; }
+            if (cn[k] <= kt && p0 + k > xl) { xl = p0 + k; cl = cn[k]; }
 #pragma unroll
         for (int k = 3; k >= 0; k--)
-            if (cn[k] > kp2 && p0 + k < xh) { xh = p0 + k; ch = cn[k]; }
+            if (cn[k] > kt && p0 + k < xh) { xh = p0 + k; ch = cn[k]; }
         int g2;
         if (it == 0) {
             const int gc = p0 + 2, nj = cn[2];  // F(gc) = fm, #{x <= gc} = nj, F(gc + 1) = F(gc) + 2 nj - cap
@@ -1405,16 +1404,18 @@ __device__ __forceinline__ bool band_solve_windows(const uint32_t (&x)[W4], uint
             const int step = __float2int_rn((float)far * 3.5f * fside * a.inv_n_sub * a.inv_n_sub);
             const int dside = up ? side - gc : gc - side;
             g2 = (4 * step < dside) ? (up ? gc + step : gc - step) : side;
+        } else if (it >= 3 && (it & 1)) {
+            g2 = (xl + xh + 1) >> 1;  // a plain bisection now and then bounds the walk along a flat stretch of the counts
         } else {
-            g2 = xl + __float2int_rn(__fdividef((float)(kp1 + 1 - cl) * (float)(xh - xl), (float)max(ch - cl, 1)));
+            g2 = xl + __float2int_rn(__fdividef((float)(kt + 1 - cl) * (float)(xh - xl), (float)max(ch - cl, 1)));
         }
-        // p0 = g - 2 in [xl, xh - 3]: count 0 of the window is then a known "<= kp1" count (or the range end), count 3 a known
-        // "> kp2" one once the bracket is narrow; an unresolved lane's bracket shrinks by at least three values per window
+        // p0 = g - 2 in [xl, xh - 3]: count 0 of the window is then a known "<= kt" count (or the range end), count 3 a known
+        // "> kt" one once the bracket is narrow; an open bracket shrinks by at least three values per window
         const int g_lo = xl + 2, g_hi = max(xl + 2, xh - 1);
         g2 = g2 < g_lo ? g_lo : (g2 > g_hi ? g_hi : g2);
-        if (!ok) g = g2;
+        if (open) g = g2;
     }
-    return !__any_sync(0xffffffffu, !ok);
+    return !__any_sync(0xffffffffu, !(have1 && have2));
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -1440,7 +1441,7 @@ __device__ __forceinline__ bool band_solve_windows(const uint32_t (&x)[W4], uint
 #define CHB_HARD_MINB 2
 #endif
 #ifndef CHB_EXACT_MINB
-#define CHB_EXACT_MINB 3
+#define CHB_EXACT_MINB 4
 #endif
 constexpr int kWarpsPerCta = CHB_WARPS;
 constexpr int kQueueCap = 64;  // per warp
