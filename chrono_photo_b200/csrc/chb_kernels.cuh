@@ -2217,6 +2217,9 @@ __global__ void __launch_bounds__(256) compact_hard_kernel(uint32_t* __restrict_
 // scratch (VABSDIFF4 F evaluations) at the start of a block and, after the iterative solver, for pixels whose order
 // statistics left the counted values. Per (window, band) results are parked in shared memory. Phase 2 goes window by
 // window: certificate, background pixel, or the exact-path queue (exact_pixel, 32 queued pixel-windows at a time).
+#ifndef CHB_VIDEO_MINB
+#define CHB_VIDEO_MINB 3
+#endif
 constexpr int kVideoWarps = 4;
 constexpr int kVideoQueueCap = 64;
 constexpr int kVideoBlock = 16;  // window starts per task
@@ -2551,7 +2554,7 @@ __device__ __forceinline__ void video_phase2(const VideoArgs& v, const uint32_t*
 // Result word 0 of a (window, band): bits 0-8 mlo + mhi (twice the median), 9-16 max |x - centre|, 17-24 the byte of
 // window position 0. Word 1 (when present): bits 0-13 band sum, 14-23 4 * IQR.
 template <int C, int NW>
-__global__ void __launch_bounds__(kVideoWarps * 32, 4) video_kernel(const __grid_constant__ VideoArgs v) {
+__global__ void __launch_bounds__(kVideoWarps * 32, CHB_VIDEO_MINB) video_kernel(const __grid_constant__ VideoArgs v) {
     constexpr int KG = (NW + 3) / 4 + 1;  // frame groups a block of 16 starts spans
     constexpr int NWL = 4 * KG;           // words per lane
     constexpr int kThreads = kVideoWarps * 32;
