@@ -17,8 +17,12 @@ for n, c in ((25, 3), (200, 3), (70, 4), (300, 3)):
             cp.OutlierProcessor(thr, bg, om, seed=3).process(fs)
             cp.OutlierProcessor(thr, bg, om, seed=3).process(fs, list(range(1, n - 1, 2)))
     cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2, sample_count=max(3, n // 3)).process(fs)
-    if n >= 70:  # chrono-video run (video_kernel + video_exact_kernel): 20 windows of 9 frames
+    if n >= 70:  # chrono-video runs (video_kernel + video_exact_kernel): 20 windows of 9 frames, 37 of 25 (relative thresholds too)
         cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 0, 2).process_video_run(fs, 3, 9, 20)
+        cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 1, 4, seed=3).process_video_run(fs, 5, 25, 37)
+        cp.OutlierProcessor(cp.Threshold.rel(3.0, 5.0), 2, 3).process_video_run(fs, 0, 24, 18)
+    # an interleaved row-block shard (blocks of 2 rows, 3 ranks): global pixel indices for the per-pixel draws
+    cp.OutlierProcessor(cp.Threshold.abs(0.05, 0.2), 1, 2, seed=3, pixel_offset=2 * 70, block_pixels=2 * 70, block_skip=4 * 70).process(fs)
     cp.SimpleProcessor(darker=True).process(fs)
     cp.SimpleProcessor((1, 0.5, 0.25, 0), cp.Fade(0, False, [(0, 1.0), (9, 0.0)]), False).process(fs, list(range(0, n, 3)))
     fs.close()
