@@ -846,6 +846,10 @@ __device__ __forceinline__ void dense_masks_int(const OutlierArgs& a, const uint
         const int s = sg + 15 - (int)(gq - 19u * qv);
         maxkey = max(maxkey, ((4u * qv + (uint32_t)im.k2) << 12) | (uint32_t)(4095 - s));
     }
+    // the D - 1 copies issued past the window's last group are still in flight: they must have landed before this thread's next
+    // pass starts writing the same ring slots (compute-sanitizer racecheck: write-after-write between two passes that follow
+    // each other closely, e.g. the iterative tier's last warp-full and the first batch of the streaming kernel's queue)
+    cp_async_wait_all();
     k_out = k;
     maxkey_out = maxkey;
 }
