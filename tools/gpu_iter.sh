@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 iteration run: tests, smoke, default bench line, shard timings (contiguous / interleaved, with and without the
-# exact-path launch), one ncu capture of video_kernel.   bash tools/gpu_r2s.sh [tag]
+# exact-path launch), one ncu capture of video_kernel.   bash tools/gpu_iter.sh [tag]
 TAG=${1:-r2s}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT

@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick iteration: tests, a1 / c3 / c4 / c5 kernel-only bench lines, two shard timings.   bash tools/gpu_r2w.sh [tag]
+# quick iteration: tests, a1 / c3 / c4 / c5 kernel-only bench lines, two shard timings.   bash tools/gpu_iter_quick.sh [tag]
 TAG=${1:-r2w}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
