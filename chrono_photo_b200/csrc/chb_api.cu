@@ -111,7 +111,9 @@ struct CallBuf {
     QueueEntry* d_queue = nullptr;        // exact-path queue of an outlier launch + its counters ([0..1] exact, [2..3] iterative tier)
     long long* d_hqueue = nullptr;        // iterative-tier queue (pixel indices)
     uint32_t* d_hflags = nullptr;         // per-tile flag words the iterative-tier queue is built from
-    unsigned int* d_qcount = nullptr;
+    unsigned int* d_qcount = nullptr;     // two sets of 16 words (queue counters + the call's four 64-bit counters), then the flag words
+    int qset = 0;                         // the set the NEXT call uses; it is all zero (the previous call's compaction kernel cleared it)
+    int last_qset = 0;                    // the set the last call used (its counters are fetched from there)
 };
 
 struct Band {
@@ -152,6 +154,7 @@ struct CallSlot {
     unsigned long long* h_counters = nullptr;  // [n_bands * 4]
     int last_kind = 0;  // what ran last on the slot: 0 nothing yet, 1 a single-window call (its planes can be fetched), 2 a video run
     bool last_has_mask = false;
+    bool counters_pending = false;  // the last enqueued call left its counters on the devices: collect_outlier fetches them
     uint64_t last_warnings = 0;
     std::vector<uint8_t> last_tables;  // fingerprint of the per-call tables currently on the devices
 };
@@ -960,14 +963,22 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
             // one allocation: words 0..7 the two queue counters, words 8..15 the call's four 64-bit counters, then the per-tile
             // flag words. The flag words are zeroed once here -- compact_hard_kernel clears every word it consumes -- so a call
             // starts with ONE 64-byte memset.
-            CU(cudaMalloc(&cb.d_qcount, sizeof(uint32_t) * (16 + (size_t)b.n_tiles)));
-            CU(cudaMemsetAsync(cb.d_qcount, 0, sizeof(uint32_t) * (16 + (size_t)b.n_tiles), s));
-            cb.d_hflags = cb.d_qcount + 16;
+            CU(cudaMalloc(&cb.d_qcount, sizeof(uint32_t) * (32 + (size_t)b.n_tiles)));
+            CU(cudaMemsetAsync(cb.d_qcount, 0, sizeof(uint32_t) * (32 + (size_t)b.n_tiles), s));
+            cb.d_hflags = cb.d_qcount + 32;
+            cb.qset = 0;
         }
-        CU(cudaMemsetAsync(cb.d_qcount, 0, sizeof(uint32_t) * 16, s));
+        // The call's counters: two sets used alternately. The set of this call is zero already -- compact_hard_kernel of the
+        // previous call cleared it -- so a call starts without a memset (one stream operation less between back-to-back calls);
+        // only the launches without a compaction kernel (series beyond the register-resident variants) clear both sets here.
+        if (long_series) CU(cudaMemsetAsync(cb.d_qcount, 0, sizeof(uint32_t) * 32, s));
+        unsigned int* const qc = cb.d_qcount + 16 * cb.qset;
+        unsigned int* const qc_other = cb.d_qcount + 16 * (cb.qset ^ 1);
+        cb.last_qset = cb.qset;
+        cb.qset ^= 1;
         OutlierArgs ab = a;
-        ab.gq = cb.d_queue; ab.gq_count = cb.d_qcount;
-        ab.ghq = cb.d_hqueue; ab.ghq_count = cb.d_qcount + 1;
+        ab.gq = cb.d_queue; ab.gq_count = qc;
+        ab.ghq = cb.d_hqueue; ab.ghq_count = qc + 1;
         ab.hflags = cb.d_hflags;
         ab.stack = b.d_stack;
         ab.n_pixels = b.n_pixels; ab.n_tiles = b.n_tiles;
@@ -977,7 +988,7 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
         ab.block_pixels = prm->block_pixels; ab.block_skip = prm->block_skip;
         ab.out_image = cb.d_out;
         ab.out_mask = want_mask ? cb.d_mask : nullptr;
-        ab.counters = reinterpret_cast<unsigned long long*>(cb.d_qcount + 8);
+        ab.counters = reinterpret_cast<unsigned long long*>(qc + 8);
         if (dbg) {
             if (dbg->median && !cb.d_dbg_median) CU(cudaMalloc(&cb.d_dbg_median, sizeof(float) * 4 * (size_t)b.n_pixels));
             if (dbg->q1 && !cb.d_dbg_q1) CU(cudaMalloc(&cb.d_dbg_q1, sizeof(float) * 4 * (size_t)b.n_pixels));
@@ -1006,7 +1017,7 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
             g_launches += 2;
             CU(cudaGetLastError());
             CU(cudaEventRecord(cb.ev1, s));
-            CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, cb.d_qcount + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, qc + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
             continue;
         }
         int occ = 1;
@@ -1023,7 +1034,7 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
         // iterative tier: long whole-stack series with relative thresholds (six ranks per band) use the histogram kernel -- one
         // shared-memory atomic per sample instead of the solver's repeated passes (measured on 1000 x UHD: 1.0 ms against
         // 1.7 ms; with absolute thresholds, two ranks, the solver's 0.6 ms wins). CHB_HIST=0 / 1 forces the choice (tests).
-        compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(cb.d_hflags, b.n_tiles, cb.d_hqueue, cb.d_qcount + 1);
+        compact_hard_kernel<<<std::min<long long>(d.sm_count * 4, (b.n_tiles + 1023) / 1024), 256, 0, s>>>(cb.d_hflags, b.n_tiles, cb.d_hqueue, qc + 1, qc_other);
         bool use_hist = kmode == 2 && n >= 256;
         if (g_tune.hist.load() >= 0) use_hist = kmode != 0 && n >= 256 && g_tune.hist.load() != 0;
         // with the dense per-frame pass in the iterative tier's kernel (every uncertified pixel of its warp-fulls finished in place)
@@ -1054,8 +1065,12 @@ static int outlier_impl(chb_stack* st, int slot, const chb_outlier_params* prm, 
         g_launches += ab.hard_drains_all ? 3 : 4;
         CU(cudaGetLastError());
         CU(cudaEventRecord(cb.ev1, s));
-        CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, cb.d_qcount + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
+        // (a call that is only enqueued leaves its counters on the device: whoever waits for it fetches them, and a run of
+        // back-to-back calls has one stream operation less between the last kernel of a call and the first of the next)
+        if (!(enqueue_only && tables_cached))
+            CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, qc + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
     }
+    cs.counters_pending = enqueue_only && tables_cached;
     (void)P;
     if (!tables_cached) cs.last_tables = blob;
     cs.last_kind = 1;
@@ -1075,6 +1090,9 @@ static int collect_outlier(chb_stack* st, int slot, const chb_debug_planes* dbg,
         Dev& d = st->ctx->devs[b.dev_slot];
         CallBuf& cb = b.call[slot];
         CU(cudaSetDevice(d.id));
+        if (cs.counters_pending)
+            CU(cudaMemcpyAsync(cs.h_counters + 4 * b.dev_slot, cb.d_qcount + 16 * cb.last_qset + 8, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost,
+                               call_stream(d, cb, slot)));
         CU(cudaStreamSynchronize(call_stream(d, cb, slot)));
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, cb.ev0, cb.ev1));
@@ -1096,6 +1114,7 @@ static int collect_outlier(chb_stack* st, int slot, const chb_debug_planes* dbg,
         }
     }
     if (kernel_ms) *kernel_ms = ms_max;
+    cs.counters_pending = false;
     cs.last_has_mask = want_mask;
     cs.last_warnings = warnings;
     g_last_slow = slow;

@@ -2162,13 +2162,16 @@ __global__ void __launch_bounds__(256, CHB_EXACT_MINB) outlier_exact_kernel(cons
 // consecutive tiles and writes their flagged pixels in tile order (blocks land in the order of their atomicAdd), so entries
 // that are neighbours in the queue are neighbours in the image.
 // The flag words are cleared as they are read, so the next call finds them zero without a per-call memset of the whole array.
+// It also clears the counter set the NEXT call on this slot will use (the host alternates between two sets), so that a call
+// starts without a memset.
 __global__ void __launch_bounds__(256) compact_hard_kernel(uint32_t* __restrict__ flags, long long n_tiles, long long* __restrict__ ghq,
-                                                           unsigned int* __restrict__ ghq_count) {
+                                                           unsigned int* __restrict__ ghq_count, unsigned int* __restrict__ next_set) {
     constexpr int kTilesPerThread = 4;
     __shared__ uint32_t warp_tot[8];
     __shared__ uint32_t block_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long n_chunks = (n_tiles + 256 * kTilesPerThread - 1) / (256 * kTilesPerThread);
+    if (blockIdx.x == 0 && threadIdx.x < 16) next_set[threadIdx.x] = 0u;
     for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const long long t0 = (chunk * 256 + threadIdx.x) * kTilesPerThread;
         uint32_t f[kTilesPerThread];
