@@ -398,6 +398,21 @@ struct ColumnReader {
             }
         }
     }
+    // makes frame group g the current one (its units in u[])
+    __device__ __forceinline__ void enter_group(int g) {
+        if (g != cur_g) {
+            cur_g = g;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c < C) u[c] = __ldg(reinterpret_cast<const uint4*>(base + c * band_stride + (long long)g * (kTilePixels * kUnitBytes)));
+        }
+    }
+    // word q (a compile-time constant) of the current group, every band
+    template <int Q>
+    __device__ __forceinline__ void group_word(uint32_t (&xw)[4]) const {
+#pragma unroll
+        for (int c = 0; c < 4; c++) xw[c] = (c < C) ? (Q == 0 ? u[c].x : (Q == 1 ? u[c].y : (Q == 2 ? u[c].z : u[c].w))) : 0u;
+    }
     // the 4-frame word (frames frame .. frame+3, frame a multiple of 4) of every band
     __device__ __forceinline__ void fetch_word(int frame, uint32_t (&xw)[4]) {
         const int g = frame >> 4;
@@ -419,6 +434,10 @@ struct ColumnReader {
 // frames at once; words without a flagged frame are skipped. Flags: bit 7 of byte k <=> frame k may be an outlier.
 struct WordScan {
     uint32_t cc[4], kadd[4];
+    // "certainly an outlier": a deviation from the band's centre from which this band ALONE reaches the threshold -- every
+    // other band's term is non-negative when no weight is negative, and f32 rounding is monotone, so the reference's sum
+    // does too (checked below with the reference's own f32 operations). kadd_hi: 128 - that deviation; m_hi: 0 = test off.
+    uint32_t kadd_hi[4], m_hi[4];
     bool use[4];
     bool all;  // caps are useless (tiny threshold, NaN): every frame is evaluated
 };
@@ -431,12 +450,25 @@ __device__ __forceinline__ void make_word_scan(const OutlierArgs& a, const float
         nb += ws.use[i] ? 1 : 0;
     }
     ws.all = false;
+    bool no_negative = a.thr_sq > 0.0f;  // (false for NaN as well)
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (i < a.C) no_negative = no_negative && (a.w[i] == 0.0f || a.w[i] > 0.0f);
     const float share = nb > 0 ? sqrtf(a.thr_sq * 0.9999f / (float)nb) : 0.0f;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        ws.cc[i] = 0; ws.kadd[i] = 0;
+        ws.cc[i] = 0; ws.kadd[i] = 0; ws.kadd_hi[i] = 0; ws.m_hi[i] = 0;
         if (ws.use[i]) {
-            const float fac = fabsf(a.absolute ? a.w[i] : a.w[i] * iqr_inv[i]);
+            const float facs = a.absolute ? a.w[i] : a.w[i] * iqr_inv[i];  // the factor of src/chrono.rs:265-278, as make_dist_ctx forms it
+            if (no_negative) {
+                const float need = sqrtf(a.thr_sq) / facs + 0.5f;  // |x - centre| >= need => |median - x| >= need - 1/2 => (fac * diff)^2 >= thr^2
+                const int ch = (need == need && need > 0.0f && need < 125.0f) ? (int)ceilf(need) + 1 : 128;
+                if (ch <= 127) {
+                    const float t = facs * ((float)ch - 0.5f);
+                    if (t * t >= a.thr_sq) { ws.kadd_hi[i] = rep4(128 - ch); ws.m_hi[i] = 0x80808080u; }
+                }
+            }
+            const float fac = fabsf(facs);
             const int center = (int)median[i];  // floor: medians are >= 0
             const float halfw = median[i] - (float)center;
             const float capf = share / fac - halfw - 1e-3f;
@@ -460,6 +492,21 @@ __device__ __forceinline__ uint32_t may_exceed(const WordScan& ws, const uint32_
         }
     }
     return ex & 0x80808080u;
+}
+// Same, plus the frames that certainly are outliers (flags in `sure`, a subset of the returned flags)
+__device__ __forceinline__ uint32_t may_exceed_sure(const WordScan& ws, const uint32_t (&xw)[4], uint32_t& sure) {
+    sure = 0;
+    if (ws.all) return 0x80808080u;
+    uint32_t ex = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (ws.use[i]) {
+            const uint32_t d = absdiff4(xw[i], ws.cc[i]), lo7 = d & 0x7f7f7f7fu;
+            ex |= d | (lo7 + ws.kadd[i]);
+            sure |= (d | (lo7 + ws.kadd_hi[i])) & ws.m_hi[i];  // bit 7: d >= 128, or low 7 bits at or above the band's own reach
+        }
+    }
+    return (ex | sure) & 0x80808080u;
 }
 
 struct DistCtx {  // per-band constants of the distance (src/chrono.rs:265-278)
@@ -1026,6 +1073,7 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
     float out_sum[4] = {0, 0, 0, 0};
     uint8_t px[4] = {0, 0, 0, 0};
     const bool need_avg = a.om == 3 || a.bg == 2;
+    const bool class_only = (a.om == 4 || a.om == 5) && !need_avg && !a.int_dist;  // (uniform) see the word loop of pass 1
     auto visit = [&](int s, float d) {  // one frame of the window, in order
         if (d >= thr_sq) {
             if (k == 0) { first_idx = s; first_d = d; }
@@ -1040,6 +1088,27 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         } else if (first_non < 0) {
             first_non = s;
         }
+    };
+    // forward / backward chains without an average: pass 1 only has to CLASSIFY the frames (the chain walk computes the distances
+    // it needs itself). Frames whose deviation in one band alone reaches the threshold are outliers without a distance
+    // evaluation -- the frames an object dwells on --, the other candidates get the reference's f32 distance as before; counts
+    // and first / last positions come off the flag word of the four frames.
+    auto classify_word = [&](const uint32_t (&xw)[4], int s, uint32_t ex, uint32_t sure) {
+        uint32_t out4 = sure, unc = ex & ~sure;
+        while (unc) {
+            const int bit = __ffs(unc) - 1;  // 8 kk + 7
+            unc &= unc - 1u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) px[i] = (uint8_t)((xw[i] >> (bit - 7)) & 0xffu);
+            if (dist_sq_px(dc, px) >= thr_sq) out4 |= 1u << bit;
+        }
+        if (out4) {
+            if (k == 0) first_idx = s + ((__ffs(out4) - 1) >> 3);
+            last_idx = s + ((31 - __clz(out4)) >> 3);
+            k += __popc(out4);
+        }
+        const uint32_t non4 = ~out4 & 0x80808080u;
+        if (first_non < 0 && non4) first_non = s + ((__ffs(non4) - 1) >> 3);
     };
     if (DENSE && a.int_dist && contig_f0 >= 0 && n <= 4096) {  // (the pass packs window positions into 12 bits)
         // every frame classified by the branch-free integer pass; the per-policy values are read off its summary
@@ -1082,10 +1151,35 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         int s = 0;
         while (s < n) {
             const int f = contig_f0 + s;
+            if ((f & 15) == 0 && s + 16 <= n) {
+                // a whole frame group inside the window: its four words tested with compile-time word selects; a group without
+                // a candidate -- the frames before and after an object's visit -- is passed in one step
+                rd.enter_group(f >> 4);
+                uint32_t any, xg[4];
+                rd.template group_word<0>(xg); any = may_exceed(ws, xg);
+                rd.template group_word<1>(xg); any |= may_exceed(ws, xg);
+                rd.template group_word<2>(xg); any |= may_exceed(ws, xg);
+                rd.template group_word<3>(xg); any |= may_exceed(ws, xg);
+                if (any == 0) {
+                    if (first_non < 0) first_non = s;
+                    s += 16;
+                    continue;
+                }
+                if (class_only) {  // the group's four words classified in place
+                    uint32_t sure, ex;
+                    rd.template group_word<0>(xg); ex = may_exceed_sure(ws, xg, sure); if (ex) classify_word(xg, s, ex, sure); else if (first_non < 0) first_non = s;
+                    rd.template group_word<1>(xg); ex = may_exceed_sure(ws, xg, sure); if (ex) classify_word(xg, s + 4, ex, sure); else if (first_non < 0) first_non = s + 4;
+                    rd.template group_word<2>(xg); ex = may_exceed_sure(ws, xg, sure); if (ex) classify_word(xg, s + 8, ex, sure); else if (first_non < 0) first_non = s + 8;
+                    rd.template group_word<3>(xg); ex = may_exceed_sure(ws, xg, sure); if (ex) classify_word(xg, s + 12, ex, sure); else if (first_non < 0) first_non = s + 12;
+                    s += 16;
+                    continue;
+                }
+            }
             if ((f & 3) == 0 && s + 4 <= n) {
                 uint32_t xw[4];
                 rd.fetch_word(f, xw);
-                const uint32_t ex = may_exceed(ws, xw);
+                uint32_t sure = 0;
+                const uint32_t ex = class_only ? may_exceed_sure(ws, xw, sure) : may_exceed(ws, xw);
                 if (ex == 0) {
                     if (first_non < 0) first_non = s;
                 } else if (a.int_dist) {  // the word's four distances as integers
@@ -1101,6 +1195,8 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
                             first_non = s + kk;
                         }
                     }
+                } else if (class_only) {
+                    classify_word(xw, s, ex, sure);
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) {
@@ -1187,6 +1283,10 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
 
     uint8_t sample[4] = {0, 0, 0, 0};
     if (k == 1) {  // src/chrono.rs:379-388
+        if (class_only) {  // the classification-only pass did not keep the distance of the single outlier
+            rd.fetch(frame_at(first_idx), px);
+            first_d = dist_sq_px(dc, px);
+        }
         const int f = frame_at(first_idx);
 #pragma unroll
         for (int i = 0; i < 4; i++)
