@@ -1149,11 +1149,13 @@ __device__ __forceinline__ uint8_t exact_pixel(const OutlierArgs& a, const Pixel
         first_non = dp.first_non == 0x7fffffff ? -1 : dp.first_non;
     } else if (contig_f0 >= 0) {  // contiguous window: position s is frame contig_f0 + s; aligned words are pre-tested four frames at a time
         int s = 0;
+        const bool long_window = n >= 64;
         while (s < n) {
             const int f = contig_f0 + s;
-            if ((f & 15) == 0 && s + 16 <= n) {
+            if (long_window && (f & 15) == 0 && s + 16 <= n) {
                 // a whole frame group inside the window: its four words tested with compile-time word selects; a group without
-                // a candidate -- the frames before and after an object's visit -- is passed in one step
+                // a candidate -- the frames before and after an object's visit -- is passed in one step (short windows, e.g.
+                // the chrono-video queue's, hold one or two whole groups: the extra test measured 1 % slower there)
                 rd.enter_group(f >> 4);
                 uint32_t any, xg[4];
                 rd.template group_word<0>(xg); any = may_exceed(ws, xg);

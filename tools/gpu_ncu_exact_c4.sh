@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=${1:-r2aa}
+TAG=${1:-ncu_exact_c4}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
