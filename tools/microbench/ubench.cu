@@ -63,6 +63,23 @@ __global__ void __launch_bounds__(512, 1) k(uint32_t* out, long long* cyc, uint3
             } else if (OP == 16) {  // mix: LOP3 + IMAD (alu + fma pipes)
                 if (i & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(c));
                 else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(c));
+            } else if (OP == 18) {  // mix: VABSDIFF4.ACC + VIMNMX.U16x2 (does the packed min share the half-rate ALU pipe?)
+                if (i & 1) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c));
+                else a[i] = __vminu2(a[i], b[i]);
+            } else if (OP == 19) {  // mix: VIMNMX.U16x2 + IMAD
+                if (i & 1) a[i] = __vminu2(a[i], b[i]);
+                else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(c));
+            } else if (OP == 20) {  // mix: 1 VABSDIFF4.ACC : 3 VIMNMX.U16x2
+                if ((i & 3) == 0) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c));
+                else a[i] = __vminu2(a[i], b[i]);
+            } else if (OP == 21) {  // SHF (funnel shift)
+                a[i] = __funnelshift_l(a[i], b[i], 7);
+            } else if (OP == 22) {  // mix: IADD3 + VABSDIFF4.ACC
+                if (i & 1) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(c));
+                else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
+            } else if (OP == 23) {  // mix: VIMNMX.U16x2 + IADD3
+                if (i & 1) a[i] = __vminu2(a[i], b[i]);
+                else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));
             } else if (OP == 17) {  // I2F u8 
                 float f; asm volatile("cvt.rn.f32.u8 %0, %1;" : "=f"(f) : "r"(a[i] & 0xff)); a[i] = __float_as_uint(f) + b[i];
             }
@@ -133,6 +150,12 @@ int main() {
     run<9>("mix IDP4A+LOP3", 1, out, cyc);
     run<14>("mix VABSDIFF4.ACC+IMAD", 1, out, cyc);
     run<16>("mix LOP3+IMAD", 1, out, cyc);
+    run<21>("SHF.L (funnel)", 1, out, cyc);
+    run<18>("mix VABSDIFF4.ACC+VIMNMX.U16x2", 1, out, cyc);
+    run<20>("mix 1 VABSDIFF4.ACC : 3 VIMNMX", 1, out, cyc);
+    run<19>("mix VIMNMX.U16x2+IMAD", 1, out, cyc);
+    run<22>("mix VABSDIFF4.ACC+IADD3", 1, out, cyc);
+    run<23>("mix VIMNMX.U16x2+IADD3", 1, out, cyc);
     // bandwidth
     size_t bytes = (size_t)8 << 30; uint4* buf; CK(cudaMalloc(&buf, bytes)); CK(cudaMemset(buf, 1, bytes));
     for (int occ = 1; occ <= 8; occ *= 2) {
