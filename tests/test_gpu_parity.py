@@ -1,6 +1,8 @@
 """GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against the CPU oracle on the
 same seeded inputs. Bit-exact everywhere (composite, mask, medians, quartiles, outlier counts, darker/lighter), which is
 stricter than the +-1 LSB north_star allows for blended bytes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -773,7 +775,8 @@ def test_concurrent_callers_overlap_on_call_slots(ctx):
     fs.close()
 
 
-@pytest.mark.parametrize("seed", range(48))
+# CHB_FUZZ_CASES / CHB_FUZZ_BASE: a longer soak of the same walk (tools/gpu_soak.sh ran 3000 cases on the round-2 build)
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CHB_FUZZ_BASE", "0")), int(os.environ.get("CHB_FUZZ_BASE", "0")) + int(os.environ.get("CHB_FUZZ_CASES", "48"))))
 def test_random_option_fuzz_against_oracle(ctx, seed):
     # seeded random walk through the option space: frame count, channels, data regime, threshold kind and size, policies,
     # weights, fades, windows, --sample; every case bit-compared with the oracle (composite, mask, medians, counts)

@@ -1,0 +1,6 @@
+#!/bin/bash
+# soak: the seeded option-space fuzz of tests/test_gpu_parity.py over many more cases than the suite runs (bit-exact against the oracle)
+OUT=gpurun_out/${1:-soak}
+mkdir -p $OUT
+CHB_FUZZ_BASE=${2:-1000} CHB_FUZZ_CASES=${3:-3000} timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "random_option_fuzz" -p no:cacheprovider > $OUT/soak.txt 2>&1
+tail -5 $OUT/soak.txt
