@@ -408,13 +408,20 @@ extern "C" size_t chb_stack_device_bytes(const chb_stack* st, int dev_slot) {
 static int kernel_config(const void* kern, int device, int threads, int smem, int* occ_out) {
     static std::mutex mu;
     static std::map<std::tuple<const void*, int, int>, int> cache;
+    static std::map<std::pair<const void*, int>, int> max_smem;  // the attribute is per function: it is only ever raised (a
+                                                                 // kernel launched with two sizes -- the chrono-video kernel with one
+                                                                 // or two result words -- must keep the larger limit)
     std::lock_guard<std::mutex> lk(mu);
     auto key = std::make_tuple(kern, device, smem);
     auto it = cache.find(key);
     if (it == cache.end()) {
         int occ = 1;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int& cur = max_smem[std::make_pair(kern, device)];
+        if (smem > cur || cur == 0) {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, cur)));
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            cur = std::max(smem, cur);
+        }
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         it = cache.emplace(key, std::max(1, occ)).first;
     }

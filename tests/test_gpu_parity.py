@@ -558,6 +558,49 @@ def test_video_run_policies(ctx, bg, om):
     fs.close()
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CHB_FUZZ_BASE", "0")), int(os.environ.get("CHB_FUZZ_BASE", "0")) + int(os.environ.get("CHB_VIDEO_FUZZ_CASES", "24"))))
+def test_video_run_fuzz_against_oracle(ctx, seed):
+    # seeded walk through the chrono-video option space: clip length, window length, run position and length (whole blocks of
+    # 16 starts and ragged ends), channels, data regime, threshold kind, policies, weights, fades; every window of the run
+    # bit-compared with the oracle's single-window result
+    rng = np.random.default_rng(50_000 + seed)
+    wl = int(rng.choice([1, 2, 3, 4, 7, 8, 12, 15, 16, 17, 24, 25, 31, 32, 33, 40, 47, 63, 64]))
+    n = wl + int(rng.integers(1, 60))
+    c = int(rng.choice([3, 3, 4]))
+    h, w = int(rng.integers(2, 7)), int(rng.integers(5, 70))
+    regime = rng.integers(0, 4)
+    if regime == 0:
+        st = make_stack(rng, n, h, w, c, noise=int(rng.integers(0, 12)), n_obj=int(rng.integers(0, 40)))
+    elif regime == 1:
+        st = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    elif regime == 2:
+        st = rng.choice(np.array([0, 255, 3, 252], np.uint8), size=(n, h, w, c))
+    else:
+        base = rng.integers(0, 256, size=(1, h, w, c))
+        st = np.clip(base + np.rint(rng.normal(0, rng.uniform(0.5, 9), size=(n, h, w, c))), 0, 255).astype(np.uint8)
+    absolute = bool(rng.integers(0, 2)) or wl < 3
+    if absolute:
+        mn = float(rng.choice([0.0, 0.01, 0.05, 0.1, 0.3]))
+        spec = (True, mn, mn + float(rng.choice([0.0, 0.05, 0.15, 0.5])))
+    else:
+        mn = float(rng.choice([0.5, 1.0, 3.0, 6.0]))
+        spec = (False, mn, mn + float(rng.choice([0.0, 1.0, 2.0])))
+    first = int(rng.integers(0, n - wl + 1))
+    count = int(rng.integers(1, n - wl - first + 2))
+    weights = tuple(float(x) for x in rng.choice([1.0, 1.0, 1.0, 0.0, 0.5, 2.0], size=4))
+    if not any(weights[:c]):
+        weights = (1.0,) + weights[1:]
+    fade = None
+    if rng.integers(0, 3) == 0:
+        f0 = int(rng.integers(-3, 5))
+        fade = (int(rng.integers(0, 2)), bool(rng.integers(0, 2)), [(f0, float(rng.uniform(-0.2, 1.3))), (f0 + int(rng.integers(1, 12)), float(rng.uniform(-0.2, 1.3)))])
+    bg = str(rng.choice(["first", "random", "average", "median"]))
+    om = str(rng.choice(["first", "last", "extreme", "average", "forward", "backward"]))
+    fs = upload(ctx, st)
+    _check_video_run(ctx, fs, st, first, wl, count, spec, bg, om, weights=weights, fade=fade, seed=int(rng.integers(0, 1000)))
+    fs.close()
+
+
 def test_video_run_adversarial_series(ctx):
     rng = np.random.default_rng(99)
     n, H, W = 70, 8, 64
