@@ -951,3 +951,57 @@ def test_interleaved_row_block_shards_match_the_whole_image(ctx):
     for f in range(5):
         assert np.array_equal(part.download(f), whole.download(f)[sh.global_rows()])
     whole.close(); part.close(); fs.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CHB_FUZZ_BASE", "0")), int(os.environ.get("CHB_FUZZ_BASE", "0")) + int(os.environ.get("CHB_SEQ_FUZZ_CASES", "6"))))
+def test_call_sequences_on_one_stack(ctx, seed):
+    """Mixed call sequences on ONE stack: blocking calls, runs of enqueued calls followed by one wait (their counters stay on
+    the device until then; the call's counter sets alternate), chrono-video runs and darker / lighter in between, with the
+    parameters -- hence the cached per-call tables -- changing or not. Images, masks AND warning counts against the oracle."""
+    rng = np.random.default_rng(70_000 + seed)
+    n, h, w = int(rng.choice([12, 40, 70, 200])), int(rng.integers(3, 8)), int(rng.integers(20, 90))
+    st = make_stack(rng, n, h, w, 3, noise=int(rng.integers(0, 9)), n_obj=int(rng.integers(5, 40)))
+    if rng.integers(0, 3) == 0:
+        st[:, :, : w // 3] = rng.integers(0, 256, size=(n, h, w // 3, 3), dtype=np.uint8)  # a stripe of iid bytes: iterative tier, all-outlier warnings
+    fs = upload(ctx, st)
+
+    def random_proc():
+        absolute = bool(rng.integers(0, 3))
+        spec = (True, float(rng.choice([0.0, 0.02, 0.05, 0.2])), 0.3) if absolute else (False, float(rng.choice([1.0, 3.0])), 5.0)
+        bg, om = str(rng.choice(["first", "random", "average", "median"])), str(rng.choice(["first", "last", "extreme", "average", "forward", "backward"]))
+        idx = None
+        if n >= 8 and rng.integers(0, 2):
+            a0 = int(rng.integers(0, n // 2))
+            idx = list(range(a0, int(rng.integers(a0 + 3, n + 1))))
+        t_gpu, t_orc = thr_pair(spec)
+        sd = int(rng.integers(0, 99))
+        return cp.OutlierProcessor(t_gpu, BG[bg], OM[om], seed=sd), (t_orc, BG[bg], OM[om], sd), idx
+
+    for _ in range(12):
+        kind = rng.integers(0, 5)
+        proc, (t_orc, bg, om, sd), idx = random_proc()
+        oimg, omsk, owarn = orc.outlier(st, t_orc, bg, om, indices=idx, seed=sd)
+        if kind == 0:  # blocking call
+            img, msk = proc.process(fs, idx)
+            assert np.array_equal(img, oimg) and np.array_equal(msk, omsk) and proc.warnings == owarn
+        elif kind == 1:  # device-side call + fetch
+            proc.process_device(fs, idx)
+            img, msk, warn = cp.fetch_last(fs, want_mask=True)
+            assert np.array_equal(img, oimg) and np.array_equal(msk, omsk) and warn == owarn
+        elif kind == 2:  # a run of enqueued calls (same parameters: the tables are cached after the first), one wait
+            for _ in range(int(rng.integers(1, 5))):
+                proc.enqueue_device(fs, idx)
+            _, warn = fs.wait()
+            img, msk, warn2 = cp.fetch_last(fs, want_mask=True)
+            assert np.array_equal(img, oimg) and np.array_equal(msk, omsk) and warn == owarn and warn2 == owarn
+        elif kind == 3 and n >= 30:  # a chrono-video run in between
+            wl, first, count = int(rng.integers(3, 26)), int(rng.integers(0, 4)), int(rng.integers(1, 20))
+            count = min(count, n - wl - first + 1)
+            imgs, masks, warns = proc.process_video_run(fs, first, wl, count)
+            for k in range(count):
+                vi, vm, vw = orc.outlier(st, t_orc, bg, om, indices=list(range(first + k, first + k + wl)), seed=sd)
+                assert np.array_equal(imgs[k], vi) and np.array_equal(masks[k], vm) and warns[k] == vw
+        else:
+            darker = bool(rng.integers(0, 2))
+            assert np.array_equal(cp.SimpleProcessor(darker=darker).process(fs), orc.simple(st, darker))
+    fs.close()
