@@ -1005,3 +1005,35 @@ def test_call_sequences_on_one_stack(ctx, seed):
             darker = bool(rng.integers(0, 2))
             assert np.array_equal(cp.SimpleProcessor(darker=darker).process(fs), orc.simple(st, darker))
     fs.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CHB_FUZZ_BASE", "0")), int(os.environ.get("CHB_FUZZ_BASE", "0")) + int(os.environ.get("CHB_SIMPLE_FUZZ_CASES", "24"))))
+def test_simple_fuzz_against_oracle(ctx, seed):
+    # darker / lighter over a seeded walk: frame count (one launch chunk and several), channels, data with many ties, weights
+    # (the integer kernel for 0 / 1, the f32 kernel otherwise), fades (running blend), contiguous and stepped windows
+    rng = np.random.default_rng(90_000 + seed)
+    n = int(rng.choice([1, 2, 3, 15, 16, 17, 63, 64, 65, 100, 200, 257]))
+    c = int(rng.choice([3, 4]))
+    h, w = int(rng.integers(2, 8)), int(rng.integers(5, 90))
+    regime = rng.integers(0, 3)
+    if regime == 0:
+        st = make_stack(rng, n, h, w, c, noise=int(rng.integers(0, 12)), n_obj=int(rng.integers(0, 30)))
+    elif regime == 1:
+        st = rng.integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    else:
+        st = rng.choice(np.array([0, 255, 3, 252, 128], np.uint8), size=(n, h, w, c))  # ties everywhere: the first extreme must win
+    weights = tuple(float(x) for x in rng.choice([1.0, 1.0, 1.0, 0.0, 0.5, 2.0, -1.0], size=4)) if rng.integers(0, 2) else (1.0, 1.0, 1.0, float(rng.integers(0, 2)))
+    fade = None
+    if rng.integers(0, 3) == 0:
+        f0 = int(rng.integers(-3, 5))
+        fade = (int(rng.integers(0, 2)), bool(rng.integers(0, 2)), [(f0, float(rng.uniform(-0.2, 1.3))), (f0 + int(rng.integers(1, 12)), float(rng.uniform(-0.2, 1.3)))])
+    idx = None
+    if n >= 4 and rng.integers(0, 2):
+        a0 = int(rng.integers(0, n // 2))
+        idx = list(range(a0, int(rng.integers(a0 + 1, n + 1)), int(rng.choice([1, 1, 2, 3]))))
+    darker = bool(rng.integers(0, 2))
+    fs = upload(ctx, st)
+    got = cp.SimpleProcessor(weights, cp.Fade(*fade) if fade else None, darker).process(fs, idx)
+    want = orc.simple(st, darker, weights, orc.fade(*fade) if fade else None, idx)
+    assert np.array_equal(got, want), (n, c, weights, fade, idx, darker)
+    fs.close()

@@ -8,3 +8,5 @@ CHB_FUZZ_BASE=${2:-1000} CHB_VIDEO_FUZZ_CASES=${4:-1500} timeout 1500 python -m 
 tail -5 $OUT/soak_video.txt
 CHB_FUZZ_BASE=${2:-1000} CHB_SEQ_FUZZ_CASES=${5:-300} timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "call_sequences" -p no:cacheprovider > $OUT/soak_seq.txt 2>&1
 tail -5 $OUT/soak_seq.txt
+CHB_FUZZ_BASE=${2:-1000} CHB_SIMPLE_FUZZ_CASES=${6:-3000} timeout 1500 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "simple_fuzz" -p no:cacheprovider > $OUT/soak_simple.txt 2>&1
+tail -5 $OUT/soak_simple.txt
