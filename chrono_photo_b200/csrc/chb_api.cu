@@ -1134,6 +1134,10 @@ static int fetch_impl(chb_stack* st, int slot, uint8_t* out_image, uint8_t* out_
     CallSlot& cs = st->slots[slot];
     if (cs.last_kind != 1) return fail(CHB_ERR_STATE, "chb_fetch_last: %s", cs.last_kind == 2 ? "the last call was a video run (its planes went to the caller's buffers)" : "no call has run on this stack yet");
     if (out_mask && !cs.last_has_mask) return fail(CHB_ERR_STATE, "chb_fetch_last: the last call did not produce a mask");
+    if (cs.counters_pending) {  // the last call was only enqueued: its counters (the warning count) are still on the devices
+        int rc = collect_outlier(st, slot, nullptr, nullptr, cs.last_has_mask);
+        if (rc) return rc;
+    }
     for (Band& b : st->bands) {
         Dev& d = st->ctx->devs[b.dev_slot];
         CallBuf& cb = b.call[slot];

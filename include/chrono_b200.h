@@ -181,7 +181,8 @@ int chb_fetch_last(chb_stack *stack, uint8_t *out_image, uint8_t *out_mask, uint
 int chb_fetch_last_device(chb_stack *stack, int dev_slot, void *d_image, void *d_mask);
 /* Back-to-back launches without a host round trip per call: chb_outlier_enqueue only launches (it waits by itself when
  * the window / sample / fade tables differ from the previous call's), chb_stack_wait waits for everything enqueued and
- * returns the device time of the last launch and its warning count. */
+ * returns the device time of the last launch and its warning count (an enqueued call leaves its counters on the device;
+ * chb_stack_wait and chb_fetch_last fetch them). */
 int chb_outlier_enqueue(chb_stack *stack, const chb_outlier_params *params, const int32_t *indices, int n_indices, int want_mask);
 int chb_stack_wait(chb_stack *stack, float *last_kernel_ms, uint64_t *n_warnings);
 
